@@ -1,0 +1,145 @@
+/* surfcascade.h -- C-ABI of the B200-native SURF-cascade detection path.
+ *
+ * The reference (mrgloom/SurfCascade) has no plugin/FFI layer: its boundary is the C++ class surface
+ * DenseSURFFeatureExtractor / CascadeClassifier / Model plus the detect loop inlined in main().  This header
+ * is the thin C layer those (kept) C++ classes call; every entry point names the reference code it replaces
+ * (paths relative to /root/reference/ObjDetector).  Plain pointers and sizes only; no exceptions cross it.
+ *
+ * Conventions: every function returns 0 on success or a negative sc_status; sc_last_error() returns a
+ * human-readable reason for the last failure on that handle.  A handle owns one CUDA device, one stream and
+ * all device buffers; it is thread-compatible (one thread at a time), not thread-safe.  Host buffers belong to
+ * the caller.  There is NO CPU fallback: sc_create fails when no CUDA device is usable.
+ */
+#ifndef SURFCASCADE_H
+#define SURFCASCADE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SC_DIM 32         /* descriptor length: 4 cells x 8 bins (DenseSURFFeatureExtractor.h:32-33,48) */
+#define SC_MAX_STAGES 16  /* reference trains at most 10 (CascadeClassifier/CascadeClassifier.h:20) */
+#define SC_MAX_SCALES 64
+
+typedef enum {
+    SC_OK = 0,
+    SC_ERR_INVALID = -1,   /* bad argument */
+    SC_ERR_CUDA = -2,      /* CUDA runtime failure (message in sc_last_error) */
+    SC_ERR_STATE = -3,     /* call order: no cascade / no integral yet */
+    SC_ERR_CAPACITY = -4,  /* output buffer too small; *n holds the required count */
+    SC_ERR_IO = -5,        /* model file unreadable or malformed */
+    SC_ERR_NOMEM = -6
+} sc_status;
+
+typedef struct sc_handle sc_handle;
+
+typedef struct { int32_t x, y, w, h; } sc_rect;   /* cv::Rect */
+
+/* Flattened cascade: what the detect loop reads out of a loaded model.  Replaces the object graph built by
+ * Model::Load (Model.cpp:97-193) + CascadeClassifier::GetFittedPatchIndexes (CascadeClassifier/CascadeClassifier.cpp:83-91)
+ * + the dense_patches[patch_index] lookup at ObjDetector.cpp:108-130. */
+typedef struct {
+    int32_t tmpl;            /* model template side; 40 at ObjDetector.cpp:112 */
+    int32_t n_stages;
+    const float* theta;      /* [n_stages]   StageClassifier::theta (StageClassifier.h:24) */
+    const int32_t* n_weak;   /* [n_stages]   weak classifiers per stage */
+    const sc_rect* rects;    /* [sum n_weak] template rect of each weak classifier's patch */
+    const float* w;          /* [sum n_weak][33] LogisticRegression::w, already float32 (Model.cpp:172-175) */
+    const double* bias;      /* [sum n_weak] liblinear model bias (Model.cpp:169) */
+} sc_cascade_desc;
+
+/* Scan parameters; the reference hard-codes all of them (SURVEY.md section 5 "Config / flags"). */
+typedef struct {
+    int32_t base;              /* base window side: literal 70 at ObjDetector.cpp:104,174,180; BASELINE uses 40 */
+    int32_t step;              /* 0 -> base > 20 ? base / 20 : 1 (ObjDetector.cpp:139) */
+    double scale;              /* 1.1 (ObjDetector.cpp:174,180) */
+    int32_t prefilter;         /* 6 (ObjDetector.cpp:188); negative disables the prefilter */
+    int32_t skip_rule;         /* 1 -> reproduce the adaptive x stride `multi` (ObjDetector.cpp:186,214-217) */
+    int32_t force_all_stages;  /* 1 -> no early reject: every stage of every window (stress mode, not in the reference) */
+} sc_detect_params;
+
+/* One raw (ungrouped) detection: wins.push_back(win) / scores.push_back(score), ObjDetector.cpp:207-208. */
+typedef struct {
+    int32_t frame, x, y, l;
+    double score;              /* (last stage score + n_stages + 1) / n_stages, ObjDetector.cpp:201 */
+} sc_detection;
+
+/* Per-frame work counters (same definitions as the oracle's). */
+typedef struct {
+    int64_t grid;              /* window origins on the step lattice, all scales */
+    int64_t visited;           /* windows the reference's adaptive stride actually evaluates */
+    int64_t prefilter_pass;    /* visited windows passing sum(win) > area*6 */
+    int64_t weak_evals;        /* weak-classifier evaluations the reference performs on visited windows */
+    int64_t raw;               /* raw detections */
+    int64_t evaluated;         /* grid windows this implementation evaluated (>= visited) */
+    int64_t reach[SC_MAX_STAGES]; /* visited windows reaching stage s */
+} sc_counters;
+
+/* ---- lifetime ------------------------------------------------------------------------------------- */
+int sc_create(int device, sc_handle** out);
+void sc_destroy(sc_handle* h);
+const char* sc_last_error(const sc_handle* h);
+const char* sc_version(void);
+
+/* ---- model ---------------------------------------------------------------------------------------- */
+/* Replaces ObjDetector.cpp:108-130 (pool + Model::Load + fitted patches), given an already flattened cascade. */
+int sc_set_cascade(sc_handle* h, const sc_cascade_desc* desc);
+/* Model::Load (Model.cpp:97-193) on a libconfig model.cfg, ExtractPatches (DenseSURFFeatureExtractor.cpp:49-63) on a
+ * tmpl x tmpl template, flatten and upload. */
+int sc_load_model(sc_handle* h, const char* model_cfg_path, int tmpl);
+/* Template pool: ExtractPatches. Returns the pool size (608 for tmpl 40); fills at most cap rects. */
+int sc_pool_patches(int tmpl, sc_rect* out, int cap);
+/* ProjectPatches (DenseSURFFeatureExtractor.cpp:486-508) for window side l at origin (0,0). */
+int sc_project_patches(int tmpl, int l, const sc_rect* patches, int n, sc_rect* out);
+
+/* ---- feature extraction (parity hooks and training-side extraction) ---------------------------------- */
+/* DenseSURFFeatureExtractor::IntegralImage (DenseSURFFeatureExtractor.cpp:65-87, T2bFilter :199-349): gray u8
+ * H x W (row stride in bytes) -> the (H+1) x (W+1) x 8 float32 interleaved integral, kept on the device for the
+ * calls below and, when out is non-null, copied to the host. */
+int sc_integral(sc_handle* h, const uint8_t* gray, int W, int H, int stride, float* out);
+/* DenseSURFFeatureExtractor::CalcFeature (+GetRectsFromPatch, Normalize; :360-457) on the current integral. */
+int sc_features(sc_handle* h, const sc_rect* rects, int n, float* out /* [n][32] */);
+/* DenseSURFFeatureExtractor::sum (:351-358). */
+int sc_window_sum(sc_handle* h, const sc_rect* rects, int n, float* out /* [n] */);
+/* GentleAdaboost::Predict2 (GentleAdaboost.cpp:247-261) of every stage on explicit windows {x,y,l} of the
+ * current integral, no early exit: out[n][n_stages]. */
+int sc_stage_scores(sc_handle* h, const int32_t* wins /* [n][3] */, int n, float* out);
+
+/* LogisticRegression::Predict (CascadeClassifier/LogisticRegression.cpp:46-68) for n independent
+ * (weights, descriptor) pairs held in host memory: w [n][33], bias [n], x [n][32] -> out [n]. */
+int sc_weak_predict(sc_handle* h, const float* w, const double* bias, const float* x, int n, float* out);
+/* GentleAdaboost::Predict2 (GentleAdaboost.cpp:247-261) on explicit descriptors: the n pairs are one stage's
+ * weak classifiers in order; *out = float32 running sum of their probabilities / n. */
+int sc_stage_predict(sc_handle* h, const float* w, const double* bias, const float* x, int n, float* out);
+
+/* ---- detection -------------------------------------------------------------------------------------- */
+/* The detect path of ObjDetector.cpp:165,174-219 on a batch of equally sized gray frames held in HOST memory:
+ * upload, integral, scan, adaptive-stride replay, download.  Detections are sorted by (frame, l, y, x).
+ * counters may be null or point at nframes entries. */
+int sc_detect(sc_handle* h, const uint8_t* const* frames, int nframes, int W, int H, int stride,
+              const sc_detect_params* params, sc_detection* out, size_t cap, size_t* n, sc_counters* counters);
+/* Same work on frames already resident in DEVICE memory (d_frames: nframes x H x W contiguous u8), detections
+ * left on the device, unsorted, in d_out (cap entries) with the count in *d_n (uint32).  Asynchronous on the
+ * handle's stream; sc_sync waits.  counters (host, nframes entries or null) are valid after sc_sync. */
+int sc_detect_device(sc_handle* h, const uint8_t* d_frames, int nframes, int W, int H,
+                     const sc_detect_params* params, sc_detection* d_out, size_t cap, uint32_t* d_n);
+int sc_sync(sc_handle* h);
+/* Counters of the last sc_detect_device batch (after sc_sync). */
+int sc_last_counters(sc_handle* h, sc_counters* counters, int nframes);
+/* cudaStream_t of the handle, for callers that time or order work with CUDA events. */
+void* sc_stream(sc_handle* h);
+/* Number of kernel launches issued by this handle so far. */
+int64_t sc_launch_count(const sc_handle* h);
+
+/* ---- host-side grouping (next row N1) ------------------------------------------------------------------ */
+/* cv::groupRectangles(wins, weights = 0.., scores, groupThreshold, eps) as called at ObjDetector.cpp:224-225. */
+int sc_group_rectangles(const sc_rect* rects, const double* scores, int n, int group_threshold, double eps,
+                        sc_rect* out_rects, double* out_scores, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

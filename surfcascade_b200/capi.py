@@ -1,0 +1,249 @@
+"""ctypes binding to the C-ABI of libsurfcascade_b200.so (include/surfcascade.h).
+
+Python is plumbing here (tests, bench.py, torch device memory / streams / torch.distributed); the product is the
+shared library.  There is no fallback: a missing library or a missing GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsurfcascade_b200.so")
+SC_MAX_STAGES = 16
+
+SC_OK, SC_ERR_INVALID, SC_ERR_CUDA, SC_ERR_STATE, SC_ERR_CAPACITY, SC_ERR_IO, SC_ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6
+
+
+class Rect(C.Structure):
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("w", C.c_int32), ("h", C.c_int32)]
+
+
+class CascadeDesc(C.Structure):
+    _fields_ = [("tmpl", C.c_int32), ("n_stages", C.c_int32), ("theta", C.POINTER(C.c_float)), ("n_weak", C.POINTER(C.c_int32)),
+                ("rects", C.POINTER(Rect)), ("w", C.POINTER(C.c_float)), ("bias", C.POINTER(C.c_double))]
+
+
+class DetectParams(C.Structure):
+    _fields_ = [("base", C.c_int32), ("step", C.c_int32), ("scale", C.c_double), ("prefilter", C.c_int32), ("skip_rule", C.c_int32),
+                ("force_all_stages", C.c_int32)]
+
+
+class Counters(C.Structure):
+    _fields_ = [("grid", C.c_int64), ("visited", C.c_int64), ("prefilter_pass", C.c_int64), ("weak_evals", C.c_int64), ("raw", C.c_int64),
+                ("evaluated", C.c_int64), ("reach", C.c_int64 * SC_MAX_STAGES)]
+
+
+DETECTION_DTYPE = np.dtype([("frame", "<i4"), ("x", "<i4"), ("y", "<i4"), ("l", "<i4"), ("score", "<f8")])
+assert DETECTION_DTYPE.itemsize == 24
+
+EXPORTS = ["sc_create", "sc_destroy", "sc_last_error", "sc_version", "sc_set_cascade", "sc_load_model", "sc_pool_patches", "sc_project_patches",
+           "sc_integral", "sc_features", "sc_window_sum", "sc_stage_scores", "sc_weak_predict", "sc_stage_predict", "sc_detect",
+           "sc_detect_device", "sc_sync", "sc_last_counters", "sc_stream", "sc_launch_count", "sc_group_rectangles"]
+
+_lib = None
+
+
+class SurfCascadeError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"surfcascade error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    """Load the shared library; raises if it has not been built (python -m surfcascade_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(f"{LIB_PATH} not built: run `python surfcascade_b200/build.py` (needs nvcc). No CPU fallback exists.")
+        L = C.CDLL(LIB_PATH)
+        L.sc_last_error.restype = C.c_char_p
+        L.sc_version.restype = C.c_char_p
+        L.sc_stream.restype = C.c_void_p
+        L.sc_launch_count.restype = C.c_int64
+        L.sc_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.sc_destroy.argtypes = [C.c_void_p]
+        L.sc_last_error.argtypes = [C.c_void_p]
+        L.sc_stream.argtypes = [C.c_void_p]
+        L.sc_launch_count.argtypes = [C.c_void_p]
+        L.sc_set_cascade.argtypes = [C.c_void_p, C.POINTER(CascadeDesc)]
+        L.sc_load_model.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.sc_pool_patches.argtypes = [C.c_int, C.c_void_p, C.c_int]
+        L.sc_project_patches.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.sc_integral.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.sc_features.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.sc_window_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.sc_stage_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.sc_weak_predict.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.sc_stage_predict.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.sc_detect.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(DetectParams), C.c_void_p,
+                                C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p]
+        L.sc_detect_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(DetectParams), C.c_void_p, C.c_size_t, C.c_void_p]
+        L.sc_sync.argtypes = [C.c_void_p]
+        L.sc_last_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.sc_group_rectangles.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int]
+        _lib = L
+    return _lib
+
+
+def params(base=40, step=0, scale=1.1, prefilter=6, skip_rule=True, force_all_stages=False) -> DetectParams:
+    """Defaults are BASELINE config 1/2: base 40 -> step 2, scale 1.1, prefilter 6, adaptive stride on."""
+    return DetectParams(base, step, scale, prefilter, int(skip_rule), int(force_all_stages))
+
+
+def counters_to_dict(c: Counters, n_stages: int) -> dict:
+    return {"grid": c.grid, "visited": c.visited, "prefilter_pass": c.prefilter_pass, "weak_evals": c.weak_evals, "raw": c.raw,
+            "evaluated": c.evaluated, "reach": [c.reach[i] for i in range(n_stages)]}
+
+
+def pool_patches(tmpl: int = 40) -> np.ndarray:
+    out = np.zeros((4096, 4), np.int32)
+    n = lib().sc_pool_patches(tmpl, out.ctypes.data, 4096)
+    return out[:n].copy()
+
+
+def project_patches(tmpl: int, l: int, patches) -> np.ndarray:
+    p = np.ascontiguousarray(patches, np.int32).reshape(-1, 4)
+    out = np.zeros_like(p)
+    rc = lib().sc_project_patches(tmpl, l, p.ctypes.data, len(p), out.ctypes.data)
+    if rc != SC_OK:
+        raise SurfCascadeError(rc, "sc_project_patches")
+    return out
+
+
+def group_rectangles(rects, scores, thr: int = 2, eps: float = 0.2):
+    r = np.ascontiguousarray(rects, np.int32).reshape(-1, 4)
+    s = np.ascontiguousarray(scores, np.float64)
+    n = len(r)
+    out_r = np.zeros((max(n, 1), 4), np.int32)
+    out_s = np.zeros(max(n, 1), np.float64)
+    m = lib().sc_group_rectangles(r.ctypes.data, s.ctypes.data, n, thr, eps, out_r.ctypes.data, out_s.ctypes.data, max(n, 1))
+    if m < 0:
+        raise SurfCascadeError(m, "sc_group_rectangles")
+    return out_r[:m].copy(), out_s[:m].copy()
+
+
+class Handle:
+    """One sc_handle: a CUDA device, a stream and its device buffers."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        rc = lib().sc_create(device, C.byref(self._h))
+        if rc != SC_OK:
+            raise SurfCascadeError(rc, "sc_create failed: no usable CUDA device (this library has no CPU path)")
+        self.device = device
+        self.n_stages = 0
+
+    def close(self):
+        if self._h:
+            lib().sc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != SC_OK:
+            raise SurfCascadeError(rc, lib().sc_last_error(self._h).decode())
+
+    @property
+    def stream(self) -> int:
+        return int(lib().sc_stream(self._h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().sc_launch_count(self._h))
+
+    # ---- model ----
+    def load_model(self, path: str, tmpl: int = 40):
+        self._check(lib().sc_load_model(self._h, path.encode(), tmpl))
+        self.n_stages = -1
+
+    def set_cascade(self, tmpl: int, theta, n_weak, rects, w, bias):
+        theta = np.ascontiguousarray(theta, np.float32); n_weak = np.ascontiguousarray(n_weak, np.int32)
+        rects = np.ascontiguousarray(rects, np.int32).reshape(-1, 4); w = np.ascontiguousarray(w, np.float32).reshape(-1, 33)
+        bias = np.ascontiguousarray(bias, np.float64)
+        d = CascadeDesc(tmpl, len(theta), theta.ctypes.data_as(C.POINTER(C.c_float)), n_weak.ctypes.data_as(C.POINTER(C.c_int32)),
+                        C.cast(rects.ctypes.data, C.POINTER(Rect)), w.ctypes.data_as(C.POINTER(C.c_float)), bias.ctypes.data_as(C.POINTER(C.c_double)))
+        self._check(lib().sc_set_cascade(self._h, C.byref(d)))
+        self.n_stages = len(theta)
+
+    # ---- parity hooks ----
+    def integral(self, img: np.ndarray, want_output: bool = True):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        out = np.empty((h + 1, w + 1, 8), np.float32) if want_output else None
+        self._check(lib().sc_integral(self._h, img.ctypes.data, w, h, w, out.ctypes.data if want_output else None))
+        return out
+
+    def features(self, rects) -> np.ndarray:
+        r = np.ascontiguousarray(rects, np.int32).reshape(-1, 4)
+        out = np.zeros((len(r), 32), np.float32)
+        self._check(lib().sc_features(self._h, r.ctypes.data, len(r), out.ctypes.data))
+        return out
+
+    def window_sum(self, rects) -> np.ndarray:
+        r = np.ascontiguousarray(rects, np.int32).reshape(-1, 4)
+        out = np.zeros(len(r), np.float32)
+        self._check(lib().sc_window_sum(self._h, r.ctypes.data, len(r), out.ctypes.data))
+        return out
+
+    def stage_scores(self, wins, n_stages: int) -> np.ndarray:
+        w = np.ascontiguousarray(wins, np.int32).reshape(-1, 3)
+        out = np.zeros((len(w), n_stages), np.float32)
+        self._check(lib().sc_stage_scores(self._h, w.ctypes.data, len(w), out.ctypes.data))
+        return out
+
+    def weak_predict(self, w, bias, x) -> np.ndarray:
+        w = np.ascontiguousarray(w, np.float32).reshape(-1, 33); x = np.ascontiguousarray(x, np.float32).reshape(-1, 32)
+        bias = np.ascontiguousarray(bias, np.float64).reshape(-1)
+        out = np.zeros(len(w), np.float32)
+        self._check(lib().sc_weak_predict(self._h, w.ctypes.data, bias.ctypes.data, x.ctypes.data, len(w), out.ctypes.data))
+        return out
+
+    def stage_predict(self, w, bias, x) -> float:
+        w = np.ascontiguousarray(w, np.float32).reshape(-1, 33); x = np.ascontiguousarray(x, np.float32).reshape(-1, 32)
+        bias = np.ascontiguousarray(bias, np.float64).reshape(-1)
+        out = np.zeros(1, np.float32)
+        self._check(lib().sc_stage_predict(self._h, w.ctypes.data, bias.ctypes.data, x.ctypes.data, len(w), out.ctypes.data))
+        return float(out[0])
+
+    # ---- detection ----
+    def detect(self, frames, prm: DetectParams | None = None, cap: int = 1 << 20):
+        """Host frames (list of HxW u8 arrays, or an N x H x W array; pinned or pageable) -> (detections, [Counters])."""
+        if isinstance(frames, np.ndarray) and frames.ndim == 3:
+            frames = [frames[i] for i in range(frames.shape[0])]
+        frames = [f if (f.dtype == np.uint8 and f.flags.c_contiguous) else np.ascontiguousarray(f, np.uint8) for f in frames]
+        h, w = frames[0].shape
+        n = len(frames)
+        ptrs = (C.c_void_p * n)(*[f.ctypes.data for f in frames])
+        return self.detect_ptrs(ptrs, n, w, h, w, prm, cap)
+
+    def detect_ptrs(self, ptrs, n: int, w: int, h: int, stride: int, prm: DetectParams | None = None, cap: int = 1 << 20):
+        prm = prm or params()
+        out = np.zeros(cap, DETECTION_DTYPE)
+        cnt = (Counters * n)()
+        found = C.c_size_t(0)
+        rc = lib().sc_detect(self._h, ptrs, n, w, h, stride, C.byref(prm), out.ctypes.data, cap, C.byref(found), C.byref(cnt))
+        if rc == SC_ERR_CAPACITY:
+            return self.detect_ptrs(ptrs, n, w, h, stride, prm, int(found.value) + 16)
+        self._check(rc)
+        return out[:found.value].copy(), list(cnt)
+
+    def detect_device(self, d_frames_ptr: int, n: int, w: int, h: int, d_out_ptr: int, cap: int, d_count_ptr: int, prm: DetectParams | None = None):
+        """Frames resident in device memory (n x h x w u8); asynchronous on the handle's stream."""
+        prm = prm or params()
+        self._check(lib().sc_detect_device(self._h, d_frames_ptr, n, w, h, C.byref(prm), d_out_ptr, cap, d_count_ptr))
+
+    def sync(self):
+        self._check(lib().sc_sync(self._h))
+
+    def last_counters(self, n: int):
+        cnt = (Counters * n)()
+        self._check(lib().sc_last_counters(self._h, C.byref(cnt), n))
+        return list(cnt)

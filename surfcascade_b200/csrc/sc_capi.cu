@@ -1,0 +1,610 @@
+// C-ABI of the B200-native SURF-cascade detection path (include/surfcascade.h).
+// Handle = one device, one stream, device buffers sized for a group of frames; no CPU fallback anywhere.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/surfcascade.h"
+#include "../host/sc_host.h"
+#include "sc_kernels.cuh"
+#include "sc_plan.h"
+
+static_assert(sizeof(sc_detection) == sizeof(sck::ScDetOut), "detection layout");
+static_assert(sizeof(sc_detection) == 24, "detection layout");
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct HostBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+bool same_params(const sc_detect_params& a, const sc_detect_params& b) {
+    return a.base == b.base && a.step == b.step && a.scale == b.scale && a.prefilter == b.prefilter && a.skip_rule == b.skip_rule &&
+           a.force_all_stages == b.force_all_stages;
+}
+
+}  // namespace
+
+struct sc_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int n_sms = 148;
+
+    // cascade (host copy + device weights)
+    bool have_cascade = false;
+    int tmpl = 40, n_stages = 0, total_weak = 0;
+    std::vector<float> theta;
+    std::vector<int> n_weak, weak_base;
+    std::vector<sc_rect> rects;
+    std::vector<float> w;       // [total][33]
+    std::vector<double> bias;   // [total]
+    DevBuf d_w, d_wb;
+
+    // plan (one cached entry)
+    bool have_plan = false;
+    sc_detect_params pparams{};
+    ScPlan plan{};
+    DevBuf d_plan, d_geom;
+
+    // group buffers
+    int group_frames = 0;       // frames the buffers below hold
+    uint32_t rec_cap = 0;
+    DevBuf d_img, d_carry, d_S, d_multi, d_pass, d_visited, d_rec, d_idx[2], d_small, d_counters, d_det;
+    HostBuf h_stage;
+    std::vector<sc_counters> last_counters;
+    int last_nframes = 0;
+
+    // single-frame state for the parity hooks
+    bool have_integral = false;
+    int cur_W = 0, cur_H = 0;
+};
+
+namespace {
+
+// d_small layout (uint32): [0] rec_count, [1..16] per-stage index-list counts, [17] det_count
+enum { SM_REC = 0, SM_STAGE0 = 1, SM_DET = 17, SM_WORDS = 32 };
+
+int fail(sc_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+int cuda_fail(sc_handle* h, cudaError_t e, const char* what) {
+    return fail(h, SC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define SC_CUDA(h, call)                                         \
+    do {                                                         \
+        cudaError_t e_ = (call);                                 \
+        if (e_ != cudaSuccess) return cuda_fail((h), e_, #call); \
+    } while (0)
+
+sc_detect_params default_params() {
+    sc_detect_params p;
+    p.base = 40; p.step = 0; p.scale = 1.1; p.prefilter = 6; p.skip_rule = 1; p.force_all_stages = 0;
+    return p;
+}
+
+// Scale ladder, lattice and per-(scale, weak) projected geometry.  Host arithmetic mirrors ObjDetector.cpp:139,174,180
+// and ProjectPatches / GetRectsFromPatch (DenseSURFFeatureExtractor.cpp:486-508, 360-377) operation for operation.
+int build_plan(sc_handle* h, int W, int H, const sc_detect_params& prm, std::vector<ScGeom>* geom_out) {
+    if (!h->have_cascade) return fail(h, SC_ERR_STATE, "no cascade loaded (sc_set_cascade / sc_load_model)");
+    if (W < 2 || H < 2 || prm.base < 1 || !(prm.scale > 1.0)) return fail(h, SC_ERR_INVALID, "bad frame size or scan parameters");
+    ScPlan& p = h->plan;
+    memset(&p, 0, sizeof(p));
+    p.W = W; p.H = H; p.pitch = W + 1;
+    p.step = prm.step > 0 ? prm.step : (prm.base > 20 ? prm.base / 20 : 1);
+    p.n_stages = h->n_stages; p.total_weak = h->total_weak;
+    p.use_prefilter = prm.prefilter >= 0; p.skip_rule = prm.skip_rule != 0; p.force_all = prm.force_all_stages != 0;
+    p.n_strips = (W + SC_STRIP - 1) / SC_STRIP;
+    for (int s = 0; s < h->n_stages; s++) { p.theta[s] = h->theta[s]; p.n_weak[s] = h->n_weak[s]; p.weak_base[s] = h->weak_base[s]; }
+    size_t frame_bytes = (size_t)(H + 1) * (W + 1) * 32;
+    frame_bytes = (frame_bytes + 255) / 256 * 256;
+    p.frame_stride4 = (long long)(frame_bytes / 16);
+
+    std::vector<int> sides;
+    sc_host::scale_ladder(W, H, prm.base, prm.scale, &sides);
+    if ((int)sides.size() > SC_PLAN_MAX_SCALES) return fail(h, SC_ERR_INVALID, "too many scales (max 64)");
+    int nsc = 0, blocks = 0, words = 0, rows = 0;
+    long long windows = 0;
+    for (size_t i = 0; i < sides.size(); i++) {
+        const int l = sides[i];
+        if (l > W || l > H) continue;
+        ScScale& s = p.sc[nsc];
+        s.l = l;
+        s.nx = (W - l) / p.step + 1; s.ny = (H - l) / p.step + 1;
+        if (s.nx > 65535 || s.ny > 65535) return fail(h, SC_ERR_INVALID, "lattice exceeds 65535 positions per axis");
+        s.wpr = (s.nx + 31) / 32;
+        s.thr = (float)(l * l * (prm.prefilter >= 0 ? prm.prefilter : 0));
+        s.tiles_x = (s.nx + SC_TILE_X - 1) / SC_TILE_X;
+        const int tiles_y = (s.ny + SC_TILE_Y - 1) / SC_TILE_Y;
+        s.block_base = blocks; s.word_base = words; s.row_base = rows;
+        blocks += s.tiles_x * tiles_y; words += s.wpr * s.ny; rows += s.ny;
+        windows += (long long)s.nx * s.ny;
+        nsc++;
+    }
+    p.n_scales = nsc; p.blocks_per_frame = blocks; p.words_per_frame = words; p.rows_per_frame = rows; p.windows_per_frame = windows;
+
+    geom_out->assign((size_t)std::max(nsc, 1) * h->total_weak, ScGeom{0, 0, 0, 0});
+    for (int i = 0; i < nsc; i++)
+        for (int k = 0; k < h->total_weak; k++)
+            if (!sc_host::project_geom(h->tmpl, p.sc[i].l, h->rects[k], p.pitch, &(*geom_out)[(size_t)i * h->total_weak + k]))
+                return fail(h, SC_ERR_INVALID, "weak classifier patch is not 2x2 / 4x1 / 1x4 cells after projection");
+    return SC_OK;
+}
+
+int ensure_plan(sc_handle* h, int W, int H, const sc_detect_params& prm) {
+    if (h->have_plan && h->plan.W == W && h->plan.H == H && same_params(prm, h->pparams)) return SC_OK;
+    h->have_plan = false;
+    std::vector<ScGeom> geom;
+    int rc = build_plan(h, W, H, prm, &geom);
+    if (rc != SC_OK) return rc;
+    SC_CUDA(h, h->d_plan.ensure(sizeof(ScPlan)));
+    SC_CUDA(h, h->d_geom.ensure(std::max<size_t>(geom.size(), 1) * sizeof(ScGeom)));
+    // synchronous copies: the plan is rebuilt only when the frame size or parameters change
+    SC_CUDA(h, cudaStreamSynchronize(h->stream));
+    SC_CUDA(h, cudaMemcpy(h->d_plan.p, &h->plan, sizeof(ScPlan), cudaMemcpyHostToDevice));
+    if (!geom.empty()) SC_CUDA(h, cudaMemcpy(h->d_geom.p, geom.data(), geom.size() * sizeof(ScGeom), cudaMemcpyHostToDevice));
+    h->pparams = prm;
+    h->have_plan = true;
+    h->group_frames = 0;  // buffers are re-sized for the new plan
+    return SC_OK;
+}
+
+size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+int ensure_group_buffers(sc_handle* h, int want_frames, bool own_images) {
+    const ScPlan& p = h->plan;
+    const size_t per_rec = sizeof(ScRecord) + 2 * sizeof(uint32_t);
+    const size_t per_frame = (size_t)p.frame_stride4 * 16 + (size_t)p.windows_per_frame * per_rec + (size_t)p.words_per_frame * 12 +
+                             (size_t)p.H * p.n_strips * 32 + (size_t)p.W * p.H;
+    int g = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)6 << 30) / std::max<size_t>(per_frame, 1)));
+    g = std::min(g, std::max(want_frames, 1));
+    if (g <= h->group_frames) return SC_OK;
+    const unsigned long long recs = (unsigned long long)p.windows_per_frame * g;
+    if (recs > 0xfffffff0ull) return fail(h, SC_ERR_INVALID, "too many windows per group");
+    if (own_images) SC_CUDA(h, h->d_img.ensure(align256((size_t)g * p.W * p.H)));
+    SC_CUDA(h, h->d_carry.ensure(align256((size_t)g * p.H * p.n_strips * 32)));
+    SC_CUDA(h, h->d_S.ensure((size_t)g * p.frame_stride4 * 16));
+    SC_CUDA(h, h->d_multi.ensure(align256((size_t)g * p.words_per_frame * 4 + 4)));
+    SC_CUDA(h, h->d_pass.ensure(align256((size_t)g * p.words_per_frame * 4 + 4)));
+    SC_CUDA(h, h->d_visited.ensure(align256((size_t)g * p.words_per_frame * 4 + 4)));
+    SC_CUDA(h, h->d_rec.ensure(align256(std::max<size_t>(recs, 1) * sizeof(ScRecord))));
+    SC_CUDA(h, h->d_idx[0].ensure(align256(std::max<size_t>(recs, 1) * 4)));
+    SC_CUDA(h, h->d_idx[1].ensure(align256(std::max<size_t>(recs, 1) * 4)));
+    SC_CUDA(h, h->d_small.ensure(SM_WORDS * 4));
+    h->rec_cap = (uint32_t)recs;
+    h->group_frames = g;
+    return SC_OK;
+}
+
+// Launches the whole path for `g` frames already in d_img (device).  Detections are appended to det / det_count.
+int run_group(sc_handle* h, const uint8_t* d_img, int g, int frame0, sc_detection* d_det, uint32_t det_cap, uint32_t* d_det_count,
+              unsigned long long* d_counters) {
+    const ScPlan& p = h->plan;
+    const ScPlan* dp = h->d_plan.as<ScPlan>();
+    cudaStream_t st = h->stream;
+    uint32_t* small = h->d_small.as<uint32_t>();
+    SC_CUDA(h, cudaMemsetAsync(small, 0, (SM_DET) * 4, st));  // rec + stage counts; det count is the caller's
+    float4* S = h->d_S.as<float4>();
+    {
+        const int rows = g * p.H;
+        sck::k_strip_carry<<<(rows + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, g, h->d_carry.as<int>());
+        const int warps = g * p.n_strips;
+        sck::k_integral_walk<<<(warps + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, g, h->d_carry.as<int>(), S, p.frame_stride4);
+        h->launches += 2;
+    }
+    if (p.n_scales > 0 && p.n_stages > 0) {
+        const ScGeom* geom = h->d_geom.as<ScGeom>();
+        const float* w = h->d_w.as<float>();
+        const double* wb = h->d_wb.as<double>();
+        uint32_t* multi = h->d_multi.as<uint32_t>();
+        ScRecord* rec = h->d_rec.as<ScRecord>();
+        {
+            const size_t smem = (size_t)p.n_weak[0] * (SC_W_PITCH * 4 + 8 + sizeof(ScGeom));
+            sck::k_scan_stage0<<<g * p.blocks_per_frame, SC_TILE_THREADS, smem, st>>>(dp, S, geom, w, wb, multi, h->d_pass.as<uint32_t>(), rec,
+                                                                                         small + SM_REC, h->rec_cap);
+            h->launches++;
+        }
+        const int tail_grid = h->n_sms * 8;
+        for (int s = 1; s < p.n_stages; s++) {
+            const bool first = s == 1 || p.force_all;
+            const uint32_t* in_idx = first ? nullptr : h->d_idx[(s - 1) & 1].as<uint32_t>();
+            const uint32_t* in_cnt = first ? small + SM_REC : small + SM_STAGE0 + (s - 1);
+            const size_t smem = (size_t)p.n_weak[s] * (SC_W_PITCH * 4 + 8);
+            sck::k_scan_stage<<<tail_grid, 128, smem, st>>>(dp, s, S, geom, w, wb, multi, rec, in_idx, in_cnt, h->d_idx[s & 1].as<uint32_t>(),
+                                                             small + SM_STAGE0 + s, h->rec_cap);
+            h->launches++;
+        }
+        const int rows = g * p.rows_per_frame;
+        sck::k_replay_rows<<<(rows + 127) / 128, 128, 0, st>>>(dp, g, multi, h->d_pass.as<uint32_t>(), h->d_visited.as<uint32_t>(), d_counters);
+        sck::k_finalize<<<h->n_sms * 4, 128, 0, st>>>(dp, rec, small + SM_REC, h->rec_cap, h->d_visited.as<uint32_t>(), d_counters,
+                                                       reinterpret_cast<sck::ScDetOut*>(d_det), d_det_count, det_cap, frame0);
+        h->launches += 2;
+    }
+    SC_CUDA(h, cudaGetLastError());
+    return SC_OK;
+}
+
+void fill_counters(const sc_handle* h, const unsigned long long* raw, int nframes, sc_counters* out) {
+    const ScPlan& p = h->plan;
+    for (int f = 0; f < nframes; f++) {
+        const unsigned long long* c = raw + (size_t)f * SC_CNT_STRIDE;
+        sc_counters& o = out[f];
+        memset(&o, 0, sizeof(o));
+        o.grid = p.windows_per_frame;
+        o.evaluated = p.windows_per_frame;
+        o.visited = (int64_t)c[SC_CNT_VISITED];
+        o.prefilter_pass = (int64_t)c[SC_CNT_PREFILTER];
+        o.raw = (int64_t)c[SC_CNT_RAW];
+        o.reach[0] = o.prefilter_pass;
+        for (int s = 1; s < p.n_stages && s < SC_MAX_STAGES; s++) o.reach[s] = (int64_t)c[SC_CNT_REACH0 + s];
+        for (int s = 0; s < p.n_stages && s < SC_MAX_STAGES; s++) o.weak_evals += o.reach[s] * p.n_weak[s];
+    }
+}
+
+bool det_less(const sc_detection& a, const sc_detection& b) {
+    if (a.frame != b.frame) return a.frame < b.frame;
+    if (a.l != b.l) return a.l < b.l;
+    if (a.y != b.y) return a.y < b.y;
+    return a.x < b.x;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sc_version(void) { return "surfcascade-b200 0.1 (sm_100a)"; }
+
+int sc_create(int device, sc_handle** out) {
+    if (!out) return SC_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) return SC_ERR_CUDA;  // no CPU fallback by design
+    if (cudaSetDevice(device) != cudaSuccess) return SC_ERR_CUDA;
+    sc_handle* h = new sc_handle();
+    h->device = device;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return SC_ERR_CUDA; }
+    cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device);
+    *out = h;
+    return SC_OK;
+}
+
+void sc_destroy(sc_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    DevBuf* bufs[] = {&h->d_w, &h->d_wb, &h->d_plan, &h->d_geom, &h->d_img, &h->d_carry, &h->d_S, &h->d_multi, &h->d_pass, &h->d_visited,
+                      &h->d_rec, &h->d_idx[0], &h->d_idx[1], &h->d_small, &h->d_counters, &h->d_det};
+    for (DevBuf* b : bufs) b->release();
+    h->h_stage.release();
+    delete h;
+}
+
+const char* sc_last_error(const sc_handle* h) { return h ? h->err.c_str() : "null handle"; }
+void* sc_stream(sc_handle* h) { return h ? (void*)h->stream : nullptr; }
+int64_t sc_launch_count(const sc_handle* h) { return h ? h->launches : 0; }
+
+int sc_set_cascade(sc_handle* h, const sc_cascade_desc* d) {
+    if (!h || !d) return SC_ERR_INVALID;
+    if (d->n_stages < 1 || d->n_stages > SC_MAX_STAGES || d->tmpl < 12) return fail(h, SC_ERR_INVALID, "n_stages must be 1..16, tmpl >= 12");
+    SC_CUDA(h, cudaSetDevice(h->device));
+    int total = 0;
+    for (int s = 0; s < d->n_stages; s++) {
+        if (d->n_weak[s] < 1) return fail(h, SC_ERR_INVALID, "stage without weak classifiers");
+        total += d->n_weak[s];
+    }
+    h->tmpl = d->tmpl; h->n_stages = d->n_stages; h->total_weak = total;
+    h->theta.assign(d->theta, d->theta + d->n_stages);
+    h->n_weak.assign(d->n_weak, d->n_weak + d->n_stages);
+    h->weak_base.resize(d->n_stages);
+    for (int s = 0, b = 0; s < d->n_stages; b += d->n_weak[s], s++) h->weak_base[s] = b;
+    h->rects.assign(d->rects, d->rects + total);
+    h->w.assign(d->w, d->w + (size_t)total * 33);
+    h->bias.assign(d->bias, d->bias + total);
+    for (int k = 0; k < total; k++) {
+        const sc_rect& r = h->rects[k];
+        const bool ok = r.w > 0 && r.h > 0 && r.x >= 0 && r.y >= 0 && r.x + r.w <= d->tmpl && r.y + r.h <= d->tmpl &&
+                        (r.w == r.h || r.w == 4 * r.h || r.h == 4 * r.w);
+        if (!ok) return fail(h, SC_ERR_INVALID, "weak classifier rect outside the template or not 2x2 / 4x1 / 1x4 cells");
+    }
+    std::vector<float> w36((size_t)total * SC_W_PITCH, 0.f);
+    std::vector<double> wb(total);
+    for (int k = 0; k < total; k++) {
+        memcpy(&w36[(size_t)k * SC_W_PITCH], &h->w[(size_t)k * 33], 33 * sizeof(float));
+        wb[k] = (double)h->w[(size_t)k * 33 + 32] * h->bias[k];  // prob += w[32] * bias, LogisticRegression.cpp:64
+    }
+    SC_CUDA(h, cudaStreamSynchronize(h->stream));
+    SC_CUDA(h, h->d_w.ensure(w36.size() * sizeof(float)));
+    SC_CUDA(h, h->d_wb.ensure(wb.size() * sizeof(double)));
+    SC_CUDA(h, cudaMemcpy(h->d_w.p, w36.data(), w36.size() * sizeof(float), cudaMemcpyHostToDevice));
+    SC_CUDA(h, cudaMemcpy(h->d_wb.p, wb.data(), wb.size() * sizeof(double), cudaMemcpyHostToDevice));
+    h->have_cascade = true;
+    h->have_plan = false;
+    return SC_OK;
+}
+
+int sc_load_model(sc_handle* h, const char* path, int tmpl) {
+    if (!h || !path) return SC_ERR_INVALID;
+    sc_host::FlatCascade fc;
+    std::string why;
+    if (!sc_host::load_flat_cascade(path, tmpl, &fc, &why)) return fail(h, SC_ERR_IO, why);
+    sc_cascade_desc d;
+    d.tmpl = tmpl; d.n_stages = (int)fc.theta.size();
+    d.theta = fc.theta.data(); d.n_weak = fc.n_weak.data(); d.rects = fc.rects.data(); d.w = fc.w.data(); d.bias = fc.bias.data();
+    return sc_set_cascade(h, &d);
+}
+
+int sc_pool_patches(int tmpl, sc_rect* out, int cap) {
+    std::vector<sc_rect> pool;
+    sc_host::pool_patches(tmpl, tmpl, &pool);
+    for (int i = 0; i < (int)pool.size() && i < cap; i++) out[i] = pool[i];
+    return (int)pool.size();
+}
+
+int sc_project_patches(int tmpl, int l, const sc_rect* patches, int n, sc_rect* out) {
+    if (!patches || !out || tmpl < 1) return SC_ERR_INVALID;
+    for (int i = 0; i < n; i++) out[i] = sc_host::project_patch(tmpl, l, patches[i]);
+    return SC_OK;
+}
+
+int sc_integral(sc_handle* h, const uint8_t* gray, int W, int H, int stride, float* out) {
+    if (!h || !gray || W < 2 || H < 2 || stride < W) return fail(h, SC_ERR_INVALID, "bad image arguments");
+    SC_CUDA(h, cudaSetDevice(h->device));
+    h->have_integral = false;
+    const int n_strips = (W + SC_STRIP - 1) / SC_STRIP;
+    const size_t frame_bytes = align256((size_t)(H + 1) * (W + 1) * 32);
+    // the parity hooks share the group buffers; a plan sized for another frame is dropped
+    if (h->have_plan && (h->plan.W != W || h->plan.H != H)) { h->have_plan = false; h->group_frames = 0; }
+    SC_CUDA(h, h->d_img.ensure(align256((size_t)W * H)));
+    SC_CUDA(h, h->d_carry.ensure(align256((size_t)H * n_strips * 32)));
+    SC_CUDA(h, h->d_S.ensure(frame_bytes));
+    SC_CUDA(h, cudaMemcpy2DAsync(h->d_img.p, W, gray, stride, W, H, cudaMemcpyHostToDevice, h->stream));
+    sck::k_strip_carry<<<(H + 3) / 4, 128, 0, h->stream>>>(h->d_img.as<uint8_t>(), W, H, n_strips, 1, h->d_carry.as<int>());
+    sck::k_integral_walk<<<(n_strips + 3) / 4, 128, 0, h->stream>>>(h->d_img.as<uint8_t>(), W, H, n_strips, 1, h->d_carry.as<int>(),
+                                                                      h->d_S.as<float4>(), (long long)(frame_bytes / 16));
+    h->launches += 2;
+    SC_CUDA(h, cudaGetLastError());
+    if (out) SC_CUDA(h, cudaMemcpyAsync(out, h->d_S.p, (size_t)(H + 1) * (W + 1) * 32, cudaMemcpyDeviceToHost, h->stream));
+    SC_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->have_integral = true; h->cur_W = W; h->cur_H = H;
+    return SC_OK;
+}
+
+static int features_impl(sc_handle* h, const sc_rect* rects, int n, float* out, float* sums) {
+    if (!h || !rects || n < 0) return SC_ERR_INVALID;
+    if (!h->have_integral) return fail(h, SC_ERR_STATE, "sc_integral has not been called");
+    if (n == 0) return SC_OK;
+    SC_CUDA(h, cudaSetDevice(h->device));
+    for (int i = 0; i < n; i++) {
+        const sc_rect& r = rects[i];
+        const bool inside = r.x >= 0 && r.y >= 0 && r.w > 0 && r.h > 0 && r.x + r.w <= h->cur_W && r.y + r.h <= h->cur_H;
+        const bool cells = !out || ((r.w == r.h && r.w >= 2) || r.w == 4 * r.h || r.h == 4 * r.w);
+        if (!inside || !cells) return fail(h, SC_ERR_INVALID, "rect outside the image or not 2x2 / 4x1 / 1x4 cells");
+    }
+    DevBuf d_r, d_o, d_s;
+    SC_CUDA(h, d_r.ensure((size_t)n * sizeof(sc_rect)));
+    SC_CUDA(h, cudaMemcpyAsync(d_r.p, rects, (size_t)n * sizeof(sc_rect), cudaMemcpyHostToDevice, h->stream));
+    if (out) SC_CUDA(h, d_o.ensure((size_t)n * 32 * sizeof(float)));
+    if (sums) SC_CUDA(h, d_s.ensure((size_t)n * sizeof(float)));
+    sck::k_features<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_S.as<float4>(), h->cur_W + 1, d_r.as<int4>(), n, d_o.as<float>(), d_s.as<float>());
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && out) e = cudaMemcpyAsync(out, d_o.p, (size_t)n * 32 * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && sums) e = cudaMemcpyAsync(sums, d_s.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    d_r.release(); d_o.release(); d_s.release();
+    if (e != cudaSuccess) return cuda_fail(h, e, "sc_features");
+    return SC_OK;
+}
+
+int sc_features(sc_handle* h, const sc_rect* rects, int n, float* out) { return out ? features_impl(h, rects, n, out, nullptr) : SC_ERR_INVALID; }
+int sc_window_sum(sc_handle* h, const sc_rect* rects, int n, float* out) { return out ? features_impl(h, rects, n, nullptr, out) : SC_ERR_INVALID; }
+
+int sc_stage_scores(sc_handle* h, const int32_t* wins, int n, float* out) {
+    if (!h || !wins || !out || n < 0) return SC_ERR_INVALID;
+    if (!h->have_integral) return fail(h, SC_ERR_STATE, "sc_integral has not been called");
+    if (!h->have_cascade) return fail(h, SC_ERR_STATE, "no cascade loaded");
+    if (n == 0) return SC_OK;
+    SC_CUDA(h, cudaSetDevice(h->device));
+    const int W = h->cur_W, H = h->cur_H, tw = h->total_weak;
+    std::vector<ScGeom> geom((size_t)n * tw);
+    for (int i = 0; i < n; i++) {
+        const int x = wins[3 * i], y = wins[3 * i + 1], l = wins[3 * i + 2];
+        if (x < 0 || y < 0 || l < 1 || x + l > W || y + l > H) return fail(h, SC_ERR_INVALID, "window outside the image");
+        for (int k = 0; k < tw; k++)
+            if (!sc_host::project_geom(h->tmpl, l, h->rects[k], W + 1, &geom[(size_t)i * tw + k]))
+                return fail(h, SC_ERR_INVALID, "degenerate projected patch");
+    }
+    ScPlan mini;
+    memset(&mini, 0, sizeof(mini));
+    mini.W = W; mini.H = H; mini.pitch = W + 1; mini.n_stages = h->n_stages; mini.total_weak = tw;
+    for (int s = 0; s < h->n_stages; s++) { mini.theta[s] = h->theta[s]; mini.n_weak[s] = h->n_weak[s]; mini.weak_base[s] = h->weak_base[s]; }
+    DevBuf d_p, d_g, d_w, d_o;
+    cudaError_t e = d_p.ensure(sizeof(ScPlan));
+    if (e == cudaSuccess) e = d_g.ensure(geom.size() * sizeof(ScGeom));
+    if (e == cudaSuccess) e = d_w.ensure((size_t)n * 3 * sizeof(int));
+    if (e == cudaSuccess) e = d_o.ensure((size_t)n * h->n_stages * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_p.p, &mini, sizeof(ScPlan), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_g.p, geom.data(), geom.size() * sizeof(ScGeom), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_w.p, wins, (size_t)n * 3 * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        sck::k_stage_scores<<<(n + 63) / 64, 64, 0, h->stream>>>(d_p.as<ScPlan>(), h->d_S.as<float4>(), d_g.as<ScGeom>(), h->d_w.as<float>(),
+                                                                  h->d_wb.as<double>(), d_w.as<int>(), n, d_o.as<float>());
+        h->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_o.p, (size_t)n * h->n_stages * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    d_p.release(); d_g.release(); d_w.release(); d_o.release();
+    if (e != cudaSuccess) return cuda_fail(h, e, "sc_stage_scores");
+    return SC_OK;
+}
+
+static int predict_impl(sc_handle* h, const float* w, const double* bias, const float* x, int n, float* out, bool stage_mean) {
+    if (!h || !w || !bias || !x || !out || n < 1) return SC_ERR_INVALID;
+    if (stage_mean && n > 1024) return fail(h, SC_ERR_INVALID, "a stage holds at most 1024 weak classifiers");
+    SC_CUDA(h, cudaSetDevice(h->device));
+    std::vector<float> w36((size_t)n * SC_W_PITCH, 0.f);
+    std::vector<double> wb(n);
+    for (int i = 0; i < n; i++) {
+        memcpy(&w36[(size_t)i * SC_W_PITCH], w + (size_t)i * 33, 33 * sizeof(float));
+        wb[i] = (double)w[(size_t)i * 33 + 32] * bias[i];
+    }
+    DevBuf d_w, d_b, d_x, d_o;
+    cudaError_t e = d_w.ensure(w36.size() * 4);
+    if (e == cudaSuccess) e = d_b.ensure((size_t)n * 8);
+    if (e == cudaSuccess) e = d_x.ensure((size_t)n * 32 * 4);
+    if (e == cudaSuccess) e = d_o.ensure((size_t)(n + 1) * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_w.p, w36.data(), w36.size() * 4, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_b.p, wb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_x.p, x, (size_t)n * 32 * 4, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        if (stage_mean)
+            sck::k_weak_predict<<<1, 128, 0, h->stream>>>(d_w.as<float>(), d_b.as<double>(), d_x.as<float>(), n, d_o.as<float>(), d_o.as<float>() + n);
+        else
+            sck::k_weak_predict<<<(n + 127) / 128, 128, 0, h->stream>>>(d_w.as<float>(), d_b.as<double>(), d_x.as<float>(), n, d_o.as<float>(), nullptr);
+        h->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess)
+        e = stage_mean ? cudaMemcpyAsync(out, d_o.as<float>() + n, 4, cudaMemcpyDeviceToHost, h->stream)
+                       : cudaMemcpyAsync(out, d_o.p, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    d_w.release(); d_b.release(); d_x.release(); d_o.release();
+    if (e != cudaSuccess) return cuda_fail(h, e, "sc_weak_predict");
+    return SC_OK;
+}
+
+int sc_weak_predict(sc_handle* h, const float* w, const double* bias, const float* x, int n, float* out) {
+    return predict_impl(h, w, bias, x, n, out, false);
+}
+int sc_stage_predict(sc_handle* h, const float* w, const double* bias, const float* x, int n, float* out) {
+    return predict_impl(h, w, bias, x, n, out, true);
+}
+
+int sc_detect_device(sc_handle* h, const uint8_t* d_frames, int nframes, int W, int H, const sc_detect_params* params, sc_detection* d_out,
+                     size_t cap, uint32_t* d_n) {
+    if (!h || !d_frames || nframes < 1 || !d_out || !d_n) return fail(h, SC_ERR_INVALID, "bad arguments");
+    SC_CUDA(h, cudaSetDevice(h->device));
+    const sc_detect_params prm = params ? *params : default_params();
+    int rc = ensure_plan(h, W, H, prm);
+    if (rc != SC_OK) return rc;
+    rc = ensure_group_buffers(h, nframes, false);
+    if (rc != SC_OK) return rc;
+    h->have_integral = false;
+    SC_CUDA(h, h->d_counters.ensure((size_t)nframes * SC_CNT_STRIDE * 8));
+    SC_CUDA(h, cudaMemsetAsync(h->d_counters.p, 0, (size_t)nframes * SC_CNT_STRIDE * 8, h->stream));
+    SC_CUDA(h, cudaMemsetAsync(d_n, 0, 4, h->stream));
+    const uint32_t det_cap = (uint32_t)std::min<size_t>(cap, 0xffffffffu);
+    for (int f0 = 0; f0 < nframes; f0 += h->group_frames) {
+        const int g = std::min(h->group_frames, nframes - f0);
+        rc = run_group(h, d_frames + (size_t)f0 * W * H, g, f0, d_out, det_cap, d_n, h->d_counters.as<unsigned long long>() + (size_t)f0 * SC_CNT_STRIDE);
+        if (rc != SC_OK) return rc;
+    }
+    SC_CUDA(h, h->h_stage.ensure((size_t)nframes * SC_CNT_STRIDE * 8));
+    SC_CUDA(h, cudaMemcpyAsync(h->h_stage.p, h->d_counters.p, (size_t)nframes * SC_CNT_STRIDE * 8, cudaMemcpyDeviceToHost, h->stream));
+    h->last_nframes = nframes;
+    return SC_OK;
+}
+
+int sc_sync(sc_handle* h) {
+    if (!h) return SC_ERR_INVALID;
+    SC_CUDA(h, cudaSetDevice(h->device));
+    SC_CUDA(h, cudaStreamSynchronize(h->stream));
+    return SC_OK;
+}
+
+int sc_last_counters(sc_handle* h, sc_counters* counters, int nframes) {
+    if (!h || !counters || nframes > h->last_nframes) return SC_ERR_INVALID;
+    fill_counters(h, h->h_stage.as<unsigned long long>(), nframes, counters);
+    return SC_OK;
+}
+
+int sc_detect(sc_handle* h, const uint8_t* const* frames, int nframes, int W, int H, int stride, const sc_detect_params* params,
+              sc_detection* out, size_t cap, size_t* n, sc_counters* counters) {
+    if (!h || !frames || nframes < 1 || !n || (cap && !out) || stride < W) return fail(h, SC_ERR_INVALID, "bad arguments");
+    SC_CUDA(h, cudaSetDevice(h->device));
+    const sc_detect_params prm = params ? *params : default_params();
+    int rc = ensure_plan(h, W, H, prm);
+    if (rc != SC_OK) return rc;
+    rc = ensure_group_buffers(h, nframes, true);
+    if (rc != SC_OK) return rc;
+    if (h->d_img.cap < (size_t)h->group_frames * W * H) SC_CUDA(h, h->d_img.ensure(align256((size_t)h->group_frames * W * H)));
+    h->have_integral = false;
+    const uint32_t det_cap = (uint32_t)std::min<size_t>(std::max<size_t>(cap, 1), 0xffffffffu);
+    SC_CUDA(h, h->d_det.ensure((size_t)det_cap * sizeof(sc_detection)));
+    SC_CUDA(h, h->d_counters.ensure((size_t)nframes * SC_CNT_STRIDE * 8));
+    SC_CUDA(h, cudaMemsetAsync(h->d_counters.p, 0, (size_t)nframes * SC_CNT_STRIDE * 8, h->stream));
+    uint32_t* d_cnt = h->d_small.as<uint32_t>() + SM_DET;
+    SC_CUDA(h, cudaMemsetAsync(d_cnt, 0, 4, h->stream));
+    for (int f0 = 0; f0 < nframes; f0 += h->group_frames) {
+        const int g = std::min(h->group_frames, nframes - f0);
+        for (int k = 0; k < g; k++)
+            SC_CUDA(h, cudaMemcpy2DAsync(h->d_img.as<uint8_t>() + (size_t)k * W * H, W, frames[f0 + k], stride, W, H, cudaMemcpyHostToDevice, h->stream));
+        rc = run_group(h, h->d_img.as<uint8_t>(), g, f0, h->d_det.as<sc_detection>(), det_cap, d_cnt, h->d_counters.as<unsigned long long>() + (size_t)f0 * SC_CNT_STRIDE);
+        if (rc != SC_OK) return rc;
+    }
+    const size_t cbytes = (size_t)nframes * SC_CNT_STRIDE * 8;
+    SC_CUDA(h, h->h_stage.ensure(cbytes + 16));
+    SC_CUDA(h, cudaMemcpyAsync(h->h_stage.p, h->d_counters.p, cbytes, cudaMemcpyDeviceToHost, h->stream));
+    SC_CUDA(h, cudaMemcpyAsync(h->h_stage.as<unsigned char>() + cbytes, d_cnt, 4, cudaMemcpyDeviceToHost, h->stream));
+    SC_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->last_nframes = nframes;
+    uint32_t found = 0;
+    memcpy(&found, h->h_stage.as<unsigned char>() + cbytes, 4);
+    if (counters) fill_counters(h, h->h_stage.as<unsigned long long>(), nframes, counters);
+    *n = found;
+    if (found > cap) return fail(h, SC_ERR_CAPACITY, "detection buffer too small");
+    if (found) {
+        SC_CUDA(h, cudaMemcpy(out, h->d_det.p, (size_t)found * sizeof(sc_detection), cudaMemcpyDeviceToHost));
+        std::sort(out, out + found, det_less);
+    }
+    return SC_OK;
+}
+
+int sc_group_rectangles(const sc_rect* rects, const double* scores, int n, int group_threshold, double eps, sc_rect* out_rects,
+                        double* out_scores, int cap) {
+    if (n < 0 || (n && (!rects || !scores))) return SC_ERR_INVALID;
+    std::vector<sc_rect> r(rects, rects + n);
+    std::vector<double> s(scores, scores + n);
+    sc_host::group_rectangles(&r, &s, group_threshold, eps);
+    for (int i = 0; i < (int)r.size() && i < cap; i++) { out_rects[i] = r[i]; out_scores[i] = s[i]; }
+    return (int)r.size();
+}
+
+}  // extern "C"

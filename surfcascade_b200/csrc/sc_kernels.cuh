@@ -1,0 +1,584 @@
+// Hand-written sm_100a kernels of the SURF-cascade detection path.
+//
+//   k_strip_carry      per (frame,row): exact int32 row-prefix of the 8 gradient channels at every 32-column
+//                      strip boundary (REDUX warp sums of packed channel pairs)
+//   k_integral_walk    one warp per (frame,strip): fused gradient + channel + packed warp-shuffle row scan, then the
+//                      reference's SEQUENTIAL float32 column recurrence, writing the channel-interleaved 32 B/pixel
+//                      integral with two 16 B stores per lane (1 KB contiguous per warp per row)
+//   k_scan_stage0      64x16-window tiles: prefilter -> in-block compaction (ballot + shared prefix) -> stage 0 on
+//                      the dense survivor list -> warp-aggregated push of survivors, multi/prefilter bitmasks
+//   k_scan_stage       stages 1..N-1 on the compacted survivor index lists (ballot + atomic prefix between stages)
+//   k_replay_rows      one thread per lattice row: exact replay of the reference's adaptive x stride from the bitmask
+//   k_finalize         visited filter, detections, reference-equivalent work counters
+//
+// Arithmetic follows SURVEY.md Appendix A operation by operation: every float op is a single IEEE binary32
+// rounding (__fadd_rn/__fsub_rn/__fmul_rn are never contracted into FMA), IEEE sqrt and divide, double sigmoid.
+#ifndef SC_KERNELS_CUH
+#define SC_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "sc_plan.h"
+
+namespace sck {
+
+// ---------------------------------------------------------------------------------------------------------
+// Gradient channels (T2bFilter, DenseSURFFeatureExtractor.cpp:199-349) as four packed pairs:
+// low 16 bits = negative part (even channel), high 16 bits = positive part (odd channel).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_halfwave(int d) {
+    return (uint32_t)max(-d, 0) | ((uint32_t)max(d, 0) << 16);
+}
+
+struct Row3 { int a, b, c; };  // pixel values at xp, x, xn of one image row
+
+__device__ __forceinline__ Row3 load_row3(const uint8_t* __restrict__ row, int xp, int x, int xn) {
+    Row3 r;
+    r.a = __ldg(row + xp); r.b = __ldg(row + x); r.c = __ldg(row + xn);
+    return r;
+}
+
+__device__ __forceinline__ void channel_pairs(const Row3& prev, const Row3& cur, const Row3& next, uint32_t p[4]) {
+    p[0] = pack_halfwave(cur.c - cur.a);    // dx  :224-254
+    p[1] = pack_halfwave(next.b - prev.b);  // dy  :256-281
+    p[2] = pack_halfwave(next.c - prev.a);  // du  :283-314
+    p[3] = pack_halfwave(prev.c - next.a);  // dv  :316-347
+}
+
+// carry[frame][y][strip][8] = sum over columns left of the strip of each channel (exact, < 2^24 for W <= 65793)
+__global__ void __launch_bounds__(128) k_strip_carry(const uint8_t* __restrict__ img, int W, int H, int n_strips, int nframes,
+                                                      int* __restrict__ carry) {
+    const int lane = threadIdx.x & 31;
+    const int row_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row_id >= nframes * H) return;
+    const int f = row_id / H, y = row_id - f * H;
+    const uint8_t* base = img + (size_t)f * W * H;
+    const uint8_t* r0 = base + (size_t)max(y - 1, 0) * W;
+    const uint8_t* r1 = base + (size_t)y * W;
+    const uint8_t* r2 = base + (size_t)min(y + 1, H - 1) * W;
+    int run[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int4* out = reinterpret_cast<int4*>(carry + ((size_t)row_id * n_strips) * 8);
+    for (int s = 0; s < n_strips; s++) {
+        if (lane == 0) {
+            out[2 * s] = make_int4(run[0], run[1], run[2], run[3]);
+            out[2 * s + 1] = make_int4(run[4], run[5], run[6], run[7]);
+        }
+        const int x = s * SC_STRIP + lane;
+        uint32_t p[4] = {0, 0, 0, 0};
+        if (x < W) {
+            const int xp = max(x - 1, 0), xn = min(x + 1, W - 1);
+            channel_pairs(load_row3(r0, xp, x, xn), load_row3(r1, xp, x, xn), load_row3(r2, xp, x, xn), p);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t t = __reduce_add_sync(0xffffffffu, p[k]);  // 32 * 255 < 2^16: the halves never carry
+            run[2 * k] += (int)(t & 0xffffu);
+            run[2 * k + 1] += (int)(t >> 16);
+        }
+    }
+}
+
+// One warp per (frame, strip).  S[y+1][x+1][c] = fl32(S[y][x+1][c] + float(rowprefix)), sequential in y
+// (cv::integral u8->f32 as called at DenseSURFFeatureExtractor.cpp:75).
+__global__ void __launch_bounds__(128) k_integral_walk(const uint8_t* __restrict__ img, int W, int H, int n_strips, int nframes,
+                                                        const int* __restrict__ carry, float4* __restrict__ S,
+                                                        long long frame_stride4) {
+    const int lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wid >= nframes * n_strips) return;
+    const int f = wid / n_strips, s = wid - f * n_strips;
+    const uint8_t* base = img + (size_t)f * W * H;
+    const int x = s * SC_STRIP + lane;
+    const bool valid = x < W;
+    const int xc = min(x, W - 1), xp = max(xc - 1, 0), xn = min(xc + 1, W - 1);
+    const int pitch = W + 1;
+    float4* out = S + (size_t)f * frame_stride4 + (size_t)(x + 1) * 2;   // column x+1 of row 0
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) { out[0] = zero; out[1] = zero; }
+    if (s == 0 && lane == 0) {                                            // column 0 of every row
+        float4* c0 = S + (size_t)f * frame_stride4;
+        for (int y = 0; y <= H; y++) { c0[(size_t)y * pitch * 2] = zero; c0[(size_t)y * pitch * 2 + 1] = zero; }
+    }
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int4* cr = reinterpret_cast<const int4*>(carry + (((size_t)f * H) * n_strips + s) * 8);
+    const size_t cr_step = (size_t)n_strips * 2;
+    Row3 prev = load_row3(base, xp, xc, xn), cur = prev;
+    Row3 next = load_row3(base + (size_t)min(1, H - 1) * W, xp, xc, xn);
+    int4 c_lo = __ldg(cr), c_hi = __ldg(cr + 1);
+    for (int y = 0; y < H; y++) {
+        // prefetch the next iteration's inputs before the dependent shuffle chain
+        const Row3 nn = load_row3(base + (size_t)min(y + 2, H - 1) * W, xp, xc, xn);
+        const int yq = min(y + 1, H - 1);
+        const int4 n_lo = __ldg(cr + (size_t)yq * cr_step), n_hi = __ldg(cr + (size_t)yq * cr_step + 1);
+        uint32_t p[4];
+        channel_pairs(prev, cur, next, p);
+        if (!valid) { p[0] = p[1] = p[2] = p[3] = 0; }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, p[k], d);
+                if (lane >= d) p[k] += t;
+            }
+        }
+        const int cy[8] = {c_lo.x, c_lo.y, c_lo.z, c_lo.w, c_hi.x, c_hi.y, c_hi.z, c_hi.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            acc[2 * k] = __fadd_rn(acc[2 * k], (float)(cy[2 * k] + (int)(p[k] & 0xffffu)));
+            acc[2 * k + 1] = __fadd_rn(acc[2 * k + 1], (float)(cy[2 * k + 1] + (int)(p[k] >> 16)));
+        }
+        out += (size_t)pitch * 2;
+        if (valid) {
+            out[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            out[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+        prev = cur; cur = next; next = nn; c_lo = n_lo; c_hi = n_hi;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Descriptor, normalisation, weak classifier
+// ---------------------------------------------------------------------------------------------------------
+struct Px { float v[8]; };
+
+__device__ __forceinline__ Px load_px(const float4* __restrict__ S4, int pix) {
+    const float4 lo = __ldg(S4 + 2 * (size_t)pix), hi = __ldg(S4 + 2 * (size_t)pix + 1);
+    Px p;
+    p.v[0] = lo.x; p.v[1] = lo.y; p.v[2] = lo.z; p.v[3] = lo.w; p.v[4] = hi.x; p.v[5] = hi.y; p.v[6] = hi.z; p.v[7] = hi.w;
+    return p;
+}
+
+// (A + D) - (B + C), CalcFeature, DenseSURFFeatureExtractor.cpp:385-412
+__device__ __forceinline__ void cell_sum(const Px& A, const Px& B, const Px& C, const Px& D, float* v) {
+#pragma unroll
+    for (int c = 0; c < 8; c++) v[c] = __fsub_rn(__fadd_rn(A.v[c], D.v[c]), __fadd_rn(B.v[c], C.v[c]));
+}
+
+// hadd-ordered sum of squares seeded with FLT_EPSILON in lane 3, Normalize :427-433 / :441-451
+__device__ __forceinline__ float sumsq_hadd(const float* v) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = FLT_EPSILON;
+#pragma unroll
+    for (int g = 0; g < 8; g++) {
+        const float q0 = __fmul_rn(v[4 * g], v[4 * g]), q1 = __fmul_rn(v[4 * g + 1], v[4 * g + 1]);
+        const float q2 = __fmul_rn(v[4 * g + 2], v[4 * g + 2]), q3 = __fmul_rn(v[4 * g + 3], v[4 * g + 3]);
+        const float n0 = __fadd_rn(s0, s1), n1 = __fadd_rn(s2, s3), n2 = __fadd_rn(q0, q1), n3 = __fadd_rn(q2, q3);
+        s0 = n0; s1 = n1; s2 = n2; s3 = n3;
+    }
+    return __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
+}
+
+// CalcFeature + Normalize for one projected patch at window-origin pixel `org`.
+__device__ __forceinline__ void descriptor(const float4* __restrict__ S4, int org, const ScGeom g, float* v) {
+    const int p0 = org + g.off;
+    if (g.shape == 0) {
+        // 3 x 3 corner lattice, cells row-major (GetRectsFromPatch :360-377)
+        Px a0 = load_px(S4, p0), a1 = load_px(S4, p0 + g.along), a2 = load_px(S4, p0 + 2 * g.along);
+        Px b0 = load_px(S4, p0 + g.across), b1 = load_px(S4, p0 + g.across + g.along), b2 = load_px(S4, p0 + g.across + 2 * g.along);
+        cell_sum(a0, a1, b0, b1, v);
+        cell_sum(a1, a2, b1, b2, v + 8);
+        a0 = load_px(S4, p0 + 2 * g.across); a1 = load_px(S4, p0 + 2 * g.across + g.along); a2 = load_px(S4, p0 + 2 * g.across + 2 * g.along);
+        cell_sum(b0, b1, a0, a1, v + 16);
+        cell_sum(b1, b2, a1, a2, v + 24);
+    } else {
+        // 2 x 5 corner lattice: four cells chained along `along` (4x1 wide or 1x4 tall; B and C swap roles
+        // between the two, and fl(B + C) == fl(C + B))
+        Px t0 = load_px(S4, p0), u0 = load_px(S4, p0 + g.across);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const Px t1 = load_px(S4, p0 + (k + 1) * g.along), u1 = load_px(S4, p0 + (k + 1) * g.along + g.across);
+            cell_sum(t0, t1, u0, u1, v + 8 * k);
+            t0 = t1; u0 = u1;
+        }
+    }
+    const float theta = 0.353553385f;  // 2 / sqrtf(32.f), DenseSURFFeatureExtractor.h:36
+    const float t = __fmul_rn(__fsqrt_rn(sumsq_hadd(v)), theta);
+    const float t2 = -t;
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = fmaxf(fminf(v[i], t), t2);
+    const float inv = __fdiv_rn(1.0f, __fsqrt_rn(sumsq_hadd(v)));
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __fmul_rn(v[i], inv);
+}
+
+// LogisticRegression::Predict, LogisticRegression.cpp:46-68.  w: 32 weights (16 B aligned), wb = double(w[32]) * bias.
+__device__ __forceinline__ float weak_predict(const float* v, const float* __restrict__ w, double wb) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+        const float4 wv = *reinterpret_cast<const float4*>(w + i);
+        s0 = __fadd_rn(__fmul_rn(wv.x, v[i]), s0);
+        s1 = __fadd_rn(__fmul_rn(wv.y, v[i + 1]), s1);
+        s2 = __fadd_rn(__fmul_rn(wv.z, v[i + 2]), s2);
+        s3 = __fadd_rn(__fmul_rn(wv.w, v[i + 3]), s3);
+    }
+    const float z32 = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
+    const double z = (double)z32 + wb;
+    return (float)(1.0 / (1.0 + exp(-z)));
+}
+
+// GentleAdaboost::Predict2 (GentleAdaboost.cpp:247-261) of one stage on one window.
+__device__ __forceinline__ float stage_score(const float4* __restrict__ S4, int org, const ScGeom* __restrict__ geom,
+                                             const float* __restrict__ w, const double* __restrict__ wb, int n_weak) {
+    float acc = 0.f;
+    for (int q = 0; q < n_weak; q++) {
+        float v[32];
+        descriptor(S4, org, geom[q], v);
+        acc = __fadd_rn(acc, weak_predict(v, w + q * SC_W_PITCH, wb[q]));
+    }
+    return __fdiv_rn(acc, (float)n_weak);
+}
+
+// DenseSURFFeatureExtractor::sum (:351-358) and the compare at ObjDetector.cpp:188
+__device__ __forceinline__ float window_sum(const float4* __restrict__ S4, int org, int dx, int dy) {
+    const float4 a = __ldg(S4 + 2 * (size_t)org), b = __ldg(S4 + 2 * (size_t)(org + dx));
+    const float4 c = __ldg(S4 + 2 * (size_t)(org + dy)), d = __ldg(S4 + 2 * (size_t)(org + dy + dx));
+    const float s0 = __fsub_rn(__fadd_rn(a.x, d.x), __fadd_rn(b.x, c.x));
+    const float s1 = __fsub_rn(__fadd_rn(a.y, d.y), __fadd_rn(b.y, c.y));
+    const float s2 = __fsub_rn(__fadd_rn(a.z, d.z), __fadd_rn(b.z, c.z));
+    const float s3 = __fsub_rn(__fadd_rn(a.w, d.w), __fadd_rn(b.w, c.w));
+    return __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(s0, s1), s2), s3), 0.5f);  // /2 is exact as *0.5
+}
+
+// multi == 2 for a window rejected at stage p with stage score s (ObjDetector.cpp:201,214)
+__device__ __forceinline__ bool rejected_skips(float s, int p, int n_stages) {
+    return ((double)s + (double)p + 1.0) / (double)n_stages < 0.5;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Stage 0 over the whole lattice
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SC_TILE_THREADS) k_scan_stage0(const ScPlan* __restrict__ plan, const float4* __restrict__ S,
+                                                                  const ScGeom* __restrict__ geom_all, const float* __restrict__ w_all,
+                                                                  const double* __restrict__ wb_all, uint32_t* __restrict__ multi_bits,
+                                                                  uint32_t* __restrict__ pass_bits, ScRecord* __restrict__ rec,
+                                                                  uint32_t* __restrict__ rec_count, uint32_t rec_cap) {
+    __shared__ uint32_t s_multi[SC_TILE_Y][2];
+    __shared__ uint32_t s_pass[SC_TILE_Y][2];
+    __shared__ uint16_t s_list[SC_TILE_X * SC_TILE_Y];
+    __shared__ uint32_t s_count;
+    extern __shared__ __align__(16) unsigned char s_dyn[];  // stage-0 weights, wb, geometry
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int f = blockIdx.x / plan->blocks_per_frame;
+    const int b = blockIdx.x - f * plan->blocks_per_frame;
+    int si = 0;
+    while (si + 1 < plan->n_scales && plan->sc[si + 1].block_base <= b) si++;
+    const ScScale sc = plan->sc[si];
+    const int tb = b - sc.block_base;
+    const int ty = tb / sc.tiles_x, tx = tb - ty * sc.tiles_x;
+    const int n_weak = plan->n_weak[0], total_weak = plan->total_weak;
+    const int pitch = plan->pitch, step = plan->step;
+    const float4* S4 = S + (size_t)f * plan->frame_stride4;
+
+    float* sw = reinterpret_cast<float*>(s_dyn);                                   // [n_weak][36]
+    double* swb = reinterpret_cast<double*>(s_dyn + (size_t)n_weak * SC_W_PITCH * 4);  // [n_weak]
+    ScGeom* sg = reinterpret_cast<ScGeom*>(swb + n_weak);                           // [n_weak]
+    for (int i = tid; i < n_weak * SC_W_PITCH; i += SC_TILE_THREADS) sw[i] = w_all[i];
+    for (int i = tid; i < n_weak; i += SC_TILE_THREADS) { swb[i] = wb_all[i]; sg[i] = geom_all[(size_t)si * total_weak + i]; }
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+
+    // phase A: prefilter + compaction of the passing windows of this tile
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int row = warp + 8 * (i >> 1), half = i & 1;
+        const int gx = tx * SC_TILE_X + half * 32 + lane, gy = ty * SC_TILE_Y + row;
+        const bool valid = gx < sc.nx && gy < sc.ny;
+        bool pass = false;
+        if (valid) {
+            pass = true;
+            if (plan->use_prefilter) {
+                const int org = gy * step * pitch + gx * step;
+                pass = window_sum(S4, org, sc.l, sc.l * pitch) > sc.thr;
+            }
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, pass);
+        uint32_t base = 0;
+        if (lane == 0) {
+            s_pass[row][half] = m;
+            s_multi[row][half] = ~m;  // prefilter failed -> multi = 2 (ObjDetector.cpp:216-217)
+            base = atomicAdd(&s_count, __popc(m));
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (pass) s_list[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)((row << 6) | (half << 5) | lane);
+    }
+    __syncthreads();
+
+    // phase B: stage 0 on the dense list
+    const uint32_t count = s_count;
+    const float theta0 = plan->theta[0];
+    const int n_stages = plan->n_stages;
+    const bool force = plan->force_all != 0;
+    for (uint32_t i0 = 0; i0 < count; i0 += SC_TILE_THREADS) {
+        const uint32_t i = i0 + tid;
+        const bool active = i < count;
+        bool push = false;
+        ScRecord r;
+        if (active) {
+            const uint32_t code = s_list[i];
+            const int row = code >> 6, half = (code >> 5) & 1, ln = code & 31;
+            const int gx = tx * SC_TILE_X + half * 32 + ln, gy = ty * SC_TILE_Y + row;
+            const int org = gy * step * pitch + gx * step;
+            const float score = stage_score(S4, org, sg, sw, swb, n_weak);
+            const bool rejected = score < theta0;
+            if (rejected && rejected_skips(score, 0, n_stages)) atomicOr(&s_multi[row][half], 1u << ln);
+            push = !rejected || force;
+            r.fs = ((uint32_t)f << 8) | (uint32_t)si;
+            r.yx = ((uint32_t)gy << 16) | (uint32_t)gx;
+            r.rej = rejected ? 0 : (n_stages == 1 ? 1 : -1);
+            r.score = __float_as_uint(score);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, push);
+        if (m) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(rec_count, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (push) {
+                const uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
+                if (slot < rec_cap) rec[slot] = r;
+            }
+        }
+    }
+    __syncthreads();
+
+    // phase C: publish the two bitmask words of every tile row
+    if (tid < SC_TILE_Y * 2) {
+        const int row = tid >> 1, half = tid & 1;
+        const int gy = ty * SC_TILE_Y + row, wx = tx * 2 + half;
+        if (gy < sc.ny && wx < sc.wpr) {
+            const size_t wi = (size_t)f * plan->words_per_frame + sc.word_base + (size_t)gy * sc.wpr + wx;
+            multi_bits[wi] = s_multi[row][half];
+            pass_bits[wi] = s_pass[row][half];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Stages 1..N-1 on compacted index lists
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_scan_stage(const ScPlan* __restrict__ plan, int stage, const float4* __restrict__ S,
+                                                     const ScGeom* __restrict__ geom_all, const float* __restrict__ w_all,
+                                                     const double* __restrict__ wb_all, uint32_t* __restrict__ multi_bits,
+                                                     ScRecord* __restrict__ rec, const uint32_t* __restrict__ in_idx,
+                                                     const uint32_t* __restrict__ in_count, uint32_t* __restrict__ out_idx,
+                                                     uint32_t* __restrict__ out_count, uint32_t cap) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    const int n_weak = plan->n_weak[stage], wbase = plan->weak_base[stage], total_weak = plan->total_weak;
+    float* sw = reinterpret_cast<float*>(s_dyn);
+    double* swb = reinterpret_cast<double*>(s_dyn + (size_t)n_weak * SC_W_PITCH * 4);
+    for (int i = threadIdx.x; i < n_weak * SC_W_PITCH; i += blockDim.x) sw[i] = w_all[(size_t)wbase * SC_W_PITCH + i];
+    for (int i = threadIdx.x; i < n_weak; i += blockDim.x) swb[i] = wb_all[wbase + i];
+    __syncthreads();
+    const uint32_t count = min(*in_count, cap);
+    const int n_stages = plan->n_stages, pitch = plan->pitch, step = plan->step;
+    const bool force = plan->force_all != 0, last = stage == n_stages - 1;
+    const float theta = plan->theta[stage];
+    const int lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < count; i0 += stride) {
+        const uint32_t i = i0 + threadIdx.x;
+        bool push = false;
+        uint32_t idx = 0;
+        if (i < count) {
+            idx = in_idx ? in_idx[i] : i;
+            ScRecord r = rec[idx];
+            const int f = r.fs >> 8, si = r.fs & 0xff;
+            const int gy = r.yx >> 16, gx = r.yx & 0xffff;
+            const int org = gy * step * pitch + gx * step;
+            const float4* S4 = S + (size_t)f * plan->frame_stride4;
+            const float score = stage_score(S4, org, geom_all + (size_t)si * total_weak + wbase, sw, swb, n_weak);
+            if (r.rej < 0) {
+                const bool rejected = score < theta;
+                if (rejected) {
+                    r.rej = stage; r.score = __float_as_uint(score);
+                    if (rejected_skips(score, stage, n_stages)) {
+                        const ScScale sc = plan->sc[si];
+                        atomicOr(&multi_bits[(size_t)f * plan->words_per_frame + sc.word_base + (size_t)gy * sc.wpr + (gx >> 5)], 1u << (gx & 31));
+                    }
+                    rec[idx] = r;
+                } else if (last) {
+                    r.rej = n_stages; r.score = __float_as_uint(score);
+                    rec[idx] = r;
+                }
+                push = !rejected && !last;
+            }
+            if (force) push = false;  // force_all walks the full record array at every stage
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, push);
+        if (m) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(out_count, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (push) {
+                const uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
+                if (slot < cap) out_idx[slot] = idx;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Adaptive-stride replay (ObjDetector.cpp:185-186,214-217): one thread per (frame, scale, lattice row)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_replay_rows(const ScPlan* __restrict__ plan, int nframes, const uint32_t* __restrict__ multi_bits,
+                                                      const uint32_t* __restrict__ pass_bits, uint32_t* __restrict__ visited_bits,
+                                                      unsigned long long* __restrict__ counters) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int rows = plan->rows_per_frame;
+    unsigned long long nvis = 0, npass = 0;
+    int f = 0;
+    if (t < nframes * rows) {
+        f = t / rows;
+        const int r = t - f * rows;
+        int si = 0;
+        while (si + 1 < plan->n_scales && plan->sc[si + 1].row_base <= r) si++;
+        const ScScale sc = plan->sc[si];
+        const size_t w0 = (size_t)f * plan->words_per_frame + sc.word_base + (size_t)(r - sc.row_base) * sc.wpr;
+        const bool skip = plan->skip_rule != 0;
+        int pos = 0;
+        for (int wi = 0; wi < sc.wpr; wi++) {
+            const uint32_t m = multi_bits[w0 + wi], pm = pass_bits[w0 + wi];
+            const int end = min(32 * (wi + 1), sc.nx);
+            uint32_t v = 0;
+            if (skip) {
+                while (pos < end) {
+                    const int bpos = pos & 31;
+                    v |= 1u << bpos;
+                    pos += 1 + ((m >> bpos) & 1u);
+                }
+            } else {
+                const int nb = end - 32 * wi;
+                v = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
+            }
+            visited_bits[w0 + wi] = v;
+            nvis += __popc(v);
+            npass += __popc(v & pm);
+        }
+    }
+    // block-level reduction is only valid when the whole block shares a frame; rows_per_frame is not a multiple
+    // of the block size, so reduce per warp with a frame-uniformity check
+    const uint32_t same = __match_any_sync(0xffffffffu, f);
+    if (same == 0xffffffffu) {
+        for (int d = 16; d > 0; d >>= 1) {
+            nvis += __shfl_down_sync(0xffffffffu, nvis, d);
+            npass += __shfl_down_sync(0xffffffffu, npass, d);
+        }
+        if ((threadIdx.x & 31) == 0 && (nvis | npass)) {
+            atomicAdd(&counters[(size_t)f * SC_CNT_STRIDE + SC_CNT_VISITED], nvis);
+            atomicAdd(&counters[(size_t)f * SC_CNT_STRIDE + SC_CNT_PREFILTER], npass);
+        }
+    } else if (nvis | npass) {
+        atomicAdd(&counters[(size_t)f * SC_CNT_STRIDE + SC_CNT_VISITED], nvis);
+        atomicAdd(&counters[(size_t)f * SC_CNT_STRIDE + SC_CNT_PREFILTER], npass);
+    }
+}
+
+// Detections = records that passed every stage AND were visited by the replay; reach counters for visited records.
+struct ScDetOut { int32_t frame, x, y, l; double score; };
+
+__global__ void __launch_bounds__(128) k_finalize(const ScPlan* __restrict__ plan, const ScRecord* __restrict__ rec,
+                                                   const uint32_t* __restrict__ rec_count, uint32_t rec_cap,
+                                                   const uint32_t* __restrict__ visited_bits, unsigned long long* __restrict__ counters,
+                                                   ScDetOut* __restrict__ det, uint32_t* __restrict__ det_count, uint32_t det_cap, int frame0) {
+    const uint32_t count = min(*rec_count, rec_cap);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const int n_stages = plan->n_stages;
+    const int lane = threadIdx.x & 31;
+    for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < count; i0 += stride) {  // warp-uniform trip count
+        const uint32_t i = i0 + threadIdx.x;
+        bool vis = false;
+        int f = 0, gx = 0, gy = 0, l = 0, reached = 0;
+        float score = 0.f;
+        if (i < count) {
+            const ScRecord r = rec[i];
+            f = r.fs >> 8;
+            const ScScale sc = plan->sc[r.fs & 0xff];
+            gy = r.yx >> 16; gx = r.yx & 0xffff; l = sc.l;
+            const uint32_t v = visited_bits[(size_t)f * plan->words_per_frame + sc.word_base + (size_t)gy * sc.wpr + (gx >> 5)];
+            vis = (v >> (gx & 31)) & 1u;
+            reached = r.rej < 0 ? n_stages : r.rej;  // stages 0..min(reached, n_stages-1) were entered
+            score = __uint_as_float(r.score);
+        }
+        unsigned long long* c = counters + (size_t)f * SC_CNT_STRIDE;
+        // warp-aggregated reach counters: one atomic per (frame group, stage)
+        const uint32_t grp = __match_any_sync(0xffffffffu, f);
+        const bool leader = lane == (__ffs(grp) - 1);
+        for (int s = 1; s < n_stages; s++) {
+            const uint32_t m = __ballot_sync(0xffffffffu, vis && s <= reached) & grp;
+            if (leader && m) atomicAdd(&c[SC_CNT_REACH0 + s], (unsigned long long)__popc(m));
+        }
+        if (vis && reached == n_stages) {
+            atomicAdd(&c[SC_CNT_RAW], 1ull);
+            const uint32_t slot = atomicAdd(det_count, 1u);
+            if (slot < det_cap) {
+                ScDetOut d;
+                d.frame = frame0 + f; d.x = gx * plan->step; d.y = gy * plan->step; d.l = l;
+                d.score = ((double)score + (double)n_stages + 1.0) / (double)n_stages;  // ObjDetector.cpp:201
+                det[slot] = d;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Parity hooks on explicit rect / window lists
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_features(const float4* __restrict__ S4, int pitch, const int4* __restrict__ rects, int n, float* __restrict__ out,
+                           float* __restrict__ sums) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 r = rects[i];  // x, y, w, h
+    const int org = r.y * pitch + r.x;
+    if (sums) sums[i] = window_sum(S4, org, r.z, r.w * pitch);
+    if (out) {
+        ScGeom g;
+        g.off = 0;
+        if (r.z == r.w) { const int ce = r.z / 2; g.shape = 0; g.along = ce; g.across = ce * pitch; }
+        else if (r.z > r.w) { g.shape = 1; g.along = r.w; g.across = r.w * pitch; }
+        else { g.shape = 1; g.along = r.z * pitch; g.across = r.z; }
+        float v[32];
+        descriptor(S4, org, g, v);
+        for (int k = 0; k < 32; k++) out[(size_t)i * 32 + k] = v[k];
+    }
+}
+
+__global__ void k_stage_scores(const ScPlan* __restrict__ plan, const float4* __restrict__ S4, const ScGeom* __restrict__ geom_win,
+                               const float* __restrict__ w_all, const double* __restrict__ wb_all, const int* __restrict__ wins, int n,
+                               float* __restrict__ out) {
+    // geom_win: [n][total_weak] geometry projected for each explicit window's side (host-built)
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int org = wins[3 * i + 1] * plan->pitch + wins[3 * i];
+    for (int s = 0; s < plan->n_stages; s++) {
+        const int wb = plan->weak_base[s];
+        out[(size_t)i * plan->n_stages + s] = stage_score(S4, org, geom_win + (size_t)i * plan->total_weak + wb,
+                                                          w_all + (size_t)wb * SC_W_PITCH, wb_all + wb, plan->n_weak[s]);
+    }
+}
+
+// LogisticRegression::Predict on explicit (weights, descriptor) pairs; with `mean` non-null thread 0 also folds
+// the probabilities in order into GentleAdaboost::Predict2's float32 mean.
+__global__ void k_weak_predict(const float* __restrict__ w36, const double* __restrict__ wb, const float* __restrict__ x, int n,
+                               float* __restrict__ out, float* __restrict__ mean) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float v[32];
+#pragma unroll
+        for (int k = 0; k < 32; k++) v[k] = x[(size_t)i * 32 + k];
+        out[i] = weak_predict(v, w36 + (size_t)i * SC_W_PITCH, wb[i]);
+    }
+    if (mean) {  // single-block launch
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float acc = 0.f;
+            for (int i = 0; i < n; i++) acc = __fadd_rn(acc, out[i]);
+            *mean = __fdiv_rn(acc, (float)n);
+        }
+    }
+}
+
+}  // namespace sck
+
+#endif

@@ -1,0 +1,161 @@
+// See sc_host.h.
+#include "sc_host.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdlib>
+#include <memory>
+
+#include "CascadeClassifier/CascadeClassifier.h"
+#include "CascadeClassifier/GentleAdaboost.h"
+#include "CascadeClassifier/LogisticRegression.h"
+#include "Model.h"
+#include "sc_access.h"
+
+namespace sc_host {
+
+void pool_patches(int tw, int th, std::vector<sc_rect>* out) {
+    // three cell layouts (columns x rows): 2x2, 1x4, 4x1; cell edge 6 .. tw/2; origin stride 4
+    static const int cols[3] = {2, 1, 4}, rows[3] = {2, 4, 1};
+    out->clear();
+    for (int shape = 0; shape < 3; shape++)
+        for (int edge = 6; edge <= tw / 2; edge++) {
+            const int pw = cols[shape] * edge, ph = rows[shape] * edge;
+            for (int y = 0; y + ph <= th; y += 4)
+                for (int x = 0; x + pw <= tw; x += 4) out->push_back(sc_rect{x, y, pw, ph});
+        }
+}
+
+sc_rect project_patch(int tmpl, int l, const sc_rect& p) {
+    const float scale = (float)l / (float)tmpl;
+    sc_rect r;
+    r.x = (int)((float)p.x * scale);
+    r.y = (int)((float)p.y * scale);
+    if (p.w >= p.h) {
+        r.h = (int)((float)p.h * scale);
+        r.w = r.h * (p.w / p.h);
+    } else {
+        r.w = (int)((float)p.w * scale);
+        r.h = r.w * (p.h / p.w);
+    }
+    return r;
+}
+
+bool project_geom(int tmpl, int l, const sc_rect& patch, int pitch, ScGeom* g) {
+    const sc_rect r = project_patch(tmpl, l, patch);
+    g->off = r.y * pitch + r.x;
+    if (r.w == r.h) {
+        const int ce = r.w / 2;
+        if (ce < 1) return false;
+        g->shape = 0; g->along = ce; g->across = ce * pitch;
+    } else {
+        const int ce = std::min(r.w, r.h);
+        if (ce < 1 || std::max(r.w, r.h) != 4 * ce) return false;
+        g->shape = 1;
+        if (r.w > r.h) { g->along = ce; g->across = ce * pitch; }
+        else { g->along = ce * pitch; g->across = ce; }
+    }
+    return true;
+}
+
+void scale_ladder(int W, int H, int base, double scale, std::vector<int>* sides) {
+    sides->clear();
+    // the ratios are float, their logs are taken in float (MSVC resolves log(float) to the float overload),
+    // the quotient and the comparison are double
+    const double a = (double)logf((float)W / (float)base) / log(scale);
+    const double b = (double)logf((float)H / (float)base) / log(scale);
+    const int n = (int)std::min(a, b);
+    for (int i = 0; i <= n; i++) sides->push_back((int)((double)base * pow(scale, (double)i)));
+}
+
+namespace {
+int find_root(std::vector<int>& parent, int i) {
+    while (parent[i] != i) { parent[i] = parent[parent[i]]; i = parent[i]; }
+    return i;
+}
+bool similar(const sc_rect& a, const sc_rect& b, double eps) {
+    const double delta = eps * (std::min(a.w, b.w) + std::min(a.h, b.h)) * 0.5;
+    return std::abs(a.x - b.x) <= delta && std::abs(a.y - b.y) <= delta && std::abs(a.x + a.w - b.x - b.w) <= delta &&
+           std::abs(a.y + a.h - b.y - b.h) <= delta;
+}
+int round_even(double v) { return (int)lrint(v); }
+}  // namespace
+
+void group_rectangles(std::vector<sc_rect>* rects, std::vector<double>* scores, int thr, double eps) {
+    const int n = (int)rects->size();
+    if (thr <= 0 || n == 0) return;
+    const std::vector<sc_rect>& r = *rects;
+    std::vector<int> parent(n), cls(n, -1), first(n, -1);
+    for (int i = 0; i < n; i++) parent[i] = i;
+    for (int i = 0; i < n; i++)
+        for (int j = i + 1; j < n; j++)
+            if (similar(r[i], r[j], eps)) {
+                const int a = find_root(parent, i), b = find_root(parent, j);
+                if (a != b) parent[std::max(a, b)] = std::min(a, b);
+            }
+    int k = 0;
+    for (int i = 0; i < n; i++) {
+        const int root = find_root(parent, i);
+        if (first[root] < 0) first[root] = k++;
+        cls[i] = first[root];
+    }
+    struct Cluster { long long x = 0, y = 0, w = 0, h = 0; int members = 0; double best = DBL_MIN; sc_rect mean{0, 0, 0, 0}; };
+    std::vector<Cluster> c(k);
+    for (int i = 0; i < n; i++) {
+        Cluster& q = c[cls[i]];
+        q.x += r[i].x; q.y += r[i].y; q.w += r[i].w; q.h += r[i].h; q.members++;
+        if ((*scores)[i] > q.best) q.best = (*scores)[i];
+    }
+    for (Cluster& q : c) {
+        const float inv = 1.f / (float)q.members;
+        q.mean = sc_rect{round_even((double)((float)(int)q.x * inv)), round_even((double)((float)(int)q.y * inv)),
+                         round_even((double)((float)(int)q.w * inv)), round_even((double)((float)(int)q.h * inv))};
+    }
+    std::vector<sc_rect> out_r;
+    std::vector<double> out_s;
+    for (int i = 0; i < k; i++) {
+        if (c[i].members <= thr) continue;
+        const sc_rect& a = c[i].mean;
+        bool swallowed = false;
+        for (int j = 0; j < k && !swallowed; j++) {
+            if (j == i || c[j].members <= thr) continue;
+            const sc_rect& b = c[j].mean;
+            const int dx = round_even(b.w * eps), dy = round_even(b.h * eps);
+            swallowed = a.x >= b.x - dx && a.y >= b.y - dy && a.x + a.w <= b.x + b.w + dx && a.y + a.h <= b.y + b.h + dy &&
+                        (c[j].members > std::max(3, c[i].members) || c[i].members < 3);
+        }
+        if (!swallowed) { out_r.push_back(a); out_s.push_back(c[i].best); }
+    }
+    rects->swap(out_r);
+    scores->swap(out_s);
+}
+
+bool Access::flatten(CascadeClassifier& cc, int tmpl, FlatCascade* out, std::string* why) {
+    std::vector<sc_rect> pool;
+    pool_patches(tmpl, tmpl, &pool);
+    out->theta.clear(); out->n_weak.clear(); out->rects.clear(); out->w.clear(); out->bias.clear();
+    for (auto& st : cc.stage_classifiers) {
+        GentleAdaboost* g = dynamic_cast<GentleAdaboost*>(st.get());
+        if (!g) { if (why) *why = "stage is not a GentleAdaboost"; return false; }
+        out->theta.push_back(g->theta);
+        out->n_weak.push_back((int)g->weak_classifiers.size());
+        for (auto& wk : g->weak_classifiers) {
+            if (wk->patch_index < 0 || wk->patch_index >= (int)pool.size()) { if (why) *why = "patch_index outside the template pool"; return false; }
+            out->rects.push_back(pool[wk->patch_index]);
+            out->w.insert(out->w.end(), wk->w, wk->w + 33);
+            out->bias.push_back(wk->bias_);
+        }
+    }
+    if (out->theta.empty()) { if (why) *why = "model holds no stages"; return false; }
+    return true;
+}
+
+bool load_flat_cascade(const std::string& model_cfg, int tmpl, FlatCascade* out, std::string* why) {
+    CascadeClassifier cc;
+    Model model(model_cfg);
+    if (model.Load(cc) != EXIT_SUCCESS) { if (why) *why = "cannot read or parse " + model_cfg; return false; }
+    return Access::flatten(cc, tmpl, out, why);
+}
+
+}  // namespace sc_host
