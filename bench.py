@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- 1080p full-scale-range SURF-cascade detection throughput (BASELINE.json metric, config C2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+A step is one pass of the whole hot path (channels + integral + cascade scan + stride replay + detection
+output) over one batch of B synthetic 1920x1080 frames per GPU.  `value` is frames/s with the frames already
+resident in HBM (sc_detect_device); `e2e` is the same metric through the host-buffer C-ABI call sc_detect
+(pinned host frames -> H2D -> path -> D2H detections) -- the number to compare with the reference arm.
+Under torchrun (N > 1) every rank runs the same work on its own GPU (frames sharded by rank, weak scaling) and
+the detections of every step are gathered over NCCL; times are CUDA-event/device based, max over ranks.
+
+`--impl reference` times the reference's own CPU code (oracle/_ref: the unmodified reference sources compiled
+by oracle/Makefile; falls back to the plain-C port oracle/libsurf_oracle.so) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 1920, 1080
+MODEL = os.path.join(ROOT, "tests", "golden", "model_c1.cfg")
+WORKLOAD = "C2: 1920x1080 synthetic frames, base 40, step 2, scale 1.1 (35 scales, 11,557,983 grid windows/frame), reference-trained cascade model_c1.cfg"
+N_UNIQUE = 8  # distinct synthetic frames; batches cycle through them with different offsets
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx = float(parts[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_frames(n: int):
+    from surfcascade_b200 import synth
+    return [synth.frame(H, W, 100 + i) for i in range(n)]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU detect path on the host cores
+# ------------------------------------------------------------------------------------------------------------
+def cpu_detect_once(frames, threads: int):
+    """Returns (seconds, kind, counters) for one pass of the reference CPU path over `frames`."""
+    from oracle import refbind
+    if refbind.available():
+        t = time.perf_counter()
+        r = refbind.detect(frames, MODEL, base=40, nthreads=threads, group=False)
+        return time.perf_counter() - t, "reference", r.counters[:, :4].sum(0).tolist()
+    from oracle import modelcfg, oracle
+    bc = oracle.BoundCascade(modelcfg.load(MODEL))
+    prm = oracle.params(base=40, nthreads=threads)
+    t = time.perf_counter()
+    vis = 0
+    for f in frames:
+        d = oracle.detect(oracle.integral(f), bc, prm)
+        vis += int(d.counters[oracle.C_VISITED])
+    return time.perf_counter() - t, "port", [vis]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    frames = make_frames(2)
+    per_step = 1  # frames per step: a bounded sample of the C2 workload
+    for i in range(args.warmup):
+        cpu_detect_once(frames[:per_step], threads)
+    t_total, kind = 0.0, "port"
+    for i in range(args.steps):
+        dt, kind, _ = cpu_detect_once([frames[i % len(frames)]] * per_step, threads)
+        t_total += dt
+    fps = args.steps * per_step / t_total
+    line = {"impl": "reference", "metric": "1080p full-scale-range detection throughput", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "frames_per_step": per_step},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
+                             "sample": f"{per_step} frame(s) of the C2 workload per step, OpenMP over scales as in ObjDetector.cpp:177"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from surfcascade_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this implementation has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    h = capi.Handle(local)
+    h.load_model(MODEL, 40)
+    prm = capi.params()
+    stream = torch.cuda.ExternalStream(h.stream, device=dev)
+
+    # inputs: N_UNIQUE distinct frames; rank r / step s read a rotated batch so consecutive steps differ
+    base_frames = make_frames(N_UNIQUE)
+    n_sets = 5  # 5 x B x 2 MB of input (> 126 MB L2 for B >= 16); intermediates are 66 MB per frame
+    host_sets, dev_sets = [], []
+    for s in range(n_sets):
+        arr = np.stack([base_frames[(rank + s + i) % N_UNIQUE] for i in range(B)])
+        ht = torch.from_numpy(arr).pin_memory()
+        host_sets.append(ht)
+        dev_sets.append(ht.to(dev))
+    cap = 1 << 16
+    d_out = torch.zeros(cap * 24, dtype=torch.uint8, device=dev)
+    d_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    gather_buf = torch.zeros(world * (cap * 24 // 8), dtype=torch.uint8, device=dev) if world > 1 else None
+    gather_cnt = torch.zeros(world, dtype=torch.int32, device=dev) if world > 1 else None
+    g_cap_bytes = cap * 24 // 8
+
+    def step_device(s):
+        x = dev_sets[s % n_sets]
+        h.detect_device(x.data_ptr(), B, W, H, d_out.data_ptr(), cap, d_cnt.data_ptr(), prm)
+        if world > 1:
+            # the one exchange step of the path: detection records to every rank (rank 0 groups them)
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(gather_cnt, d_cnt)
+                dist.all_gather_into_tensor(gather_buf, d_out[:g_cap_bytes])
+
+    def step_host(s):
+        x = host_sets[s % n_sets]
+        ptrs = (ctypes.c_void_p * B)(*[x.data_ptr() + i * W * H for i in range(B)])
+        dets, _ = h.detect_ptrs(ptrs, B, W, H, W, prm, cap)
+        return dets
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """Device time of `steps` steps on the handle's stream (CUDA events), max over ranks."""
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for s in range(steps):
+            fn(s)
+        e1.record(stream)
+        h.sync()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for s in range(args.warmup):
+        step_device(s)
+    h.sync()
+    cnts = h.last_counters(B)
+    n_stages = len([1 for i in range(16) if cnts[0].reach[i] > 0]) or 1
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = h.launch_count
+    ms = timed(step_device, args.steps)
+    launches = h.launch_count - launches0
+    clk = clocks.stop() if rank == 0 else {}
+    fps = world * B * args.steps / (ms / 1e3)
+
+    # per-kernel split of one more timed pass (same steps) with event spans inside the library
+    h.set_profiling(True)
+    h.kernel_stats(reset=True)
+    ms_prof = timed(step_device, args.steps)
+    stats = h.kernel_stats(reset=True)
+    h.set_profiling(False)
+
+    # e2e: host buffers through sc_detect (H2D and D2H inside the timed region), wall clock bracketed by syncs
+    for s in range(min(args.warmup, 2)):
+        step_host(s)
+    barrier()
+    t0 = time.perf_counter()
+    nd = 0
+    for s in range(args.steps):
+        nd += len(step_host(s))
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_fps = world * B * args.steps / e2e_s
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        frames_timed = B * args.steps
+        c = cnts[0]
+        grid, visited = c.grid, c.visited
+        mean = lambda f: float(np.mean([f(x) for x in cnts]))
+        # algorithmic gather bytes of the scan per frame: 32 B x (4 per prefilter + 9|10 corners per weak eval)
+        # evaluated on the grid windows this implementation scores (prefilter on every grid window)
+        st0_ms, st0_n = stats.get("k_scan_stage0", (0.0, 0))
+        walk_ms, walk_n = stats.get("k_integral_walk", (0.0, 0))
+        carry_ms, _ = stats.get("k_strip_carry", (0.0, 0))
+        total_k_ms = sum(v[0] for v in stats.values()) or 1.0
+        weak_ref = mean(lambda x: x.weak_evals)
+        alg_scan_bytes = 32.0 * (4.0 * grid + 10.0 * weak_ref)  # this cascade's stage-0 patches are all 1x4 / 4x1 (10 corners)
+        scan_gbs = alg_scan_bytes * frames_timed / (st0_ms / 1e3) / 1e9 if st0_ms else None
+        alg_int_bytes = W * H + 32.0 * (W + 1) * (H + 1)
+        int_gbs = alg_int_bytes * frames_timed / ((walk_ms + carry_ms) / 1e3) / 1e9 if walk_ms else None
+        cpu = None
+        if world == 1:
+            try:
+                th = os.cpu_count() or 1
+                fr = make_frames(2)
+                cpu_detect_once(fr[:1], th)
+                dt, kind, _ = cpu_detect_once(fr, th)
+                dt1, _, _ = cpu_detect_once(fr[:1], 1)
+                cpu = {"value": len(fr) / dt, "unit": "frames/s", "cores": th, "kind": kind,
+                       "sample": f"2 frames of the C2 workload, all {th} host threads (OpenMP over scales, ObjDetector.cpp:177); single-thread: {1.0 / dt1:.3f} frames/s"}
+            except Exception as e:  # the checker is optional for the product arm
+                cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
+        line = {
+            "metric": "1080p full-scale-range detection throughput", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "parallelism": f"frames sharded over {world} GPU(s)",
+                       "l2": f"inputs rotate over {n_sets} batches ({n_sets * B * W * H / 1e6:.0f} MB) and each step writes {B * 66.4:.0f} MB of integral images: larger than the 126 MB L2"},
+            "windows_per_s": {"grid": fps * grid, "reference_visited": fps * mean(lambda x: x.visited)},
+            "work_per_frame": {"grid_windows": grid, "visited": mean(lambda x: x.visited), "prefilter_pass": mean(lambda x: x.prefilter_pass),
+                               "weak_evals_reference": weak_ref, "raw_detections": mean(lambda x: x.raw)},
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": B * W * H, "d2h_bytes_per_step": int(24 * nd / max(args.steps, 1)) + B * 19 * 8 + 4},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"kernel": "k_scan_stage0", "bound": "hbm", "achieved": scan_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": (scan_gbs / peak) if scan_gbs else None, "traffic": None,
+                         "note": "algorithmic gather bytes 32 B x (4 x grid windows + 10 x reference weak evals) per frame over the kernel's CUDA-event time; the gather is served by L1/L2, so this is a cache-resident rate set against the HBM copy peak (" + peak_src + "); the kernel is issue-bound, see DESIGN.md",
+                         "share_of_step": st0_ms / total_k_ms},
+            "roofline_integral": {"kernel": "k_strip_carry+k_integral_walk", "bound": "hbm", "achieved": int_gbs, "peak": peak, "unit": "GB/s",
+                                  "frac": (int_gbs / peak) if int_gbs else None, "traffic": None, "share_of_step": (walk_ms + carry_ms) / total_k_ms,
+                                  "algorithmic_bytes_per_frame": alg_int_bytes},
+            "kernel_ms_per_frame": {k: v[0] / frames_timed for k, v in stats.items()},
+            "profiled_pass_ms_per_step": ms_prof / args.steps,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32, help="1080p frames per step per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

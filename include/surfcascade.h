@@ -134,6 +134,12 @@ void* sc_stream(sc_handle* h);
 /* Number of kernel launches issued by this handle so far. */
 int64_t sc_launch_count(const sc_handle* h);
 
+/* Optional per-kernel timing (CUDA events on the handle's stream around every launch of the detect path).
+ * sc_kernel_stats enumerates kernels by id 0,1,..; returns 1 past the last id.  Times are accumulated at sc_sync /
+ * at the end of sc_detect. */
+int sc_set_profiling(sc_handle* h, int on);
+int sc_kernel_stats(sc_handle* h, int kernel_id, const char** name, double* ms, int64_t* launches, int reset);
+
 /* ---- host-side grouping (next row N1) ------------------------------------------------------------------ */
 /* cv::groupRectangles(wins, weights = 0.., scores, groupThreshold, eps) as called at ObjDetector.cpp:224-225. */
 int sc_group_rectangles(const sc_rect* rects, const double* scores, int n, int group_threshold, double eps,

@@ -41,7 +41,8 @@ assert DETECTION_DTYPE.itemsize == 24
 
 EXPORTS = ["sc_create", "sc_destroy", "sc_last_error", "sc_version", "sc_set_cascade", "sc_load_model", "sc_pool_patches", "sc_project_patches",
            "sc_integral", "sc_features", "sc_window_sum", "sc_stage_scores", "sc_weak_predict", "sc_stage_predict", "sc_detect",
-           "sc_detect_device", "sc_sync", "sc_last_counters", "sc_stream", "sc_launch_count", "sc_group_rectangles"]
+           "sc_detect_device", "sc_sync", "sc_last_counters", "sc_stream", "sc_launch_count", "sc_group_rectangles",
+           "sc_set_profiling", "sc_kernel_stats"]
 
 _lib = None
 
@@ -83,6 +84,8 @@ def lib():
         L.sc_detect_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(DetectParams), C.c_void_p, C.c_size_t, C.c_void_p]
         L.sc_sync.argtypes = [C.c_void_p]
         L.sc_last_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.sc_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.sc_kernel_stats.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]
         L.sc_group_rectangles.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_int]
         _lib = L
     return _lib
@@ -239,6 +242,21 @@ class Handle:
         """Frames resident in device memory (n x h x w u8); asynchronous on the handle's stream."""
         prm = prm or params()
         self._check(lib().sc_detect_device(self._h, d_frames_ptr, n, w, h, C.byref(prm), d_out_ptr, cap, d_count_ptr))
+
+    def set_profiling(self, on: bool):
+        self._check(lib().sc_set_profiling(self._h, int(on)))
+
+    def kernel_stats(self, reset: bool = False) -> dict:
+        """{kernel name: (total ms, launches)} accumulated by the event spans since the last reset."""
+        out, k = {}, 0
+        while True:
+            name = C.c_char_p(); ms = C.c_double(0); n = C.c_int64(0)
+            rc = lib().sc_kernel_stats(self._h, k, C.byref(name), C.byref(ms), C.byref(n), int(reset))
+            if rc != SC_OK:
+                break
+            out[name.value.decode()] = (ms.value, n.value)
+            k += 1
+        return out
 
     def sync(self):
         self._check(lib().sc_sync(self._h))

@@ -90,6 +90,14 @@ struct sc_handle {
     // single-frame state for the parity hooks
     bool have_integral = false;
     int cur_W = 0, cur_H = 0;
+
+    // optional per-kernel timing with CUDA events on the handle's stream (bench.py's roofline leg)
+    bool profiling = false;
+    struct Span { int kid; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
+    double kernel_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t kernel_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace {
@@ -111,6 +119,44 @@ int cuda_fail(sc_handle* h, cudaError_t e, const char* what) {
         cudaError_t e_ = (call);                                 \
         if (e_ != cudaSuccess) return cuda_fail((h), e_, #call); \
     } while (0)
+
+enum { K_CARRY = 0, K_WALK, K_STAGE0, K_STAGE, K_REPLAY, K_FINALIZE, K_COUNT };
+const char* const kKernelNames[K_COUNT] = {"k_strip_carry", "k_integral_walk", "k_scan_stage0", "k_scan_stage", "k_replay_rows", "k_finalize"};
+
+cudaEvent_t take_event(sc_handle* h) {
+    cudaEvent_t e = nullptr;
+    if (!h->event_pool.empty()) { e = h->event_pool.back(); h->event_pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+}
+
+struct KernelSpan {
+    sc_handle* h;
+    int kid;
+    cudaEvent_t a = nullptr;
+    KernelSpan(sc_handle* h_, int kid_) : h(h_), kid(kid_) {
+        h->launches++;
+        if (h->profiling) { a = take_event(h); cudaEventRecord(a, h->stream); }
+    }
+    ~KernelSpan() {
+        if (a) {
+            cudaEvent_t b = take_event(h);
+            cudaEventRecord(b, h->stream);
+            h->spans.push_back(sc_handle::Span{kid, a, b});
+        }
+    }
+};
+
+// call after the stream has been synchronised
+void drain_spans(sc_handle* h) {
+    for (auto& sp : h->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) { h->kernel_ms[sp.kid] += ms; h->kernel_launches[sp.kid]++; }
+        h->event_pool.push_back(sp.a);
+        h->event_pool.push_back(sp.b);
+    }
+    h->spans.clear();
+}
 
 sc_detect_params default_params() {
     sc_detect_params p;
@@ -222,10 +268,9 @@ int run_group(sc_handle* h, const uint8_t* d_img, int g, int frame0, sc_detectio
     float4* S = h->d_S.as<float4>();
     {
         const int rows = g * p.H;
-        sck::k_strip_carry<<<(rows + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, g, h->d_carry.as<int>());
+        { KernelSpan ks(h, K_CARRY); sck::k_strip_carry<<<(rows + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, g, h->d_carry.as<int>()); }
         const int warps = g * p.n_strips;
-        sck::k_integral_walk<<<(warps + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, g, h->d_carry.as<int>(), S, p.frame_stride4);
-        h->launches += 2;
+        { KernelSpan ks(h, K_WALK); sck::k_integral_walk<<<(warps + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, g, h->d_carry.as<int>(), S, p.frame_stride4); }
     }
     if (p.n_scales > 0 && p.n_stages > 0) {
         const ScGeom* geom = h->d_geom.as<ScGeom>();
@@ -235,9 +280,9 @@ int run_group(sc_handle* h, const uint8_t* d_img, int g, int frame0, sc_detectio
         ScRecord* rec = h->d_rec.as<ScRecord>();
         {
             const size_t smem = (size_t)p.n_weak[0] * (SC_W_PITCH * 4 + 8 + sizeof(ScGeom));
+            KernelSpan ks(h, K_STAGE0);
             sck::k_scan_stage0<<<g * p.blocks_per_frame, SC_TILE_THREADS, smem, st>>>(dp, S, geom, w, wb, multi, h->d_pass.as<uint32_t>(), rec,
                                                                                          small + SM_REC, h->rec_cap);
-            h->launches++;
         }
         const int tail_grid = h->n_sms * 8;
         for (int s = 1; s < p.n_stages; s++) {
@@ -245,15 +290,15 @@ int run_group(sc_handle* h, const uint8_t* d_img, int g, int frame0, sc_detectio
             const uint32_t* in_idx = first ? nullptr : h->d_idx[(s - 1) & 1].as<uint32_t>();
             const uint32_t* in_cnt = first ? small + SM_REC : small + SM_STAGE0 + (s - 1);
             const size_t smem = (size_t)p.n_weak[s] * (SC_W_PITCH * 4 + 8);
+            KernelSpan ks(h, K_STAGE);
             sck::k_scan_stage<<<tail_grid, 128, smem, st>>>(dp, s, S, geom, w, wb, multi, rec, in_idx, in_cnt, h->d_idx[s & 1].as<uint32_t>(),
                                                              small + SM_STAGE0 + s, h->rec_cap);
-            h->launches++;
         }
         const int rows = g * p.rows_per_frame;
-        sck::k_replay_rows<<<(rows + 127) / 128, 128, 0, st>>>(dp, g, multi, h->d_pass.as<uint32_t>(), h->d_visited.as<uint32_t>(), d_counters);
-        sck::k_finalize<<<h->n_sms * 4, 128, 0, st>>>(dp, rec, small + SM_REC, h->rec_cap, h->d_visited.as<uint32_t>(), d_counters,
-                                                       reinterpret_cast<sck::ScDetOut*>(d_det), d_det_count, det_cap, frame0);
-        h->launches += 2;
+        { KernelSpan ks(h, K_REPLAY); sck::k_replay_rows<<<(rows + 127) / 128, 128, 0, st>>>(dp, g, multi, h->d_pass.as<uint32_t>(), h->d_visited.as<uint32_t>(), d_counters); }
+        { KernelSpan ks(h, K_FINALIZE);
+          sck::k_finalize<<<h->n_sms * 4, 128, 0, st>>>(dp, rec, small + SM_REC, h->rec_cap, h->d_visited.as<uint32_t>(), d_counters,
+                                                         reinterpret_cast<sck::ScDetOut*>(d_det), d_det_count, det_cap, frame0); }
     }
     SC_CUDA(h, cudaGetLastError());
     return SC_OK;
@@ -312,6 +357,8 @@ void sc_destroy(sc_handle* h) {
                       &h->d_rec, &h->d_idx[0], &h->d_idx[1], &h->d_small, &h->d_counters, &h->d_det};
     for (DevBuf* b : bufs) b->release();
     h->h_stage.release();
+    for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
     delete h;
 }
 
@@ -546,6 +593,23 @@ int sc_sync(sc_handle* h) {
     if (!h) return SC_ERR_INVALID;
     SC_CUDA(h, cudaSetDevice(h->device));
     SC_CUDA(h, cudaStreamSynchronize(h->stream));
+    drain_spans(h);
+    return SC_OK;
+}
+
+int sc_set_profiling(sc_handle* h, int on) {
+    if (!h) return SC_ERR_INVALID;
+    h->profiling = on != 0;
+    return SC_OK;
+}
+
+int sc_kernel_stats(sc_handle* h, int kernel_id, const char** name, double* ms, int64_t* launches, int reset) {
+    if (!h || kernel_id < 0) return SC_ERR_INVALID;
+    if (kernel_id >= K_COUNT) return 1;  // past the end
+    if (name) *name = kKernelNames[kernel_id];
+    if (ms) *ms = h->kernel_ms[kernel_id];
+    if (launches) *launches = h->kernel_launches[kernel_id];
+    if (reset) { h->kernel_ms[kernel_id] = 0; h->kernel_launches[kernel_id] = 0; }
     return SC_OK;
 }
 
@@ -584,6 +648,7 @@ int sc_detect(sc_handle* h, const uint8_t* const* frames, int nframes, int W, in
     SC_CUDA(h, cudaMemcpyAsync(h->h_stage.p, h->d_counters.p, cbytes, cudaMemcpyDeviceToHost, h->stream));
     SC_CUDA(h, cudaMemcpyAsync(h->h_stage.as<unsigned char>() + cbytes, d_cnt, 4, cudaMemcpyDeviceToHost, h->stream));
     SC_CUDA(h, cudaStreamSynchronize(h->stream));
+    drain_spans(h);
     h->last_nframes = nframes;
     uint32_t found = 0;
     memcpy(&found, h->h_stage.as<unsigned char>() + cbytes, 4);
