@@ -170,7 +170,7 @@ def run_ours(args):
     n_sets = 5  # 5 x B x 2 MB of input (> 126 MB L2 for B >= 16); intermediates are 66 MB per frame
     host_sets, dev_sets = [], []
     for s in range(n_sets):
-        arr = np.stack([base_frames[(rank + s + i) % N_UNIQUE] for i in range(B)])
+        arr = np.ascontiguousarray(np.stack([base_frames[(rank + s + i) % N_UNIQUE] for i in range(B)]))
         ht = torch.from_numpy(arr).pin_memory()
         host_sets.append(ht)
         dev_sets.append(ht.to(dev))

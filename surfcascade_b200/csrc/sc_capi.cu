@@ -90,6 +90,8 @@ struct sc_handle {
     // single-frame state for the parity hooks
     bool have_integral = false;
     int cur_W = 0, cur_H = 0;
+    ScLayout hook_lay{};
+    DevBuf d_hook_img, d_hook_carry, d_hook_S;
 
     // optional per-kernel timing with CUDA events on the handle's stream (bench.py's roofline leg)
     bool profiling = false;
@@ -171,15 +173,14 @@ int build_plan(sc_handle* h, int W, int H, const sc_detect_params& prm, std::vec
     if (W < 2 || H < 2 || prm.base < 1 || !(prm.scale > 1.0)) return fail(h, SC_ERR_INVALID, "bad frame size or scan parameters");
     ScPlan& p = h->plan;
     memset(&p, 0, sizeof(p));
-    p.W = W; p.H = H; p.pitch = W + 1;
+    p.W = W; p.H = H;
     p.step = prm.step > 0 ? prm.step : (prm.base > 20 ? prm.base / 20 : 1);
+    p.lay = sc_host::make_layout(W, H, p.step);
+    if (p.lay.frame4 > 0x7fffffffLL) return fail(h, SC_ERR_INVALID, "frame too large for 32-bit layout offsets");
     p.n_stages = h->n_stages; p.total_weak = h->total_weak;
     p.use_prefilter = prm.prefilter >= 0; p.skip_rule = prm.skip_rule != 0; p.force_all = prm.force_all_stages != 0;
     p.n_strips = (W + SC_STRIP - 1) / SC_STRIP;
     for (int s = 0; s < h->n_stages; s++) { p.theta[s] = h->theta[s]; p.n_weak[s] = h->n_weak[s]; p.weak_base[s] = h->weak_base[s]; }
-    size_t frame_bytes = (size_t)(H + 1) * (W + 1) * 32;
-    frame_bytes = (frame_bytes + 255) / 256 * 256;
-    p.frame_stride4 = (long long)(frame_bytes / 16);
 
     std::vector<int> sides;
     sc_host::scale_ladder(W, H, prm.base, prm.scale, &sides);
@@ -198,16 +199,22 @@ int build_plan(sc_handle* h, int W, int H, const sc_detect_params& prm, std::vec
         s.tiles_x = (s.nx + SC_TILE_X - 1) / SC_TILE_X;
         const int tiles_y = (s.ny + SC_TILE_Y - 1) / SC_TILE_Y;
         s.block_base = blocks; s.word_base = words; s.row_base = rows;
+        s.pf[0] = 0;
+        s.pf[1] = (int)sc_layout_index(p.lay, l, 0);
+        s.pf[2] = (int)sc_layout_index(p.lay, 0, l);
+        s.pf[3] = (int)sc_layout_index(p.lay, l, l);
         blocks += s.tiles_x * tiles_y; words += s.wpr * s.ny; rows += s.ny;
         windows += (long long)s.nx * s.ny;
         nsc++;
     }
     p.n_scales = nsc; p.blocks_per_frame = blocks; p.words_per_frame = words; p.rows_per_frame = rows; p.windows_per_frame = windows;
 
-    geom_out->assign((size_t)std::max(nsc, 1) * h->total_weak, ScGeom{0, 0, 0, 0});
+    ScGeom zero_geom;
+    memset(&zero_geom, 0, sizeof(zero_geom));
+    geom_out->assign((size_t)std::max(nsc, 1) * h->total_weak, zero_geom);
     for (int i = 0; i < nsc; i++)
         for (int k = 0; k < h->total_weak; k++)
-            if (!sc_host::project_geom(h->tmpl, p.sc[i].l, h->rects[k], p.pitch, &(*geom_out)[(size_t)i * h->total_weak + k]))
+            if (!sc_host::project_geom(h->tmpl, p.sc[i].l, h->rects[k], p.lay, &(*geom_out)[(size_t)i * h->total_weak + k]))
                 return fail(h, SC_ERR_INVALID, "weak classifier patch is not 2x2 / 4x1 / 1x4 cells after projection");
     return SC_OK;
 }
@@ -235,7 +242,7 @@ size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 int ensure_group_buffers(sc_handle* h, int want_frames, bool own_images) {
     const ScPlan& p = h->plan;
     const size_t per_rec = sizeof(ScRecord) + 2 * sizeof(uint32_t);
-    const size_t per_frame = (size_t)p.frame_stride4 * 16 + (size_t)p.windows_per_frame * per_rec + (size_t)p.words_per_frame * 12 +
+    const size_t per_frame = (size_t)p.lay.frame4 * 16 + (size_t)p.windows_per_frame * per_rec + (size_t)p.words_per_frame * 12 +
                              (size_t)p.H * p.n_strips * 32 + (size_t)p.W * p.H;
     int g = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)6 << 30) / std::max<size_t>(per_frame, 1)));
     g = std::min(g, std::max(want_frames, 1));
@@ -244,7 +251,7 @@ int ensure_group_buffers(sc_handle* h, int want_frames, bool own_images) {
     if (recs > 0xfffffff0ull) return fail(h, SC_ERR_INVALID, "too many windows per group");
     if (own_images) SC_CUDA(h, h->d_img.ensure(align256((size_t)g * p.W * p.H)));
     SC_CUDA(h, h->d_carry.ensure(align256((size_t)g * p.H * p.n_strips * 32)));
-    SC_CUDA(h, h->d_S.ensure((size_t)g * p.frame_stride4 * 16));
+    SC_CUDA(h, h->d_S.ensure((size_t)g * p.lay.frame4 * 16));
     SC_CUDA(h, h->d_multi.ensure(align256((size_t)g * p.words_per_frame * 4 + 4)));
     SC_CUDA(h, h->d_pass.ensure(align256((size_t)g * p.words_per_frame * 4 + 4)));
     SC_CUDA(h, h->d_visited.ensure(align256((size_t)g * p.words_per_frame * 4 + 4)));
@@ -270,7 +277,7 @@ int run_group(sc_handle* h, const uint8_t* d_img, int g, int frame0, sc_detectio
         const int rows = g * p.H;
         { KernelSpan ks(h, K_CARRY); sck::k_strip_carry<<<(rows + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, g, h->d_carry.as<int>()); }
         const int warps = g * p.n_strips;
-        { KernelSpan ks(h, K_WALK); sck::k_integral_walk<<<(warps + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, g, h->d_carry.as<int>(), S, p.frame_stride4); }
+        { KernelSpan ks(h, K_WALK); sck::k_integral_walk<<<(warps + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, g, h->d_carry.as<int>(), S, p.lay); }
     }
     if (p.n_scales > 0 && p.n_stages > 0) {
         const ScGeom* geom = h->d_geom.as<ScGeom>();
@@ -354,7 +361,7 @@ void sc_destroy(sc_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     DevBuf* bufs[] = {&h->d_w, &h->d_wb, &h->d_plan, &h->d_geom, &h->d_img, &h->d_carry, &h->d_S, &h->d_multi, &h->d_pass, &h->d_visited,
-                      &h->d_rec, &h->d_idx[0], &h->d_idx[1], &h->d_small, &h->d_counters, &h->d_det};
+                      &h->d_rec, &h->d_idx[0], &h->d_idx[1], &h->d_small, &h->d_counters, &h->d_det, &h->d_hook_img, &h->d_hook_carry, &h->d_hook_S};
     for (DevBuf* b : bufs) b->release();
     h->h_stage.release();
     for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -434,21 +441,32 @@ int sc_integral(sc_handle* h, const uint8_t* gray, int W, int H, int stride, flo
     SC_CUDA(h, cudaSetDevice(h->device));
     h->have_integral = false;
     const int n_strips = (W + SC_STRIP - 1) / SC_STRIP;
-    const size_t frame_bytes = align256((size_t)(H + 1) * (W + 1) * 32);
-    // the parity hooks share the group buffers; a plan sized for another frame is dropped
-    if (h->have_plan && (h->plan.W != W || h->plan.H != H)) { h->have_plan = false; h->group_frames = 0; }
-    SC_CUDA(h, h->d_img.ensure(align256((size_t)W * H)));
-    SC_CUDA(h, h->d_carry.ensure(align256((size_t)H * n_strips * 32)));
-    SC_CUDA(h, h->d_S.ensure(frame_bytes));
-    SC_CUDA(h, cudaMemcpy2DAsync(h->d_img.p, W, gray, stride, W, H, cudaMemcpyHostToDevice, h->stream));
-    sck::k_strip_carry<<<(H + 3) / 4, 128, 0, h->stream>>>(h->d_img.as<uint8_t>(), W, H, n_strips, 1, h->d_carry.as<int>());
-    sck::k_integral_walk<<<(n_strips + 3) / 4, 128, 0, h->stream>>>(h->d_img.as<uint8_t>(), W, H, n_strips, 1, h->d_carry.as<int>(),
-                                                                      h->d_S.as<float4>(), (long long)(frame_bytes / 16));
+    // the hooks keep their own single-frame integral in the step-1 layout (explicit rects sit on any pixel)
+    const ScLayout L = sc_host::make_layout(W, H, 1);
+    SC_CUDA(h, h->d_hook_img.ensure(align256((size_t)W * H)));
+    SC_CUDA(h, h->d_hook_carry.ensure(align256((size_t)H * n_strips * 32)));
+    SC_CUDA(h, h->d_hook_S.ensure((size_t)L.frame4 * 16));
+    SC_CUDA(h, cudaMemcpy2DAsync(h->d_hook_img.p, W, gray, stride, W, H, cudaMemcpyHostToDevice, h->stream));
+    sck::k_strip_carry<<<(H + 3) / 4, 128, 0, h->stream>>>(h->d_hook_img.as<uint8_t>(), W, H, n_strips, 1, h->d_hook_carry.as<int>());
+    sck::k_integral_walk<<<(n_strips + 3) / 4, 128, 0, h->stream>>>(h->d_hook_img.as<uint8_t>(), W, H, n_strips, 1, h->d_hook_carry.as<int>(),
+                                                                      h->d_hook_S.as<float4>(), L);
     h->launches += 2;
     SC_CUDA(h, cudaGetLastError());
-    if (out) SC_CUDA(h, cudaMemcpyAsync(out, h->d_S.p, (size_t)(H + 1) * (W + 1) * 32, cudaMemcpyDeviceToHost, h->stream));
+    if (out) {
+        // hand the caller the reference's interleaved (H+1) x (W+1) x 8 image
+        DevBuf d_out;
+        const size_t bytes = (size_t)(H + 1) * (W + 1) * 32;
+        SC_CUDA(h, d_out.ensure(bytes));
+        sck::k_export_integral<<<h->n_sms * 8, 256, 0, h->stream>>>(h->d_hook_S.as<float4>(), L, W, H, d_out.as<float4>());
+        h->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out.p, bytes, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        d_out.release();
+        if (e != cudaSuccess) return cuda_fail(h, e, "sc_integral export");
+    }
     SC_CUDA(h, cudaStreamSynchronize(h->stream));
-    h->have_integral = true; h->cur_W = W; h->cur_H = H;
+    h->have_integral = true; h->cur_W = W; h->cur_H = H; h->hook_lay = L;
     return SC_OK;
 }
 
@@ -468,7 +486,7 @@ static int features_impl(sc_handle* h, const sc_rect* rects, int n, float* out, 
     SC_CUDA(h, cudaMemcpyAsync(d_r.p, rects, (size_t)n * sizeof(sc_rect), cudaMemcpyHostToDevice, h->stream));
     if (out) SC_CUDA(h, d_o.ensure((size_t)n * 32 * sizeof(float)));
     if (sums) SC_CUDA(h, d_s.ensure((size_t)n * sizeof(float)));
-    sck::k_features<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_S.as<float4>(), h->cur_W + 1, d_r.as<int4>(), n, d_o.as<float>(), d_s.as<float>());
+    sck::k_features<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_hook_S.as<float4>(), h->hook_lay, d_r.as<int4>(), n, d_o.as<float>(), d_s.as<float>());
     h->launches++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && out) e = cudaMemcpyAsync(out, d_o.p, (size_t)n * 32 * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
@@ -494,12 +512,12 @@ int sc_stage_scores(sc_handle* h, const int32_t* wins, int n, float* out) {
         const int x = wins[3 * i], y = wins[3 * i + 1], l = wins[3 * i + 2];
         if (x < 0 || y < 0 || l < 1 || x + l > W || y + l > H) return fail(h, SC_ERR_INVALID, "window outside the image");
         for (int k = 0; k < tw; k++)
-            if (!sc_host::project_geom(h->tmpl, l, h->rects[k], W + 1, &geom[(size_t)i * tw + k]))
+            if (!sc_host::project_geom(h->tmpl, l, h->rects[k], h->hook_lay, &geom[(size_t)i * tw + k]))
                 return fail(h, SC_ERR_INVALID, "degenerate projected patch");
     }
     ScPlan mini;
     memset(&mini, 0, sizeof(mini));
-    mini.W = W; mini.H = H; mini.pitch = W + 1; mini.n_stages = h->n_stages; mini.total_weak = tw;
+    mini.W = W; mini.H = H; mini.lay = h->hook_lay; mini.n_stages = h->n_stages; mini.total_weak = tw;
     for (int s = 0; s < h->n_stages; s++) { mini.theta[s] = h->theta[s]; mini.n_weak[s] = h->n_weak[s]; mini.weak_base[s] = h->weak_base[s]; }
     DevBuf d_p, d_g, d_w, d_o;
     cudaError_t e = d_p.ensure(sizeof(ScPlan));
@@ -510,7 +528,7 @@ int sc_stage_scores(sc_handle* h, const int32_t* wins, int n, float* out) {
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_g.p, geom.data(), geom.size() * sizeof(ScGeom), cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_w.p, wins, (size_t)n * 3 * sizeof(int), cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess) {
-        sck::k_stage_scores<<<(n + 63) / 64, 64, 0, h->stream>>>(d_p.as<ScPlan>(), h->d_S.as<float4>(), d_g.as<ScGeom>(), h->d_w.as<float>(),
+        sck::k_stage_scores<<<(n + 63) / 64, 64, 0, h->stream>>>(d_p.as<ScPlan>(), h->d_hook_S.as<float4>(), d_g.as<ScGeom>(), h->d_w.as<float>(),
                                                                   h->d_wb.as<double>(), d_w.as<int>(), n, d_o.as<float>());
         h->launches++;
         e = cudaGetLastError();
@@ -573,7 +591,6 @@ int sc_detect_device(sc_handle* h, const uint8_t* d_frames, int nframes, int W, 
     if (rc != SC_OK) return rc;
     rc = ensure_group_buffers(h, nframes, false);
     if (rc != SC_OK) return rc;
-    h->have_integral = false;
     SC_CUDA(h, h->d_counters.ensure((size_t)nframes * SC_CNT_STRIDE * 8));
     SC_CUDA(h, cudaMemsetAsync(h->d_counters.p, 0, (size_t)nframes * SC_CNT_STRIDE * 8, h->stream));
     SC_CUDA(h, cudaMemsetAsync(d_n, 0, 4, h->stream));
@@ -629,7 +646,6 @@ int sc_detect(sc_handle* h, const uint8_t* const* frames, int nframes, int W, in
     rc = ensure_group_buffers(h, nframes, true);
     if (rc != SC_OK) return rc;
     if (h->d_img.cap < (size_t)h->group_frames * W * H) SC_CUDA(h, h->d_img.ensure(align256((size_t)h->group_frames * W * H)));
-    h->have_integral = false;
     const uint32_t det_cap = (uint32_t)std::min<size_t>(std::max<size_t>(cap, 1), 0xffffffffu);
     SC_CUDA(h, h->d_det.ensure((size_t)det_cap * sizeof(sc_detection)));
     SC_CUDA(h, h->d_counters.ensure((size_t)nframes * SC_CNT_STRIDE * 8));

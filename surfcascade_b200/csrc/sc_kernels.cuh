@@ -3,8 +3,8 @@
 //   k_strip_carry      per (frame,row): exact int32 row-prefix of the 8 gradient channels at every 32-column
 //                      strip boundary (REDUX warp sums of packed channel pairs)
 //   k_integral_walk    one warp per (frame,strip): fused gradient + channel + packed warp-shuffle row scan, then the
-//                      reference's SEQUENTIAL float32 column recurrence, writing the channel-interleaved 32 B/pixel
-//                      integral with two 16 B stores per lane (1 KB contiguous per warp per row)
+//                      reference's SEQUENTIAL float32 column recurrence, stored in the lattice-deinterleaved,
+//                      half-split layout (sc_plan.h) with two 16 B stores per lane
 //   k_scan_stage0      64x16-window tiles: prefilter -> in-block compaction (ballot + shared prefix) -> stage 0 on
 //                      the dense survivor list -> warp-aggregated push of survivors, multi/prefilter bitmasks
 //   k_scan_stage       stages 1..N-1 on the compacted survivor index lists (ballot + atomic prefix between stages)
@@ -83,8 +83,7 @@ __global__ void __launch_bounds__(128) k_strip_carry(const uint8_t* __restrict__
 // One warp per (frame, strip).  S[y+1][x+1][c] = fl32(S[y][x+1][c] + float(rowprefix)), sequential in y
 // (cv::integral u8->f32 as called at DenseSURFFeatureExtractor.cpp:75).
 __global__ void __launch_bounds__(128) k_integral_walk(const uint8_t* __restrict__ img, int W, int H, int n_strips, int nframes,
-                                                        const int* __restrict__ carry, float4* __restrict__ S,
-                                                        long long frame_stride4) {
+                                                        const int* __restrict__ carry, float4* __restrict__ S, const ScLayout L) {
     const int lane = threadIdx.x & 31;
     const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (wid >= nframes * n_strips) return;
@@ -93,20 +92,20 @@ __global__ void __launch_bounds__(128) k_integral_walk(const uint8_t* __restrict
     const int x = s * SC_STRIP + lane;
     const bool valid = x < W;
     const int xc = min(x, W - 1), xp = max(xc - 1, 0), xn = min(xc + 1, W - 1);
-    const int pitch = W + 1;
-    float4* out = S + (size_t)f * frame_stride4 + (size_t)(x + 1) * 2;   // column x+1 of row 0
+    float4* Sf = S + (size_t)f * L.frame4;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) { out[0] = zero; out[1] = zero; }
-    if (s == 0 && lane == 0) {                                            // column 0 of every row
-        float4* c0 = S + (size_t)f * frame_stride4;
-        for (int y = 0; y <= H; y++) { c0[(size_t)y * pitch * 2] = zero; c0[(size_t)y * pitch * 2 + 1] = zero; }
-    }
+    // this lane's integral column X = x + 1: in-plane column and the plane column residue are fixed
+    const int X = x + 1, px = X / L.step, rx = X - px * L.step;
+    if (valid) { float4* o = Sf + (size_t)rx * 2 * L.hps4 + px; o[0] = zero; o[L.hps4] = zero; }   // row Y = 0
+    if (s == 0 && lane == 0)                                                                       // column X = 0
+        for (int Y = 0; Y <= H; Y++) { float4* o = Sf + sc_layout_index(L, 0, Y); o[0] = zero; o[L.hps4] = zero; }
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const int4* cr = reinterpret_cast<const int4*>(carry + (((size_t)f * H) * n_strips + s) * 8);
     const size_t cr_step = (size_t)n_strips * 2;
     Row3 prev = load_row3(base, xp, xc, xn), cur = prev;
     Row3 next = load_row3(base + (size_t)min(1, H - 1) * W, xp, xc, xn);
     int4 c_lo = __ldg(cr), c_hi = __ldg(cr + 1);
+    int py = 0, ry = 0;  // plane row / residue of Y = y + 1, advanced incrementally
     for (int y = 0; y < H; y++) {
         // prefetch the next iteration's inputs before the dependent shuffle chain
         const Row3 nn = load_row3(base + (size_t)min(y + 2, H - 1) * W, xp, xc, xn);
@@ -129,12 +128,24 @@ __global__ void __launch_bounds__(128) k_integral_walk(const uint8_t* __restrict
             acc[2 * k] = __fadd_rn(acc[2 * k], (float)(cy[2 * k] + (int)(p[k] & 0xffffu)));
             acc[2 * k + 1] = __fadd_rn(acc[2 * k + 1], (float)(cy[2 * k + 1] + (int)(p[k] >> 16)));
         }
-        out += (size_t)pitch * 2;
+        if (++ry == L.step) { ry = 0; py++; }
         if (valid) {
-            out[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            out[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            float4* o = Sf + (size_t)(ry * L.step + rx) * 2 * L.hps4 + (size_t)py * L.ppitch + px;
+            o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            o[L.hps4] = make_float4(acc[4], acc[5], acc[6], acc[7]);
         }
         prev = cur; cur = next; next = nn; c_lo = n_lo; c_hi = n_hi;
+    }
+}
+
+// Layout -> the reference's interleaved (H+1) x (W+1) x 8 float image (parity hook output of sc_integral).
+__global__ void k_export_integral(const float4* __restrict__ S, const ScLayout L, int W, int H, float4* __restrict__ out) {
+    const int n = (W + 1) * (H + 1);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int Y = i / (W + 1), X = i - Y * (W + 1);
+        const float4* p = S + sc_layout_index(L, X, Y);
+        out[2 * (size_t)i] = p[0];
+        out[2 * (size_t)i + 1] = p[L.hps4];
     }
 }
 
@@ -143,8 +154,8 @@ __global__ void __launch_bounds__(128) k_integral_walk(const uint8_t* __restrict
 // ---------------------------------------------------------------------------------------------------------
 struct Px { float v[8]; };
 
-__device__ __forceinline__ Px load_px(const float4* __restrict__ S4, int pix) {
-    const float4 lo = __ldg(S4 + 2 * (size_t)pix), hi = __ldg(S4 + 2 * (size_t)pix + 1);
+__device__ __forceinline__ Px load_px(const float4* __restrict__ lo4, const float4* __restrict__ hi4, int idx) {
+    const float4 lo = __ldg(lo4 + idx), hi = __ldg(hi4 + idx);
     Px p;
     p.v[0] = lo.x; p.v[1] = lo.y; p.v[2] = lo.z; p.v[3] = lo.w; p.v[4] = hi.x; p.v[5] = hi.y; p.v[6] = hi.z; p.v[7] = hi.w;
     return p;
@@ -156,38 +167,38 @@ __device__ __forceinline__ void cell_sum(const Px& A, const Px& B, const Px& C, 
     for (int c = 0; c < 8; c++) v[c] = __fsub_rn(__fadd_rn(A.v[c], D.v[c]), __fadd_rn(B.v[c], C.v[c]));
 }
 
-// hadd-ordered sum of squares seeded with FLT_EPSILON in lane 3, Normalize :427-433 / :441-451
+// Sum of squares in the order of Normalize's hadd chain (:427-433 / :441-451).  Unrolling
+//   s = (0,0,0,eps);  s <- hadd(s, q_g) for g = 0..7;  s <- hadd(s,s) twice
+// gives  ((((((((eps + c0) + c1) + c2) + c3) + c4) + c5) + c6) + c7)  with  c_g = (q0 + q1) + (q2 + q3)  of group g.
 __device__ __forceinline__ float sumsq_hadd(const float* v) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = FLT_EPSILON;
+    float s = FLT_EPSILON;
 #pragma unroll
     for (int g = 0; g < 8; g++) {
         const float q0 = __fmul_rn(v[4 * g], v[4 * g]), q1 = __fmul_rn(v[4 * g + 1], v[4 * g + 1]);
         const float q2 = __fmul_rn(v[4 * g + 2], v[4 * g + 2]), q3 = __fmul_rn(v[4 * g + 3], v[4 * g + 3]);
-        const float n0 = __fadd_rn(s0, s1), n1 = __fadd_rn(s2, s3), n2 = __fadd_rn(q0, q1), n3 = __fadd_rn(q2, q3);
-        s0 = n0; s1 = n1; s2 = n2; s3 = n3;
+        s = __fadd_rn(s, __fadd_rn(__fadd_rn(q0, q1), __fadd_rn(q2, q3)));
     }
-    return __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
+    return s;
 }
 
-// CalcFeature + Normalize for one projected patch at window-origin pixel `org`.
-__device__ __forceinline__ void descriptor(const float4* __restrict__ S4, int org, const ScGeom g, float* v) {
-    const int p0 = org + g.off;
+// CalcFeature + Normalize for one projected patch; `org` = layout index of the window origin.
+__device__ __forceinline__ void descriptor(const float4* __restrict__ lo4, const float4* __restrict__ hi4, int org, const ScGeom& g, float* v) {
     if (g.shape == 0) {
         // 3 x 3 corner lattice, cells row-major (GetRectsFromPatch :360-377)
-        Px a0 = load_px(S4, p0), a1 = load_px(S4, p0 + g.along), a2 = load_px(S4, p0 + 2 * g.along);
-        Px b0 = load_px(S4, p0 + g.across), b1 = load_px(S4, p0 + g.across + g.along), b2 = load_px(S4, p0 + g.across + 2 * g.along);
+        Px a0 = load_px(lo4, hi4, org + g.c[0]), a1 = load_px(lo4, hi4, org + g.c[1]), a2 = load_px(lo4, hi4, org + g.c[2]);
+        const Px b0 = load_px(lo4, hi4, org + g.c[3]), b1 = load_px(lo4, hi4, org + g.c[4]), b2 = load_px(lo4, hi4, org + g.c[5]);
         cell_sum(a0, a1, b0, b1, v);
         cell_sum(a1, a2, b1, b2, v + 8);
-        a0 = load_px(S4, p0 + 2 * g.across); a1 = load_px(S4, p0 + 2 * g.across + g.along); a2 = load_px(S4, p0 + 2 * g.across + 2 * g.along);
+        a0 = load_px(lo4, hi4, org + g.c[6]); a1 = load_px(lo4, hi4, org + g.c[7]); a2 = load_px(lo4, hi4, org + g.c[8]);
         cell_sum(b0, b1, a0, a1, v + 16);
         cell_sum(b1, b2, a1, a2, v + 24);
     } else {
-        // 2 x 5 corner lattice: four cells chained along `along` (4x1 wide or 1x4 tall; B and C swap roles
+        // 2 x 5 corner lattice: four cells chained along the long side (4x1 wide or 1x4 tall; B and C swap roles
         // between the two, and fl(B + C) == fl(C + B))
-        Px t0 = load_px(S4, p0), u0 = load_px(S4, p0 + g.across);
+        Px t0 = load_px(lo4, hi4, org + g.c[0]), u0 = load_px(lo4, hi4, org + g.c[5]);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const Px t1 = load_px(S4, p0 + (k + 1) * g.along), u1 = load_px(S4, p0 + (k + 1) * g.along + g.across);
+            const Px t1 = load_px(lo4, hi4, org + g.c[k + 1]), u1 = load_px(lo4, hi4, org + g.c[k + 6]);
             cell_sum(t0, t1, u0, u1, v + 8 * k);
             t0 = t1; u0 = u1;
         }
@@ -219,21 +230,23 @@ __device__ __forceinline__ float weak_predict(const float* v, const float* __res
 }
 
 // GentleAdaboost::Predict2 (GentleAdaboost.cpp:247-261) of one stage on one window.
-__device__ __forceinline__ float stage_score(const float4* __restrict__ S4, int org, const ScGeom* __restrict__ geom,
-                                             const float* __restrict__ w, const double* __restrict__ wb, int n_weak) {
+__device__ __forceinline__ float stage_score(const float4* __restrict__ lo4, const float4* __restrict__ hi4, int org,
+                                             const ScGeom* __restrict__ geom, const float* __restrict__ w, const double* __restrict__ wb,
+                                             int n_weak) {
     float acc = 0.f;
     for (int q = 0; q < n_weak; q++) {
         float v[32];
-        descriptor(S4, org, geom[q], v);
+        descriptor(lo4, hi4, org, geom[q], v);
         acc = __fadd_rn(acc, weak_predict(v, w + q * SC_W_PITCH, wb[q]));
     }
     return __fdiv_rn(acc, (float)n_weak);
 }
 
-// DenseSURFFeatureExtractor::sum (:351-358) and the compare at ObjDetector.cpp:188
-__device__ __forceinline__ float window_sum(const float4* __restrict__ S4, int org, int dx, int dy) {
-    const float4 a = __ldg(S4 + 2 * (size_t)org), b = __ldg(S4 + 2 * (size_t)(org + dx));
-    const float4 c = __ldg(S4 + 2 * (size_t)(org + dy)), d = __ldg(S4 + 2 * (size_t)(org + dy + dx));
+// DenseSURFFeatureExtractor::sum (:351-358) and the compare at ObjDetector.cpp:188; pf = layout offsets of the corners
+// (0,0) (l,0) (0,l) (l,l)
+__device__ __forceinline__ float window_sum(const float4* __restrict__ lo4, int org, const int* pf) {
+    const float4 a = __ldg(lo4 + org + pf[0]), b = __ldg(lo4 + org + pf[1]);
+    const float4 c = __ldg(lo4 + org + pf[2]), d = __ldg(lo4 + org + pf[3]);
     const float s0 = __fsub_rn(__fadd_rn(a.x, d.x), __fadd_rn(b.x, c.x));
     const float s1 = __fsub_rn(__fadd_rn(a.y, d.y), __fadd_rn(b.y, c.y));
     const float s2 = __fsub_rn(__fadd_rn(a.z, d.z), __fadd_rn(b.z, c.z));
@@ -258,6 +271,7 @@ __global__ void __launch_bounds__(SC_TILE_THREADS) k_scan_stage0(const ScPlan* _
     __shared__ uint32_t s_pass[SC_TILE_Y][2];
     __shared__ uint16_t s_list[SC_TILE_X * SC_TILE_Y];
     __shared__ uint32_t s_count;
+    __shared__ ScScale s_sc;
     extern __shared__ __align__(16) unsigned char s_dyn[];  // stage-0 weights, wb, geometry
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -265,44 +279,43 @@ __global__ void __launch_bounds__(SC_TILE_THREADS) k_scan_stage0(const ScPlan* _
     const int b = blockIdx.x - f * plan->blocks_per_frame;
     int si = 0;
     while (si + 1 < plan->n_scales && plan->sc[si + 1].block_base <= b) si++;
-    const ScScale sc = plan->sc[si];
-    const int tb = b - sc.block_base;
-    const int ty = tb / sc.tiles_x, tx = tb - ty * sc.tiles_x;
     const int n_weak = plan->n_weak[0], total_weak = plan->total_weak;
-    const int pitch = plan->pitch, step = plan->step;
-    const float4* S4 = S + (size_t)f * plan->frame_stride4;
+    const int ppitch = plan->lay.ppitch;
+    const float4* lo4 = S + (size_t)f * plan->lay.frame4;
+    const float4* hi4 = lo4 + plan->lay.hps4;
 
-    float* sw = reinterpret_cast<float*>(s_dyn);                                   // [n_weak][36]
+    float* sw = reinterpret_cast<float*>(s_dyn);                                       // [n_weak][36]
     double* swb = reinterpret_cast<double*>(s_dyn + (size_t)n_weak * SC_W_PITCH * 4);  // [n_weak]
-    ScGeom* sg = reinterpret_cast<ScGeom*>(swb + n_weak);                           // [n_weak]
+    ScGeom* sg = reinterpret_cast<ScGeom*>(swb + n_weak);                              // [n_weak]
     for (int i = tid; i < n_weak * SC_W_PITCH; i += SC_TILE_THREADS) sw[i] = w_all[i];
     for (int i = tid; i < n_weak; i += SC_TILE_THREADS) { swb[i] = wb_all[i]; sg[i] = geom_all[(size_t)si * total_weak + i]; }
-    if (tid == 0) s_count = 0;
+    if (tid == 0) { s_count = 0; s_sc = plan->sc[si]; }
     __syncthreads();
+    const int nx = s_sc.nx, ny = s_sc.ny;
+    const int tb = b - s_sc.block_base;
+    const int ty = tb / s_sc.tiles_x, tx = tb - ty * s_sc.tiles_x;
 
     // phase A: prefilter + compaction of the passing windows of this tile
+    {
+        const float thr = s_sc.thr;
+        const bool use_pf = plan->use_prefilter != 0;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int row = warp + 8 * (i >> 1), half = i & 1;
-        const int gx = tx * SC_TILE_X + half * 32 + lane, gy = ty * SC_TILE_Y + row;
-        const bool valid = gx < sc.nx && gy < sc.ny;
-        bool pass = false;
-        if (valid) {
-            pass = true;
-            if (plan->use_prefilter) {
-                const int org = gy * step * pitch + gx * step;
-                pass = window_sum(S4, org, sc.l, sc.l * pitch) > sc.thr;
+        for (int i = 0; i < 4; i++) {
+            const int row = warp + 8 * (i >> 1), half = i & 1;
+            const int gx = tx * SC_TILE_X + half * 32 + lane, gy = ty * SC_TILE_Y + row;
+            const bool valid = gx < nx && gy < ny;
+            bool pass = false;
+            if (valid) pass = use_pf ? (window_sum(lo4, gy * ppitch + gx, s_sc.pf) > thr) : true;
+            const uint32_t m = __ballot_sync(0xffffffffu, pass);
+            uint32_t base = 0;
+            if (lane == 0) {
+                s_pass[row][half] = m;
+                s_multi[row][half] = ~m;  // prefilter failed -> multi = 2 (ObjDetector.cpp:216-217)
+                base = atomicAdd(&s_count, __popc(m));
             }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pass) s_list[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)((row << 6) | (half << 5) | lane);
         }
-        const uint32_t m = __ballot_sync(0xffffffffu, pass);
-        uint32_t base = 0;
-        if (lane == 0) {
-            s_pass[row][half] = m;
-            s_multi[row][half] = ~m;  // prefilter failed -> multi = 2 (ObjDetector.cpp:216-217)
-            base = atomicAdd(&s_count, __popc(m));
-        }
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (pass) s_list[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)((row << 6) | (half << 5) | lane);
     }
     __syncthreads();
 
@@ -313,15 +326,14 @@ __global__ void __launch_bounds__(SC_TILE_THREADS) k_scan_stage0(const ScPlan* _
     const bool force = plan->force_all != 0;
     for (uint32_t i0 = 0; i0 < count; i0 += SC_TILE_THREADS) {
         const uint32_t i = i0 + tid;
-        const bool active = i < count;
         bool push = false;
         ScRecord r;
-        if (active) {
+        r.fs = 0; r.yx = 0; r.rej = 0; r.score = 0;
+        if (i < count) {
             const uint32_t code = s_list[i];
             const int row = code >> 6, half = (code >> 5) & 1, ln = code & 31;
             const int gx = tx * SC_TILE_X + half * 32 + ln, gy = ty * SC_TILE_Y + row;
-            const int org = gy * step * pitch + gx * step;
-            const float score = stage_score(S4, org, sg, sw, swb, n_weak);
+            const float score = stage_score(lo4, hi4, gy * ppitch + gx, sg, sw, swb, n_weak);
             const bool rejected = score < theta0;
             if (rejected && rejected_skips(score, 0, n_stages)) atomicOr(&s_multi[row][half], 1u << ln);
             push = !rejected || force;
@@ -347,8 +359,8 @@ __global__ void __launch_bounds__(SC_TILE_THREADS) k_scan_stage0(const ScPlan* _
     if (tid < SC_TILE_Y * 2) {
         const int row = tid >> 1, half = tid & 1;
         const int gy = ty * SC_TILE_Y + row, wx = tx * 2 + half;
-        if (gy < sc.ny && wx < sc.wpr) {
-            const size_t wi = (size_t)f * plan->words_per_frame + sc.word_base + (size_t)gy * sc.wpr + wx;
+        if (gy < ny && wx < s_sc.wpr) {
+            const size_t wi = (size_t)f * plan->words_per_frame + s_sc.word_base + (size_t)gy * s_sc.wpr + wx;
             multi_bits[wi] = s_multi[row][half];
             pass_bits[wi] = s_pass[row][half];
         }
@@ -372,7 +384,7 @@ __global__ void __launch_bounds__(128) k_scan_stage(const ScPlan* __restrict__ p
     for (int i = threadIdx.x; i < n_weak; i += blockDim.x) swb[i] = wb_all[wbase + i];
     __syncthreads();
     const uint32_t count = min(*in_count, cap);
-    const int n_stages = plan->n_stages, pitch = plan->pitch, step = plan->step;
+    const int n_stages = plan->n_stages, ppitch = plan->lay.ppitch;
     const bool force = plan->force_all != 0, last = stage == n_stages - 1;
     const float theta = plan->theta[stage];
     const int lane = threadIdx.x & 31;
@@ -386,16 +398,15 @@ __global__ void __launch_bounds__(128) k_scan_stage(const ScPlan* __restrict__ p
             ScRecord r = rec[idx];
             const int f = r.fs >> 8, si = r.fs & 0xff;
             const int gy = r.yx >> 16, gx = r.yx & 0xffff;
-            const int org = gy * step * pitch + gx * step;
-            const float4* S4 = S + (size_t)f * plan->frame_stride4;
-            const float score = stage_score(S4, org, geom_all + (size_t)si * total_weak + wbase, sw, swb, n_weak);
+            const float4* lo4 = S + (size_t)f * plan->lay.frame4;
+            const float score = stage_score(lo4, lo4 + plan->lay.hps4, gy * ppitch + gx, geom_all + (size_t)si * total_weak + wbase, sw, swb, n_weak);
             if (r.rej < 0) {
                 const bool rejected = score < theta;
                 if (rejected) {
                     r.rej = stage; r.score = __float_as_uint(score);
                     if (rejected_skips(score, stage, n_stages)) {
-                        const ScScale sc = plan->sc[si];
-                        atomicOr(&multi_bits[(size_t)f * plan->words_per_frame + sc.word_base + (size_t)gy * sc.wpr + (gx >> 5)], 1u << (gx & 31));
+                        const int word_base = plan->sc[si].word_base, wpr = plan->sc[si].wpr;
+                        atomicOr(&multi_bits[(size_t)f * plan->words_per_frame + word_base + (size_t)gy * wpr + (gx >> 5)], 1u << (gx & 31));
                     }
                     rec[idx] = r;
                 } else if (last) {
@@ -434,13 +445,13 @@ __global__ void __launch_bounds__(128) k_replay_rows(const ScPlan* __restrict__ 
         const int r = t - f * rows;
         int si = 0;
         while (si + 1 < plan->n_scales && plan->sc[si + 1].row_base <= r) si++;
-        const ScScale sc = plan->sc[si];
-        const size_t w0 = (size_t)f * plan->words_per_frame + sc.word_base + (size_t)(r - sc.row_base) * sc.wpr;
+        const int wpr = plan->sc[si].wpr, nx = plan->sc[si].nx;
+        const size_t w0 = (size_t)f * plan->words_per_frame + plan->sc[si].word_base + (size_t)(r - plan->sc[si].row_base) * wpr;
         const bool skip = plan->skip_rule != 0;
         int pos = 0;
-        for (int wi = 0; wi < sc.wpr; wi++) {
+        for (int wi = 0; wi < wpr; wi++) {
             const uint32_t m = multi_bits[w0 + wi], pm = pass_bits[w0 + wi];
-            const int end = min(32 * (wi + 1), sc.nx);
+            const int end = min(32 * (wi + 1), nx);
             uint32_t v = 0;
             if (skip) {
                 while (pos < end) {
@@ -457,8 +468,7 @@ __global__ void __launch_bounds__(128) k_replay_rows(const ScPlan* __restrict__ 
             npass += __popc(v & pm);
         }
     }
-    // block-level reduction is only valid when the whole block shares a frame; rows_per_frame is not a multiple
-    // of the block size, so reduce per warp with a frame-uniformity check
+    // one atomic per warp when the whole warp works on the same frame, else one per thread
     const uint32_t same = __match_any_sync(0xffffffffu, f);
     if (same == 0xffffffffu) {
         for (int d = 16; d > 0; d >>= 1) {
@@ -494,9 +504,9 @@ __global__ void __launch_bounds__(128) k_finalize(const ScPlan* __restrict__ pla
         if (i < count) {
             const ScRecord r = rec[i];
             f = r.fs >> 8;
-            const ScScale sc = plan->sc[r.fs & 0xff];
-            gy = r.yx >> 16; gx = r.yx & 0xffff; l = sc.l;
-            const uint32_t v = visited_bits[(size_t)f * plan->words_per_frame + sc.word_base + (size_t)gy * sc.wpr + (gx >> 5)];
+            const int si = r.fs & 0xff;
+            gy = r.yx >> 16; gx = r.yx & 0xffff; l = plan->sc[si].l;
+            const uint32_t v = visited_bits[(size_t)f * plan->words_per_frame + plan->sc[si].word_base + (size_t)gy * plan->sc[si].wpr + (gx >> 5)];
             vis = (v >> (gx & 31)) & 1u;
             reached = r.rej < 0 ? n_stages : r.rej;  // stages 0..min(reached, n_stages-1) were entered
             score = __uint_as_float(r.score);
@@ -523,37 +533,50 @@ __global__ void __launch_bounds__(128) k_finalize(const ScPlan* __restrict__ pla
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Parity hooks on explicit rect / window lists
+// Parity hooks on explicit rect / window lists (layout step 1)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void k_features(const float4* __restrict__ S4, int pitch, const int4* __restrict__ rects, int n, float* __restrict__ out,
+__global__ void k_features(const float4* __restrict__ S, const ScLayout L, const int4* __restrict__ rects, int n, float* __restrict__ out,
                            float* __restrict__ sums) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int4 r = rects[i];  // x, y, w, h
+    const int pitch = L.ppitch;
     const int org = r.y * pitch + r.x;
-    if (sums) sums[i] = window_sum(S4, org, r.z, r.w * pitch);
+    const float4* hi4 = S + L.hps4;
+    if (sums) {
+        const int pf[4] = {0, r.z, r.w * pitch, r.w * pitch + r.z};
+        sums[i] = window_sum(S, org, pf);
+    }
     if (out) {
         ScGeom g;
-        g.off = 0;
-        if (r.z == r.w) { const int ce = r.z / 2; g.shape = 0; g.along = ce; g.across = ce * pitch; }
-        else if (r.z > r.w) { g.shape = 1; g.along = r.w; g.across = r.w * pitch; }
-        else { g.shape = 1; g.along = r.z * pitch; g.across = r.z; }
+        if (r.z == r.w) {
+            const int ce = r.z / 2;
+            g.shape = 0;
+            for (int b = 0; b < 3; b++)
+                for (int a = 0; a < 3; a++) g.c[3 * b + a] = b * ce * pitch + a * ce;
+            g.c[9] = 0;
+        } else {
+            const int ce = min(r.z, r.w);
+            const int along = r.z > r.w ? ce : ce * pitch, across = r.z > r.w ? ce * pitch : ce;
+            g.shape = 1;
+            for (int k = 0; k < 5; k++) { g.c[k] = k * along; g.c[5 + k] = k * along + across; }
+        }
         float v[32];
-        descriptor(S4, org, g, v);
+        descriptor(S, hi4, org, g, v);
         for (int k = 0; k < 32; k++) out[(size_t)i * 32 + k] = v[k];
     }
 }
 
-__global__ void k_stage_scores(const ScPlan* __restrict__ plan, const float4* __restrict__ S4, const ScGeom* __restrict__ geom_win,
+__global__ void k_stage_scores(const ScPlan* __restrict__ plan, const float4* __restrict__ S, const ScGeom* __restrict__ geom_win,
                                const float* __restrict__ w_all, const double* __restrict__ wb_all, const int* __restrict__ wins, int n,
                                float* __restrict__ out) {
-    // geom_win: [n][total_weak] geometry projected for each explicit window's side (host-built)
+    // geom_win: [n][total_weak] geometry projected for each explicit window's side (host-built, layout step 1)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int org = wins[3 * i + 1] * plan->pitch + wins[3 * i];
+    const int org = wins[3 * i + 1] * plan->lay.ppitch + wins[3 * i];
     for (int s = 0; s < plan->n_stages; s++) {
         const int wb = plan->weak_base[s];
-        out[(size_t)i * plan->n_stages + s] = stage_score(S4, org, geom_win + (size_t)i * plan->total_weak + wb,
+        out[(size_t)i * plan->n_stages + s] = stage_score(S, S + plan->lay.hps4, org, geom_win + (size_t)i * plan->total_weak + wb,
                                                           w_all + (size_t)wb * SC_W_PITCH, wb_all + wb, plan->n_weak[s]);
     }
 }

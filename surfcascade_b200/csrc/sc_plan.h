@@ -16,6 +16,21 @@
 // Integral strips: one warp walks one 32-column strip down the frame.
 #define SC_STRIP 32
 
+// Integral-image layout in HBM ("lattice-deinterleaved, half-split"):
+//   the reference keeps 8 interleaved floats (32 B) per pixel; a warp of 32 neighbouring windows on a step-s
+//   lattice would then touch 32 sectors in 16 cache lines per 16-byte load.  Here pixel (X, Y) lives in plane
+//   (Y mod s, X mod s) at (Y div s, X div s), and every plane is stored as two float4 half-planes (channels 0-3,
+//   channels 4-7).  Neighbouring lattice windows read neighbouring float4s: one corner fetch of a warp is two
+//   fully coalesced 512-byte loads.  s = lattice step for detection plans, 1 for the explicit-rect hooks.
+struct ScLayout {
+    int step;              // s
+    int ppitch;            // float4 elements per plane row   = roundup(ceil((W+1)/s), 8)
+    int prows;             // plane rows                      = ceil((H+1)/s)
+    int pad;
+    long long hps4;        // float4 elements per half-plane  = ppitch * prows
+    long long frame4;      // float4 elements per frame       = s*s*2*hps4 rounded up to 16
+};
+
 struct ScScale {
     int l;            // window side (int)(base * scale^i), ObjDetector.cpp:180
     int nx, ny;       // window origins per row / rows on the step lattice
@@ -25,11 +40,12 @@ struct ScScale {
     int block_base;   // first stage-0 CTA of this scale inside a frame
     int word_base;    // first bitmask word of this scale inside a frame
     int row_base;     // first lattice row of this scale inside a frame (replay threads)
-    int pad;
+    int pf[4];        // layout offsets of the prefilter corners (0,0) (l,0) (0,l) (l,l) relative to the window origin
+    int pad[3];
 };
 
 struct ScPlan {
-    int W, H, pitch;              // pitch = W + 1 integral pixels per row
+    int W, H;
     int step;
     int n_scales;
     int n_stages;
@@ -39,27 +55,28 @@ struct ScPlan {
     int words_per_frame;          // bitmask words per frame
     int rows_per_frame;           // lattice rows per frame (all scales)
     int n_strips;                 // ceil(W / 32)
+    int pad0;
     long long windows_per_frame;  // grid windows per frame
-    long long frame_stride4;      // float4 elements between consecutive frames' integrals
+    ScLayout lay;
     float theta[SC_PLAN_MAX_STAGES];
     int n_weak[SC_PLAN_MAX_STAGES];
     int weak_base[SC_PLAN_MAX_STAGES];
-    // multi == 2 for a window rejected at stage p with score s  <=>  ((double)s + p + 1) / n_stages < 0.5
     ScScale sc[SC_PLAN_MAX_SCALES];
 };
 
-// Per (scale, weak classifier) projected geometry, relative to the window origin, in integral pixels.
-//   off    = oy * pitch + ox           first corner
-//   along  = pixel stride between consecutive corners along the cell chain (square: ce; wide: ce; tall: ce * pitch)
-//   across = pixel stride to the second line of corners                    (square: ce * pitch; wide: ce * pitch; tall: ce)
-//   shape  = 0 square 2x2 (3 x 3 corners), 1 long 4x1 / 1x4 (2 x 5 corners)
+// Per (scale, weak classifier) projected geometry: layout offsets (float4 units, low half) of the patch's corner
+// lattice relative to the window origin's layout index.
+//   shape 0, square 2x2 cells: c[3*b + a], a, b in 0..2   (corner (ox + a*ce, oy + b*ce))
+//   shape 1, long 4x1 / 1x4  : c[k] first line, c[5 + k] second line, k in 0..4 along the cell chain
 struct ScGeom {
-    int off, along, across, shape;
+    int c[10];
+    int shape;
+    int pad;
 };
 
 // Device record of a window that passed stage 0 (or of every window in force_all mode).
-//   x: frame << 8 | scale      y: gy << 16 | gx (lattice coordinates)
-//   z: stage that rejected it (n_stages = passed all, -1 = still alive)     w: float bits of the score at that stage
+//   fs: frame << 8 | scale      yx: gy << 16 | gx (lattice coordinates)
+//   rej: stage that rejected it (n_stages = passed all, -1 = still alive)     score: float bits of that stage's score
 struct ScRecord {
     uint32_t fs, yx;
     int32_t rej;
@@ -67,5 +84,17 @@ struct ScRecord {
 };
 
 enum { SC_CNT_VISITED = 0, SC_CNT_PREFILTER = 1, SC_CNT_RAW = 2, SC_CNT_REACH0 = 3, SC_CNT_STRIDE = 3 + SC_PLAN_MAX_STAGES };
+
+#ifdef __CUDACC__
+#define SC_HD __host__ __device__ __forceinline__
+#else
+#define SC_HD inline
+#endif
+
+// layout index (float4 units, low half) of integral pixel (X, Y)
+SC_HD long long sc_layout_index(const ScLayout& L, int X, int Y) {
+    const int px = X / L.step, rx = X - px * L.step, py = Y / L.step, ry = Y - py * L.step;
+    return (long long)(ry * L.step + rx) * 2 * L.hps4 + (long long)py * L.ppitch + px;
+}
 
 #endif

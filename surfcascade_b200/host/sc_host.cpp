@@ -42,21 +42,41 @@ sc_rect project_patch(int tmpl, int l, const sc_rect& p) {
     return r;
 }
 
-bool project_geom(int tmpl, int l, const sc_rect& patch, int pitch, ScGeom* g) {
+bool project_geom(int tmpl, int l, const sc_rect& patch, const ScLayout& L, ScGeom* g) {
     const sc_rect r = project_patch(tmpl, l, patch);
-    g->off = r.y * pitch + r.x;
+    for (int k = 0; k < 10; k++) g->c[k] = 0;
+    g->pad = 0;
     if (r.w == r.h) {
         const int ce = r.w / 2;
         if (ce < 1) return false;
-        g->shape = 0; g->along = ce; g->across = ce * pitch;
+        g->shape = 0;
+        for (int b = 0; b < 3; b++)
+            for (int a = 0; a < 3; a++) g->c[3 * b + a] = (int)sc_layout_index(L, r.x + a * ce, r.y + b * ce);
     } else {
         const int ce = std::min(r.w, r.h);
         if (ce < 1 || std::max(r.w, r.h) != 4 * ce) return false;
         g->shape = 1;
-        if (r.w > r.h) { g->along = ce; g->across = ce * pitch; }
-        else { g->along = ce * pitch; g->across = ce; }
+        const bool wide = r.w > r.h;
+        for (int k = 0; k < 5; k++) {
+            // first line: the chain of corners along the long side; second line: one cell edge across
+            const int x0 = r.x + (wide ? k * ce : 0), y0 = r.y + (wide ? 0 : k * ce);
+            g->c[k] = (int)sc_layout_index(L, x0, y0);
+            g->c[5 + k] = (int)sc_layout_index(L, x0 + (wide ? 0 : ce), y0 + (wide ? ce : 0));
+        }
     }
     return true;
+}
+
+ScLayout make_layout(int W, int H, int step) {
+    ScLayout L;
+    L.step = step < 1 ? 1 : step;
+    const int cols = (W + 1 + L.step - 1) / L.step;
+    L.ppitch = (cols + 7) / 8 * 8;
+    L.prows = (H + 1 + L.step - 1) / L.step;
+    L.pad = 0;
+    L.hps4 = (long long)L.ppitch * L.prows;
+    L.frame4 = ((long long)L.step * L.step * 2 * L.hps4 + 15) / 16 * 16;
+    return L;
 }
 
 void scale_ladder(int W, int H, int base, double scale, std::vector<int>* sides) {

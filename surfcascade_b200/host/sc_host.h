@@ -18,8 +18,12 @@ void pool_patches(int tw, int th, std::vector<sc_rect>* out);
 // ProjectPatches at window origin (0,0), DenseSURFFeatureExtractor.cpp:486-508
 sc_rect project_patch(int tmpl, int l, const sc_rect& patch);
 
-// ProjectPatches + GetRectsFromPatch (:360-377) folded into corner strides; false if not 2x2 / 4x1 / 1x4 cells
-bool project_geom(int tmpl, int l, const sc_rect& patch, int pitch, ScGeom* g);
+// ProjectPatches + GetRectsFromPatch (:360-377) folded into the layout offsets of the corner lattice (relative to a
+// window origin on the layout's lattice); false if the projected patch is not 2x2 / 4x1 / 1x4 cells
+bool project_geom(int tmpl, int l, const sc_rect& patch, const ScLayout& L, ScGeom* g);
+
+// Integral-image layout for a W x H frame scanned on a lattice of `step` pixels (sc_plan.h)
+ScLayout make_layout(int W, int H, int step);
 
 // Window sides of the scale loop, ObjDetector.cpp:174,180
 void scale_ladder(int W, int H, int base, double scale, std::vector<int>* sides);

@@ -89,7 +89,7 @@ def positive(seed: int) -> np.ndarray:
     bg = 0.5 * (bg - bg.mean()) + 110.0 + 30.0 * rng.random()
     contrast = 22.0 + 50.0 * rng.random()
     img = bg + _render_object(TEMPLATE, rng, contrast) + rng.normal(0.0, 8.0, size=(TEMPLATE, TEMPLATE))
-    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(np.clip(np.rint(img), 0, 255).astype(np.uint8))
 
 
 def _distractor(side: int, rng: np.random.Generator, contrast: float) -> np.ndarray:
@@ -120,7 +120,7 @@ def negative_frame(seed: int, h: int = 240, w: int = 320) -> np.ndarray:
         y = int(rng.integers(0, h - side)); x = int(rng.integers(0, w - side))
         img[y:y + side, x:x + side] += _distractor(side, rng, 35.0 + 40.0 * rng.random())
     img += rng.normal(0.0, 4.0, size=(h, w))
-    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(np.clip(np.rint(img), 0, 255).astype(np.uint8))
 
 
 def frame(h: int, w: int, seed: int, n_objects: int = 8) -> np.ndarray:
@@ -138,7 +138,7 @@ def frame(h: int, w: int, seed: int, n_objects: int = 8) -> np.ndarray:
         y = int(rng.integers(0, h - side)); x = int(rng.integers(0, w - side))
         img[y:y + side, x:x + side] += _render_object(side, rng, 55.0 + 30.0 * rng.random())
     img += rng.normal(0.0, 4.0, size=(h, w))
-    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(np.clip(np.rint(img), 0, 255).astype(np.uint8))
 
 
 def noise_frame(h: int, w: int, seed: int) -> np.ndarray:
