@@ -82,7 +82,7 @@ struct sc_handle {
     // group buffers
     int group_frames = 0;       // frames the buffers below hold
     uint32_t rec_cap = 0;
-    DevBuf d_img, d_carry, d_S, d_multi, d_pass, d_visited, d_rec, d_idx[2], d_small, d_counters, d_det;
+    DevBuf d_img, d_carry, d_S, d_multi, d_pass, d_visited, d_start, d_rec, d_idx[2], d_small, d_counters, d_det;
     HostBuf h_stage;
     std::vector<sc_counters> last_counters;
     int last_nframes = 0;
@@ -122,8 +122,9 @@ int cuda_fail(sc_handle* h, cudaError_t e, const char* what) {
         if (e_ != cudaSuccess) return cuda_fail((h), e_, #call); \
     } while (0)
 
-enum { K_CARRY = 0, K_WALK, K_STAGE0, K_STAGE, K_REPLAY, K_FINALIZE, K_COUNT };
-const char* const kKernelNames[K_COUNT] = {"k_strip_carry", "k_integral_walk", "k_scan_stage0", "k_scan_stage", "k_replay_rows", "k_finalize"};
+enum { K_CARRY = 0, K_WALK, K_STAGE0, K_STAGE, K_REPLAY, K_FINALIZE, K_EVENTS, K_COUNT };
+const char* const kKernelNames[K_COUNT] = {"k_strip_carry", "k_integral_walk", "k_scan_stage0", "k_scan_stage", "k_replay_rows", "k_finalize",
+                                            "k_row_events"};
 
 cudaEvent_t take_event(sc_handle* h) {
     cudaEvent_t e = nullptr;
@@ -175,7 +176,7 @@ int build_plan(sc_handle* h, int W, int H, const sc_detect_params& prm, std::vec
     memset(&p, 0, sizeof(p));
     p.W = W; p.H = H;
     p.step = prm.step > 0 ? prm.step : (prm.base > 20 ? prm.base / 20 : 1);
-    p.lay = sc_host::make_layout(W, H, p.step);
+    p.lay = sc_host::make_layout(W, H, 2 * p.step, p.step);
     if (p.lay.frame4 > 0x7fffffffLL) return fail(h, SC_ERR_INVALID, "frame too large for 32-bit layout offsets");
     p.n_stages = h->n_stages; p.total_weak = h->total_weak;
     p.use_prefilter = prm.prefilter >= 0; p.skip_rule = prm.skip_rule != 0; p.force_all = prm.force_all_stages != 0;
@@ -196,13 +197,16 @@ int build_plan(sc_handle* h, int W, int H, const sc_detect_params& prm, std::vec
         if (s.nx > 65535 || s.ny > 65535) return fail(h, SC_ERR_INVALID, "lattice exceeds 65535 positions per axis");
         s.wpr = (s.nx + 31) / 32;
         s.thr = (float)(l * l * (prm.prefilter >= 0 ? prm.prefilter : 0));
-        s.tiles_x = (s.nx + SC_TILE_X - 1) / SC_TILE_X;
+        s.tiles_x = ((s.nx + 1) / 2 + SC_TILE_X - 1) / SC_TILE_X;  // tiles of 64 same-parity columns
         const int tiles_y = (s.ny + SC_TILE_Y - 1) / SC_TILE_Y;
         s.block_base = blocks; s.word_base = words; s.row_base = rows;
-        s.pf[0] = 0;
-        s.pf[1] = (int)sc_layout_index(p.lay, l, 0);
-        s.pf[2] = (int)sc_layout_index(p.lay, 0, l);
-        s.pf[3] = (int)sc_layout_index(p.lay, l, l);
+        for (int ph = 0; ph < 2; ph++) {
+            const int x0 = ph * p.step;
+            s.pf[ph][0] = (int)sc_layout_index(p.lay, x0, 0);
+            s.pf[ph][1] = (int)sc_layout_index(p.lay, x0 + l, 0);
+            s.pf[ph][2] = (int)sc_layout_index(p.lay, x0, l);
+            s.pf[ph][3] = (int)sc_layout_index(p.lay, x0 + l, l);
+        }
         blocks += s.tiles_x * tiles_y; words += s.wpr * s.ny; rows += s.ny;
         windows += (long long)s.nx * s.ny;
         nsc++;
@@ -211,11 +215,13 @@ int build_plan(sc_handle* h, int W, int H, const sc_detect_params& prm, std::vec
 
     ScGeom zero_geom;
     memset(&zero_geom, 0, sizeof(zero_geom));
-    geom_out->assign((size_t)std::max(nsc, 1) * h->total_weak, zero_geom);
-    for (int i = 0; i < nsc; i++)
-        for (int k = 0; k < h->total_weak; k++)
-            if (!sc_host::project_geom(h->tmpl, p.sc[i].l, h->rects[k], p.lay, &(*geom_out)[(size_t)i * h->total_weak + k]))
-                return fail(h, SC_ERR_INVALID, "weak classifier patch is not 2x2 / 4x1 / 1x4 cells after projection");
+    geom_out->assign((size_t)2 * std::max(nsc, 1) * h->total_weak, zero_geom);  // [column parity][scale][weak]
+    for (int ph = 0; ph < 2; ph++)
+        for (int i = 0; i < nsc; i++)
+            for (int k = 0; k < h->total_weak; k++)
+                if (!sc_host::project_geom(h->tmpl, p.sc[i].l, h->rects[k], p.lay, ph * p.step,
+                                           &(*geom_out)[((size_t)ph * nsc + i) * h->total_weak + k]))
+                    return fail(h, SC_ERR_INVALID, "weak classifier patch is not 2x2 / 4x1 / 1x4 cells after projection");
     return SC_OK;
 }
 
@@ -255,6 +261,7 @@ int ensure_group_buffers(sc_handle* h, int want_frames, bool own_images) {
     SC_CUDA(h, h->d_multi.ensure(align256((size_t)g * p.words_per_frame * 4 + 4)));
     SC_CUDA(h, h->d_pass.ensure(align256((size_t)g * p.words_per_frame * 4 + 4)));
     SC_CUDA(h, h->d_visited.ensure(align256((size_t)g * p.words_per_frame * 4 + 4)));
+    SC_CUDA(h, h->d_start.ensure(align256((size_t)g * p.rows_per_frame * 4 + 4)));
     SC_CUDA(h, h->d_rec.ensure(align256(std::max<size_t>(recs, 1) * sizeof(ScRecord))));
     SC_CUDA(h, h->d_idx[0].ensure(align256(std::max<size_t>(recs, 1) * 4)));
     SC_CUDA(h, h->d_idx[1].ensure(align256(std::max<size_t>(recs, 1) * 4)));
@@ -286,10 +293,26 @@ int run_group(sc_handle* h, const uint8_t* d_img, int g, int frame0, sc_detectio
         uint32_t* multi = h->d_multi.as<uint32_t>();
         ScRecord* rec = h->d_rec.as<ScRecord>();
         {
+            // even lattice columns everywhere, then the odd columns the reference's stride can reach
             const size_t smem = (size_t)p.n_weak[0] * (SC_W_PITCH * 4 + 8 + sizeof(ScGeom));
-            KernelSpan ks(h, K_STAGE0);
-            sck::k_scan_stage0<<<g * p.blocks_per_frame, SC_TILE_THREADS, smem, st>>>(dp, S, geom, w, wb, multi, h->d_pass.as<uint32_t>(), rec,
-                                                                                         small + SM_REC, h->rec_cap);
+            int* start_odd = h->d_start.as<int>();
+            const int rows0 = g * p.rows_per_frame;
+            {
+                KernelSpan ks(h, K_STAGE0);
+                sck::k_scan_stage0<<<g * p.blocks_per_frame, SC_TILE_THREADS, smem, st>>>(dp, S, geom, w, wb, multi, h->d_pass.as<uint32_t>(), rec,
+                                                                                             small + SM_REC, h->rec_cap, 0, start_odd);
+            }
+            if (p.skip_rule) {
+                KernelSpan ks(h, K_EVENTS);
+                sck::k_row_events<<<(rows0 + 127) / 128, 128, 0, st>>>(dp, g, multi, start_odd, d_counters);
+            } else {
+                SC_CUDA(h, cudaMemsetAsync(start_odd, 0, (size_t)rows0 * 4, st));  // every odd column is visited
+            }
+            {
+                KernelSpan ks(h, K_STAGE0);
+                sck::k_scan_stage0<<<g * p.blocks_per_frame, SC_TILE_THREADS, smem, st>>>(dp, S, geom, w, wb, multi, h->d_pass.as<uint32_t>(), rec,
+                                                                                             small + SM_REC, h->rec_cap, 1, start_odd);
+            }
         }
         const int tail_grid = h->n_sms * 8;
         for (int s = 1; s < p.n_stages; s++) {
@@ -318,7 +341,12 @@ void fill_counters(const sc_handle* h, const unsigned long long* raw, int nframe
         sc_counters& o = out[f];
         memset(&o, 0, sizeof(o));
         o.grid = p.windows_per_frame;
-        o.evaluated = p.windows_per_frame;
+        if (p.skip_rule) {
+            for (int i = 0; i < p.n_scales; i++) o.evaluated += (int64_t)((p.sc[i].nx + 1) / 2) * p.sc[i].ny;  // even columns
+            o.evaluated += (int64_t)c[SC_CNT_EVALODD];                                                          // reachable odd columns
+        } else {
+            o.evaluated = p.windows_per_frame;
+        }
         o.visited = (int64_t)c[SC_CNT_VISITED];
         o.prefilter_pass = (int64_t)c[SC_CNT_PREFILTER];
         o.raw = (int64_t)c[SC_CNT_RAW];
@@ -361,7 +389,7 @@ void sc_destroy(sc_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     DevBuf* bufs[] = {&h->d_w, &h->d_wb, &h->d_plan, &h->d_geom, &h->d_img, &h->d_carry, &h->d_S, &h->d_multi, &h->d_pass, &h->d_visited,
-                      &h->d_rec, &h->d_idx[0], &h->d_idx[1], &h->d_small, &h->d_counters, &h->d_det, &h->d_hook_img, &h->d_hook_carry, &h->d_hook_S};
+                      &h->d_rec, &h->d_idx[0], &h->d_idx[1], &h->d_small, &h->d_counters, &h->d_det, &h->d_start, &h->d_hook_img, &h->d_hook_carry, &h->d_hook_S};
     for (DevBuf* b : bufs) b->release();
     h->h_stage.release();
     for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -442,7 +470,7 @@ int sc_integral(sc_handle* h, const uint8_t* gray, int W, int H, int stride, flo
     h->have_integral = false;
     const int n_strips = (W + SC_STRIP - 1) / SC_STRIP;
     // the hooks keep their own single-frame integral in the step-1 layout (explicit rects sit on any pixel)
-    const ScLayout L = sc_host::make_layout(W, H, 1);
+    const ScLayout L = sc_host::make_layout(W, H, 1, 1);
     SC_CUDA(h, h->d_hook_img.ensure(align256((size_t)W * H)));
     SC_CUDA(h, h->d_hook_carry.ensure(align256((size_t)H * n_strips * 32)));
     SC_CUDA(h, h->d_hook_S.ensure((size_t)L.frame4 * 16));
@@ -512,7 +540,7 @@ int sc_stage_scores(sc_handle* h, const int32_t* wins, int n, float* out) {
         const int x = wins[3 * i], y = wins[3 * i + 1], l = wins[3 * i + 2];
         if (x < 0 || y < 0 || l < 1 || x + l > W || y + l > H) return fail(h, SC_ERR_INVALID, "window outside the image");
         for (int k = 0; k < tw; k++)
-            if (!sc_host::project_geom(h->tmpl, l, h->rects[k], h->hook_lay, &geom[(size_t)i * tw + k]))
+            if (!sc_host::project_geom(h->tmpl, l, h->rects[k], h->hook_lay, 0, &geom[(size_t)i * tw + k]))
                 return fail(h, SC_ERR_INVALID, "degenerate projected patch");
     }
     ScPlan mini;

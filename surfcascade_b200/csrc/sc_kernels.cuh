@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(128) k_integral_walk(const uint8_t* __restrict
     float4* Sf = S + (size_t)f * L.frame4;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     // this lane's integral column X = x + 1: in-plane column and the plane column residue are fixed
-    const int X = x + 1, px = X / L.step, rx = X - px * L.step;
+    const int X = x + 1, px = X / L.sx, rx = X - px * L.sx;
     if (valid) { float4* o = Sf + (size_t)rx * 2 * L.hps4 + px; o[0] = zero; o[L.hps4] = zero; }   // row Y = 0
     if (s == 0 && lane == 0)                                                                       // column X = 0
         for (int Y = 0; Y <= H; Y++) { float4* o = Sf + sc_layout_index(L, 0, Y); o[0] = zero; o[L.hps4] = zero; }
@@ -128,9 +128,9 @@ __global__ void __launch_bounds__(128) k_integral_walk(const uint8_t* __restrict
             acc[2 * k] = __fadd_rn(acc[2 * k], (float)(cy[2 * k] + (int)(p[k] & 0xffffu)));
             acc[2 * k + 1] = __fadd_rn(acc[2 * k + 1], (float)(cy[2 * k + 1] + (int)(p[k] >> 16)));
         }
-        if (++ry == L.step) { ry = 0; py++; }
+        if (++ry == L.sy) { ry = 0; py++; }
         if (valid) {
-            float4* o = Sf + (size_t)(ry * L.step + rx) * 2 * L.hps4 + (size_t)py * L.ppitch + px;
+            float4* o = Sf + (size_t)(ry * L.sx + rx) * 2 * L.hps4 + (size_t)py * L.ppitch + px;
             o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
             o[L.hps4] = make_float4(acc[4], acc[5], acc[6], acc[7]);
         }
@@ -154,8 +154,17 @@ __global__ void k_export_integral(const float4* __restrict__ S, const ScLayout L
 // ---------------------------------------------------------------------------------------------------------
 struct Px { float v[8]; };
 
+// p + idx float4s in ONE instruction (IMAD.WIDE.U32); plain pointer arithmetic costs 4-5 here because the compiler
+// re-associates the 64-bit sum.  Layout offsets are non-negative 32-bit element counts.
+__device__ __forceinline__ const float4* at(const float4* p, int idx) {
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(r) : "r"((unsigned)idx), "l"(p));
+    return reinterpret_cast<const float4*>(r);
+}
+
+// lo4 / hi4 already point at the window origin's element of the two half-planes
 __device__ __forceinline__ Px load_px(const float4* __restrict__ lo4, const float4* __restrict__ hi4, int idx) {
-    const float4 lo = __ldg(lo4 + idx), hi = __ldg(hi4 + idx);
+    const float4 lo = __ldg(at(lo4, idx)), hi = __ldg(at(hi4, idx));
     Px p;
     p.v[0] = lo.x; p.v[1] = lo.y; p.v[2] = lo.z; p.v[3] = lo.w; p.v[4] = hi.x; p.v[5] = hi.y; p.v[6] = hi.z; p.v[7] = hi.w;
     return p;
@@ -182,23 +191,25 @@ __device__ __forceinline__ float sumsq_hadd(const float* v) {
 }
 
 // CalcFeature + Normalize for one projected patch; `org` = layout index of the window origin.
-__device__ __forceinline__ void descriptor(const float4* __restrict__ lo4, const float4* __restrict__ hi4, int org, const ScGeom& g, float* v) {
+__device__ __forceinline__ void descriptor(const float4* __restrict__ lo4_, const float4* __restrict__ hi4_, int org, const ScGeom& g, float* v) {
+    const float4* lo4 = at(lo4_, org);
+    const float4* hi4 = at(hi4_, org);
     if (g.shape == 0) {
         // 3 x 3 corner lattice, cells row-major (GetRectsFromPatch :360-377)
-        Px a0 = load_px(lo4, hi4, org + g.c[0]), a1 = load_px(lo4, hi4, org + g.c[1]), a2 = load_px(lo4, hi4, org + g.c[2]);
-        const Px b0 = load_px(lo4, hi4, org + g.c[3]), b1 = load_px(lo4, hi4, org + g.c[4]), b2 = load_px(lo4, hi4, org + g.c[5]);
+        Px a0 = load_px(lo4, hi4, g.c[0]), a1 = load_px(lo4, hi4, g.c[1]), a2 = load_px(lo4, hi4, g.c[2]);
+        const Px b0 = load_px(lo4, hi4, g.c[3]), b1 = load_px(lo4, hi4, g.c[4]), b2 = load_px(lo4, hi4, g.c[5]);
         cell_sum(a0, a1, b0, b1, v);
         cell_sum(a1, a2, b1, b2, v + 8);
-        a0 = load_px(lo4, hi4, org + g.c[6]); a1 = load_px(lo4, hi4, org + g.c[7]); a2 = load_px(lo4, hi4, org + g.c[8]);
+        a0 = load_px(lo4, hi4, g.c[6]); a1 = load_px(lo4, hi4, g.c[7]); a2 = load_px(lo4, hi4, g.c[8]);
         cell_sum(b0, b1, a0, a1, v + 16);
         cell_sum(b1, b2, a1, a2, v + 24);
     } else {
         // 2 x 5 corner lattice: four cells chained along the long side (4x1 wide or 1x4 tall; B and C swap roles
         // between the two, and fl(B + C) == fl(C + B))
-        Px t0 = load_px(lo4, hi4, org + g.c[0]), u0 = load_px(lo4, hi4, org + g.c[5]);
+        Px t0 = load_px(lo4, hi4, g.c[0]), u0 = load_px(lo4, hi4, g.c[5]);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const Px t1 = load_px(lo4, hi4, org + g.c[k + 1]), u1 = load_px(lo4, hi4, org + g.c[k + 6]);
+            const Px t1 = load_px(lo4, hi4, g.c[k + 1]), u1 = load_px(lo4, hi4, g.c[k + 6]);
             cell_sum(t0, t1, u0, u1, v + 8 * k);
             t0 = t1; u0 = u1;
         }
@@ -245,8 +256,9 @@ __device__ __forceinline__ float stage_score(const float4* __restrict__ lo4, con
 // DenseSURFFeatureExtractor::sum (:351-358) and the compare at ObjDetector.cpp:188; pf = layout offsets of the corners
 // (0,0) (l,0) (0,l) (l,l)
 __device__ __forceinline__ float window_sum(const float4* __restrict__ lo4, int org, const int* pf) {
-    const float4 a = __ldg(lo4 + org + pf[0]), b = __ldg(lo4 + org + pf[1]);
-    const float4 c = __ldg(lo4 + org + pf[2]), d = __ldg(lo4 + org + pf[3]);
+    const float4* p = at(lo4, org);
+    const float4 a = __ldg(at(p, pf[0])), b = __ldg(at(p, pf[1]));
+    const float4 c = __ldg(at(p, pf[2])), d = __ldg(at(p, pf[3]));
     const float s0 = __fsub_rn(__fadd_rn(a.x, d.x), __fadd_rn(b.x, c.x));
     const float s1 = __fsub_rn(__fadd_rn(a.y, d.y), __fadd_rn(b.y, c.y));
     const float s2 = __fsub_rn(__fadd_rn(a.z, d.z), __fadd_rn(b.z, c.z));
@@ -260,16 +272,28 @@ __device__ __forceinline__ bool rejected_skips(float s, int p, int n_stages) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Stage 0 over the whole lattice
+// Stage 0 over the lattice, one x-parity per launch (see SC_TILE_X in sc_plan.h)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SC_TILE_THREADS) k_scan_stage0(const ScPlan* __restrict__ plan, const float4* __restrict__ S,
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {  // bit i (i < 16) -> bit 2i
+    x &= 0xffffu;
+    x = (x | (x << 8)) & 0x00ff00ffu;
+    x = (x | (x << 4)) & 0x0f0f0f0fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+
+// phase 0: lattice columns gx = 2j, every row.  phase 1: gx = 2j + 1, only gx >= start_odd[row].
+__global__ void __launch_bounds__(SC_TILE_THREADS, 3) k_scan_stage0(const ScPlan* __restrict__ plan, const float4* __restrict__ S,
                                                                   const ScGeom* __restrict__ geom_all, const float* __restrict__ w_all,
                                                                   const double* __restrict__ wb_all, uint32_t* __restrict__ multi_bits,
                                                                   uint32_t* __restrict__ pass_bits, ScRecord* __restrict__ rec,
-                                                                  uint32_t* __restrict__ rec_count, uint32_t rec_cap) {
-    __shared__ uint32_t s_multi[SC_TILE_Y][2];
-    __shared__ uint32_t s_pass[SC_TILE_Y][2];
+                                                                  uint32_t* __restrict__ rec_count, uint32_t rec_cap, int phase,
+                                                                  const int* __restrict__ start_odd) {
+    __shared__ uint32_t s_multi[SC_TILE_Y][4];
+    __shared__ uint32_t s_pass[SC_TILE_Y][4];
     __shared__ uint16_t s_list[SC_TILE_X * SC_TILE_Y];
+    __shared__ int s_start[SC_TILE_Y];
     __shared__ uint32_t s_count;
     __shared__ ScScale s_sc;
     extern __shared__ __align__(16) unsigned char s_dyn[];  // stage-0 weights, wb, geometry
@@ -279,21 +303,34 @@ __global__ void __launch_bounds__(SC_TILE_THREADS) k_scan_stage0(const ScPlan* _
     const int b = blockIdx.x - f * plan->blocks_per_frame;
     int si = 0;
     while (si + 1 < plan->n_scales && plan->sc[si + 1].block_base <= b) si++;
-    const int n_weak = plan->n_weak[0], total_weak = plan->total_weak;
-    const int ppitch = plan->lay.ppitch;
-    const float4* lo4 = S + (size_t)f * plan->lay.frame4;
-    const float4* hi4 = lo4 + plan->lay.hps4;
-
-    float* sw = reinterpret_cast<float*>(s_dyn);                                       // [n_weak][36]
-    double* swb = reinterpret_cast<double*>(s_dyn + (size_t)n_weak * SC_W_PITCH * 4);  // [n_weak]
-    ScGeom* sg = reinterpret_cast<ScGeom*>(swb + n_weak);                              // [n_weak]
-    for (int i = tid; i < n_weak * SC_W_PITCH; i += SC_TILE_THREADS) sw[i] = w_all[i];
-    for (int i = tid; i < n_weak; i += SC_TILE_THREADS) { swb[i] = wb_all[i]; sg[i] = geom_all[(size_t)si * total_weak + i]; }
     if (tid == 0) { s_count = 0; s_sc = plan->sc[si]; }
     __syncthreads();
     const int nx = s_sc.nx, ny = s_sc.ny;
     const int tb = b - s_sc.block_base;
     const int ty = tb / s_sc.tiles_x, tx = tb - ty * s_sc.tiles_x;
+    if (phase) {
+        // odd columns are needed only from the row's first non-skipping even window on
+        int need = 0;
+        if (tid < SC_TILE_Y) {
+            const int gy = ty * SC_TILE_Y + tid;
+            const int st = gy < ny ? start_odd[(size_t)f * plan->rows_per_frame + s_sc.row_base + gy] : 0x7fffffff;
+            s_start[tid] = st;
+            need = st < nx && st < 2 * (tx * SC_TILE_X + SC_TILE_X);
+        }
+        if (!__syncthreads_or(need)) return;
+    }
+    const int n_weak = plan->n_weak[0], total_weak = plan->total_weak;
+    const int ppitch = plan->lay.ppitch;
+    const float4* lo4 = S + (size_t)f * plan->lay.frame4;
+    const float4* hi4 = lo4 + plan->lay.hps4;
+    float* sw = reinterpret_cast<float*>(s_dyn);                                       // [n_weak][36]
+    double* swb = reinterpret_cast<double*>(s_dyn + (size_t)n_weak * SC_W_PITCH * 4);  // [n_weak]
+    ScGeom* sg = reinterpret_cast<ScGeom*>(swb + n_weak);                              // [n_weak]
+    for (int i = tid; i < n_weak * SC_W_PITCH; i += SC_TILE_THREADS) sw[i] = w_all[i];
+    for (int i = tid; i < n_weak; i += SC_TILE_THREADS) {
+        swb[i] = wb_all[i];
+        sg[i] = geom_all[((size_t)phase * plan->n_scales + si) * total_weak + i];
+    }
 
     // phase A: prefilter + compaction of the passing windows of this tile
     {
@@ -302,15 +339,20 @@ __global__ void __launch_bounds__(SC_TILE_THREADS) k_scan_stage0(const ScPlan* _
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int row = warp + 8 * (i >> 1), half = i & 1;
-            const int gx = tx * SC_TILE_X + half * 32 + lane, gy = ty * SC_TILE_Y + row;
-            const bool valid = gx < nx && gy < ny;
+            const int j = tx * SC_TILE_X + half * 32 + lane;
+            const int gx = 2 * j + phase, gy = ty * SC_TILE_Y + row;
+            bool valid = gx < nx && gy < ny;
+            if (phase) valid = valid && gx >= s_start[row];
             bool pass = false;
-            if (valid) pass = use_pf ? (window_sum(lo4, gy * ppitch + gx, s_sc.pf) > thr) : true;
+            if (valid) pass = use_pf ? (window_sum(lo4, gy * ppitch + j, s_sc.pf[phase]) > thr) : true;
             const uint32_t m = __ballot_sync(0xffffffffu, pass);
+            const uint32_t fail = __ballot_sync(0xffffffffu, valid && !pass);
             uint32_t base = 0;
             if (lane == 0) {
-                s_pass[row][half] = m;
-                s_multi[row][half] = ~m;  // prefilter failed -> multi = 2 (ObjDetector.cpp:216-217)
+                s_pass[row][2 * half] = spread16(m) << phase;
+                s_pass[row][2 * half + 1] = spread16(m >> 16) << phase;
+                s_multi[row][2 * half] = spread16(fail) << phase;  // prefilter failed -> multi = 2 (ObjDetector.cpp:216-217)
+                s_multi[row][2 * half + 1] = spread16(fail >> 16) << phase;
                 base = atomicAdd(&s_count, __popc(m));
             }
             base = __shfl_sync(0xffffffffu, base, 0);
@@ -332,10 +374,11 @@ __global__ void __launch_bounds__(SC_TILE_THREADS) k_scan_stage0(const ScPlan* _
         if (i < count) {
             const uint32_t code = s_list[i];
             const int row = code >> 6, half = (code >> 5) & 1, ln = code & 31;
-            const int gx = tx * SC_TILE_X + half * 32 + ln, gy = ty * SC_TILE_Y + row;
-            const float score = stage_score(lo4, hi4, gy * ppitch + gx, sg, sw, swb, n_weak);
+            const int j = tx * SC_TILE_X + half * 32 + ln;
+            const int gx = 2 * j + phase, gy = ty * SC_TILE_Y + row;
+            const float score = stage_score(lo4, hi4, gy * ppitch + j, sg, sw, swb, n_weak);
             const bool rejected = score < theta0;
-            if (rejected && rejected_skips(score, 0, n_stages)) atomicOr(&s_multi[row][half], 1u << ln);
+            if (rejected && rejected_skips(score, 0, n_stages)) atomicOr(&s_multi[row][2 * half + (ln >> 4)], 1u << (2 * (ln & 15) + phase));
             push = !rejected || force;
             r.fs = ((uint32_t)f << 8) | (uint32_t)si;
             r.yx = ((uint32_t)gy << 16) | (uint32_t)gx;
@@ -355,16 +398,45 @@ __global__ void __launch_bounds__(SC_TILE_THREADS) k_scan_stage0(const ScPlan* _
     }
     __syncthreads();
 
-    // phase C: publish the two bitmask words of every tile row
-    if (tid < SC_TILE_Y * 2) {
-        const int row = tid >> 1, half = tid & 1;
-        const int gy = ty * SC_TILE_Y + row, wx = tx * 2 + half;
+    // phase C: publish the four bitmask words of every tile row (phase 0 defines the words, phase 1 ORs its bits in)
+    if (tid < SC_TILE_Y * 4) {
+        const int row = tid >> 2, w = tid & 3;
+        const int gy = ty * SC_TILE_Y + row, wx = tx * 4 + w;
         if (gy < ny && wx < s_sc.wpr) {
             const size_t wi = (size_t)f * plan->words_per_frame + s_sc.word_base + (size_t)gy * s_sc.wpr + wx;
-            multi_bits[wi] = s_multi[row][half];
-            pass_bits[wi] = s_pass[row][half];
+            if (phase == 0) {
+                multi_bits[wi] = s_multi[row][w];
+                pass_bits[wi] = s_pass[row][w];
+            } else {
+                if (s_multi[row][w]) atomicOr(&multi_bits[wi], s_multi[row][w]);
+                if (s_pass[row][w]) atomicOr(&pass_bits[wi], s_pass[row][w]);
+            }
         }
     }
+}
+
+// After phase 0: per lattice row, the first even column whose window does not certainly skip (multi bit clear: it
+// passed stage 0, or was rejected with (s + 1) / N >= 0.5).  The reference's chain x += multi * step stays on even
+// columns up to there; odd columns can only be visited from the next one on.
+__global__ void __launch_bounds__(128) k_row_events(const ScPlan* __restrict__ plan, int nframes, const uint32_t* __restrict__ multi_bits,
+                                                     int* __restrict__ start_odd, unsigned long long* __restrict__ counters) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int rows = plan->rows_per_frame;
+    if (t >= nframes * rows) return;
+    const int f = t / rows, r = t - f * rows;
+    int si = 0;
+    while (si + 1 < plan->n_scales && plan->sc[si + 1].row_base <= r) si++;
+    const int wpr = plan->sc[si].wpr, nx = plan->sc[si].nx;
+    const size_t w0 = (size_t)f * plan->words_per_frame + plan->sc[si].word_base + (size_t)(r - plan->sc[si].row_base) * wpr;
+    int start = 0x7fffffff;
+    for (int wi = 0; wi < wpr; wi++) {
+        const int nb = min(32, nx - 32 * wi);
+        const uint32_t valid = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
+        const uint32_t z = ~multi_bits[w0 + wi] & 0x55555555u & valid;
+        if (z) { start = 32 * wi + __ffs(z); break; }  // (ffs - 1) is the even column, + 1 the first odd one
+    }
+    start_odd[t] = start;
+    if (start < nx) atomicAdd(&counters[(size_t)f * SC_CNT_STRIDE + SC_CNT_EVALODD], (unsigned long long)((nx - start + 1) / 2));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -399,7 +471,8 @@ __global__ void __launch_bounds__(128) k_scan_stage(const ScPlan* __restrict__ p
             const int f = r.fs >> 8, si = r.fs & 0xff;
             const int gy = r.yx >> 16, gx = r.yx & 0xffff;
             const float4* lo4 = S + (size_t)f * plan->lay.frame4;
-            const float score = stage_score(lo4, lo4 + plan->lay.hps4, gy * ppitch + gx, geom_all + (size_t)si * total_weak + wbase, sw, swb, n_weak);
+            const float score = stage_score(lo4, lo4 + plan->lay.hps4, gy * ppitch + (gx >> 1),
+                                            geom_all + ((size_t)(gx & 1) * plan->n_scales + si) * total_weak + wbase, sw, swb, n_weak);
             if (r.rej < 0) {
                 const bool rejected = score < theta;
                 if (rejected) {

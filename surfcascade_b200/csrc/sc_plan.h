@@ -8,7 +8,10 @@
 #define SC_PLAN_MAX_STAGES 16
 #define SC_W_PITCH 36          // floats per weak classifier in device memory: w[0..32] + 3 pad (16 B aligned rows)
 
-// Stage-0 tile: 64 x 16 window origins per CTA (two 32-wide bitmask words per tile row).
+// Stage-0 tile: 64 x 16 window origins of ONE x-parity per CTA (lattice columns 2j + phase, j in a 64-run: four
+// 32-wide bitmask words per tile row).  The reference's adaptive stride (multi = 2 after almost every window) walks
+// the even columns until the first window that does not skip; the scan therefore evaluates the even columns first
+// (phase 0) and the odd columns only from that window on (phase 1), about 56-58 % of the lattice at 1080p.
 #define SC_TILE_X 64
 #define SC_TILE_Y 16
 #define SC_TILE_THREADS 256
@@ -21,14 +24,15 @@
 //   lattice would then touch 32 sectors in 16 cache lines per 16-byte load.  Here pixel (X, Y) lives in plane
 //   (Y mod s, X mod s) at (Y div s, X div s), and every plane is stored as two float4 half-planes (channels 0-3,
 //   channels 4-7).  Neighbouring lattice windows read neighbouring float4s: one corner fetch of a warp is two
-//   fully coalesced 512-byte loads.  s = lattice step for detection plans, 1 for the explicit-rect hooks.
+//   fully coalesced 512-byte loads.  Detection plans deinterleave rows by sy = lattice step and columns by
+//   sx = 2 * step, because one launch of the scan walks lattice columns of a single parity (2j or 2j + 1, see
+//   SC_TILE_X): consecutive j are then consecutive float4s.  The explicit-rect hooks use sx = sy = 1.
 struct ScLayout {
-    int step;              // s
-    int ppitch;            // float4 elements per plane row   = roundup(ceil((W+1)/s), 8)
-    int prows;             // plane rows                      = ceil((H+1)/s)
-    int pad;
+    int sx, sy;            // column / row deinterleave factors
+    int ppitch;            // float4 elements per plane row   = roundup(ceil((W+1)/sx), 8)
+    int prows;             // plane rows                      = ceil((H+1)/sy)
     long long hps4;        // float4 elements per half-plane  = ppitch * prows
-    long long frame4;      // float4 elements per frame       = s*s*2*hps4 rounded up to 16
+    long long frame4;      // float4 elements per frame       = sx*sy*2*hps4 rounded up to 16
 };
 
 struct ScScale {
@@ -40,7 +44,8 @@ struct ScScale {
     int block_base;   // first stage-0 CTA of this scale inside a frame
     int word_base;    // first bitmask word of this scale inside a frame
     int row_base;     // first lattice row of this scale inside a frame (replay threads)
-    int pf[4];        // layout offsets of the prefilter corners (0,0) (l,0) (0,l) (l,l) relative to the window origin
+    int pf[2][4];     // per column parity: layout offsets of the prefilter corners (0,0) (l,0) (0,l) (l,l) relative to
+                      // the layout index gy * ppitch + (gx >> 1) of the window
     int pad[3];
 };
 
@@ -64,8 +69,8 @@ struct ScPlan {
     ScScale sc[SC_PLAN_MAX_SCALES];
 };
 
-// Per (scale, weak classifier) projected geometry: layout offsets (float4 units, low half) of the patch's corner
-// lattice relative to the window origin's layout index.
+// Per (column parity, scale, weak classifier) projected geometry: layout offsets (float4 units, low half) of the
+// patch's corner lattice relative to the window's layout index gy * ppitch + (gx >> 1)  [hooks: y * ppitch + x].
 //   shape 0, square 2x2 cells: c[3*b + a], a, b in 0..2   (corner (ox + a*ce, oy + b*ce))
 //   shape 1, long 4x1 / 1x4  : c[k] first line, c[5 + k] second line, k in 0..4 along the cell chain
 struct ScGeom {
@@ -83,7 +88,7 @@ struct ScRecord {
     uint32_t score;
 };
 
-enum { SC_CNT_VISITED = 0, SC_CNT_PREFILTER = 1, SC_CNT_RAW = 2, SC_CNT_REACH0 = 3, SC_CNT_STRIDE = 3 + SC_PLAN_MAX_STAGES };
+enum { SC_CNT_VISITED = 0, SC_CNT_PREFILTER = 1, SC_CNT_RAW = 2, SC_CNT_EVALODD = 3, SC_CNT_REACH0 = 4, SC_CNT_STRIDE = 4 + SC_PLAN_MAX_STAGES };
 
 #ifdef __CUDACC__
 #define SC_HD __host__ __device__ __forceinline__
@@ -93,8 +98,8 @@ enum { SC_CNT_VISITED = 0, SC_CNT_PREFILTER = 1, SC_CNT_RAW = 2, SC_CNT_REACH0 =
 
 // layout index (float4 units, low half) of integral pixel (X, Y)
 SC_HD long long sc_layout_index(const ScLayout& L, int X, int Y) {
-    const int px = X / L.step, rx = X - px * L.step, py = Y / L.step, ry = Y - py * L.step;
-    return (long long)(ry * L.step + rx) * 2 * L.hps4 + (long long)py * L.ppitch + px;
+    const int px = X / L.sx, rx = X - px * L.sx, py = Y / L.sy, ry = Y - py * L.sy;
+    return (long long)(ry * L.sx + rx) * 2 * L.hps4 + (long long)py * L.ppitch + px;
 }
 
 #endif

@@ -42,8 +42,9 @@ sc_rect project_patch(int tmpl, int l, const sc_rect& p) {
     return r;
 }
 
-bool project_geom(int tmpl, int l, const sc_rect& patch, const ScLayout& L, ScGeom* g) {
-    const sc_rect r = project_patch(tmpl, l, patch);
+bool project_geom(int tmpl, int l, const sc_rect& patch, const ScLayout& L, int x0, ScGeom* g) {
+    sc_rect r = project_patch(tmpl, l, patch);
+    r.x += x0;  // column residue of the window origin inside the layout's deinterleave period
     for (int k = 0; k < 10; k++) g->c[k] = 0;
     g->pad = 0;
     if (r.w == r.h) {
@@ -67,15 +68,15 @@ bool project_geom(int tmpl, int l, const sc_rect& patch, const ScLayout& L, ScGe
     return true;
 }
 
-ScLayout make_layout(int W, int H, int step) {
+ScLayout make_layout(int W, int H, int sx, int sy) {
     ScLayout L;
-    L.step = step < 1 ? 1 : step;
-    const int cols = (W + 1 + L.step - 1) / L.step;
+    L.sx = sx < 1 ? 1 : sx;
+    L.sy = sy < 1 ? 1 : sy;
+    const int cols = (W + 1 + L.sx - 1) / L.sx;
     L.ppitch = (cols + 7) / 8 * 8;
-    L.prows = (H + 1 + L.step - 1) / L.step;
-    L.pad = 0;
+    L.prows = (H + 1 + L.sy - 1) / L.sy;
     L.hps4 = (long long)L.ppitch * L.prows;
-    L.frame4 = ((long long)L.step * L.step * 2 * L.hps4 + 15) / 16 * 16;
+    L.frame4 = ((long long)L.sx * L.sy * 2 * L.hps4 + 15) / 16 * 16;
     return L;
 }
 

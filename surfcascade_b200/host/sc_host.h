@@ -20,10 +20,12 @@ sc_rect project_patch(int tmpl, int l, const sc_rect& patch);
 
 // ProjectPatches + GetRectsFromPatch (:360-377) folded into the layout offsets of the corner lattice (relative to a
 // window origin on the layout's lattice); false if the projected patch is not 2x2 / 4x1 / 1x4 cells
-bool project_geom(int tmpl, int l, const sc_rect& patch, const ScLayout& L, ScGeom* g);
+// x0 = (window origin x) mod L.sx: the origin's column residue (0 for even lattice columns and for the hooks,
+// `step` for odd lattice columns of a detection plan)
+bool project_geom(int tmpl, int l, const sc_rect& patch, const ScLayout& L, int x0, ScGeom* g);
 
-// Integral-image layout for a W x H frame scanned on a lattice of `step` pixels (sc_plan.h)
-ScLayout make_layout(int W, int H, int step);
+// Integral-image layout deinterleaved by sx columns and sy rows (sc_plan.h)
+ScLayout make_layout(int W, int H, int sx, int sy);
 
 // Window sides of the scale loop, ObjDetector.cpp:174,180
 void scale_ladder(int W, int H, int base, double scale, std::vector<int>* sides);
