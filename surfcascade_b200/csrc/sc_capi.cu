@@ -80,7 +80,8 @@ struct sc_handle {
     DevBuf d_plan, d_geom;
 
     // group buffers
-    int group_frames = 0;       // frames the buffers below hold
+    int group_frames = 0;       // frames one scan group holds (records, bitmasks)
+    int int_frames = 0;         // frames one integral super-group holds (images, carries, integral images)
     uint32_t rec_cap = 0;
     DevBuf d_img, d_carry, d_S, d_multi, d_pass, d_visited, d_start, d_rec, d_idx[2], d_small, d_counters, d_det;
     HostBuf h_stage;
@@ -240,6 +241,7 @@ int ensure_plan(sc_handle* h, int W, int H, const sc_detect_params& prm) {
     h->pparams = prm;
     h->have_plan = true;
     h->group_frames = 0;  // buffers are re-sized for the new plan
+    h->int_frames = 0;
     return SC_OK;
 }
 
@@ -252,12 +254,18 @@ int ensure_group_buffers(sc_handle* h, int want_frames, bool own_images) {
                              (size_t)p.H * p.n_strips * 32 + (size_t)p.W * p.H;
     int g = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)6 << 30) / std::max<size_t>(per_frame, 1)));
     g = std::min(g, std::max(want_frames, 1));
-    if (g <= h->group_frames) return SC_OK;
+    // the integral stage runs on a larger super-group (its warps walk rows sequentially and need many frames in flight)
+    const size_t int_frame = (size_t)p.lay.frame4 * 16 + (size_t)p.H * p.n_strips * 32 + (size_t)p.W * p.H;
+    int gi = (int)std::max<size_t>(1, std::min<size_t>(32, ((size_t)4 << 30) / std::max<size_t>(int_frame, 1)));
+    gi = std::max(g, std::min(gi, std::max(want_frames, 1)));
+    if (g <= h->group_frames && gi <= h->int_frames) return SC_OK;
+    g = std::max(g, h->group_frames);
+    gi = std::max(gi, h->int_frames);
     const unsigned long long recs = (unsigned long long)p.windows_per_frame * g;
     if (recs > 0xfffffff0ull) return fail(h, SC_ERR_INVALID, "too many windows per group");
-    if (own_images) SC_CUDA(h, h->d_img.ensure(align256((size_t)g * p.W * p.H)));
-    SC_CUDA(h, h->d_carry.ensure(align256((size_t)g * p.H * p.n_strips * 32)));
-    SC_CUDA(h, h->d_S.ensure((size_t)g * p.lay.frame4 * 16));
+    if (own_images) SC_CUDA(h, h->d_img.ensure(align256((size_t)gi * p.W * p.H)));
+    SC_CUDA(h, h->d_carry.ensure(align256((size_t)gi * p.H * p.n_strips * 32)));
+    SC_CUDA(h, h->d_S.ensure((size_t)gi * p.lay.frame4 * 16));
     SC_CUDA(h, h->d_multi.ensure(align256((size_t)g * p.words_per_frame * 4 + 4)));
     SC_CUDA(h, h->d_pass.ensure(align256((size_t)g * p.words_per_frame * 4 + 4)));
     SC_CUDA(h, h->d_visited.ensure(align256((size_t)g * p.words_per_frame * 4 + 4)));
@@ -268,24 +276,32 @@ int ensure_group_buffers(sc_handle* h, int want_frames, bool own_images) {
     SC_CUDA(h, h->d_small.ensure(SM_WORDS * 4));
     h->rec_cap = (uint32_t)recs;
     h->group_frames = g;
+    h->int_frames = gi;
+    return SC_OK;
+}
+
+// Channels + integral images of `n` frames (device images) into d_S
+int run_integral(sc_handle* h, const uint8_t* d_img, int n) {
+    const ScPlan& p = h->plan;
+    cudaStream_t st = h->stream;
+    const int rows = n * p.H;
+    { KernelSpan ks(h, K_CARRY); sck::k_strip_carry<<<(rows + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, n, h->d_carry.as<int>()); }
+    const int warps = n * p.n_strips;
+    { KernelSpan ks(h, K_WALK); sck::k_integral_walk<<<(warps + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, n, h->d_carry.as<int>(), h->d_S.as<float4>(), p.lay); }
+    SC_CUDA(h, cudaGetLastError());
     return SC_OK;
 }
 
 // Launches the whole path for `g` frames already in d_img (device).  Detections are appended to det / det_count.
-int run_group(sc_handle* h, const uint8_t* d_img, int g, int frame0, sc_detection* d_det, uint32_t det_cap, uint32_t* d_det_count,
+// Scan of `g` frames whose integrals start at frame slot `s0` of d_S.
+int run_group(sc_handle* h, int s0, int g, int frame0, sc_detection* d_det, uint32_t det_cap, uint32_t* d_det_count,
               unsigned long long* d_counters) {
     const ScPlan& p = h->plan;
     const ScPlan* dp = h->d_plan.as<ScPlan>();
     cudaStream_t st = h->stream;
     uint32_t* small = h->d_small.as<uint32_t>();
     SC_CUDA(h, cudaMemsetAsync(small, 0, (SM_DET) * 4, st));  // rec + stage counts; det count is the caller's
-    float4* S = h->d_S.as<float4>();
-    {
-        const int rows = g * p.H;
-        { KernelSpan ks(h, K_CARRY); sck::k_strip_carry<<<(rows + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, g, h->d_carry.as<int>()); }
-        const int warps = g * p.n_strips;
-        { KernelSpan ks(h, K_WALK); sck::k_integral_walk<<<(warps + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, g, h->d_carry.as<int>(), S, p.lay); }
-    }
+    float4* S = h->d_S.as<float4>() + (size_t)s0 * p.lay.frame4;
     if (p.n_scales > 0 && p.n_stages > 0) {
         const ScGeom* geom = h->d_geom.as<ScGeom>();
         const float* w = h->d_w.as<float>();
@@ -623,10 +639,15 @@ int sc_detect_device(sc_handle* h, const uint8_t* d_frames, int nframes, int W, 
     SC_CUDA(h, cudaMemsetAsync(h->d_counters.p, 0, (size_t)nframes * SC_CNT_STRIDE * 8, h->stream));
     SC_CUDA(h, cudaMemsetAsync(d_n, 0, 4, h->stream));
     const uint32_t det_cap = (uint32_t)std::min<size_t>(cap, 0xffffffffu);
-    for (int f0 = 0; f0 < nframes; f0 += h->group_frames) {
-        const int g = std::min(h->group_frames, nframes - f0);
-        rc = run_group(h, d_frames + (size_t)f0 * W * H, g, f0, d_out, det_cap, d_n, h->d_counters.as<unsigned long long>() + (size_t)f0 * SC_CNT_STRIDE);
+    for (int i0 = 0; i0 < nframes; i0 += h->int_frames) {
+        const int ni = std::min(h->int_frames, nframes - i0);
+        rc = run_integral(h, d_frames + (size_t)i0 * W * H, ni);
         if (rc != SC_OK) return rc;
+        for (int f0 = 0; f0 < ni; f0 += h->group_frames) {
+            const int g = std::min(h->group_frames, ni - f0);
+            rc = run_group(h, f0, g, i0 + f0, d_out, det_cap, d_n, h->d_counters.as<unsigned long long>() + (size_t)(i0 + f0) * SC_CNT_STRIDE);
+            if (rc != SC_OK) return rc;
+        }
     }
     SC_CUDA(h, h->h_stage.ensure((size_t)nframes * SC_CNT_STRIDE * 8));
     SC_CUDA(h, cudaMemcpyAsync(h->h_stage.p, h->d_counters.p, (size_t)nframes * SC_CNT_STRIDE * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -673,19 +694,24 @@ int sc_detect(sc_handle* h, const uint8_t* const* frames, int nframes, int W, in
     if (rc != SC_OK) return rc;
     rc = ensure_group_buffers(h, nframes, true);
     if (rc != SC_OK) return rc;
-    if (h->d_img.cap < (size_t)h->group_frames * W * H) SC_CUDA(h, h->d_img.ensure(align256((size_t)h->group_frames * W * H)));
+    if (h->d_img.cap < (size_t)h->int_frames * W * H) SC_CUDA(h, h->d_img.ensure(align256((size_t)h->int_frames * W * H)));
     const uint32_t det_cap = (uint32_t)std::min<size_t>(std::max<size_t>(cap, 1), 0xffffffffu);
     SC_CUDA(h, h->d_det.ensure((size_t)det_cap * sizeof(sc_detection)));
     SC_CUDA(h, h->d_counters.ensure((size_t)nframes * SC_CNT_STRIDE * 8));
     SC_CUDA(h, cudaMemsetAsync(h->d_counters.p, 0, (size_t)nframes * SC_CNT_STRIDE * 8, h->stream));
     uint32_t* d_cnt = h->d_small.as<uint32_t>() + SM_DET;
     SC_CUDA(h, cudaMemsetAsync(d_cnt, 0, 4, h->stream));
-    for (int f0 = 0; f0 < nframes; f0 += h->group_frames) {
-        const int g = std::min(h->group_frames, nframes - f0);
-        for (int k = 0; k < g; k++)
-            SC_CUDA(h, cudaMemcpy2DAsync(h->d_img.as<uint8_t>() + (size_t)k * W * H, W, frames[f0 + k], stride, W, H, cudaMemcpyHostToDevice, h->stream));
-        rc = run_group(h, h->d_img.as<uint8_t>(), g, f0, h->d_det.as<sc_detection>(), det_cap, d_cnt, h->d_counters.as<unsigned long long>() + (size_t)f0 * SC_CNT_STRIDE);
+    for (int i0 = 0; i0 < nframes; i0 += h->int_frames) {
+        const int ni = std::min(h->int_frames, nframes - i0);
+        for (int k = 0; k < ni; k++)
+            SC_CUDA(h, cudaMemcpy2DAsync(h->d_img.as<uint8_t>() + (size_t)k * W * H, W, frames[i0 + k], stride, W, H, cudaMemcpyHostToDevice, h->stream));
+        rc = run_integral(h, h->d_img.as<uint8_t>(), ni);
         if (rc != SC_OK) return rc;
+        for (int f0 = 0; f0 < ni; f0 += h->group_frames) {
+            const int g = std::min(h->group_frames, ni - f0);
+            rc = run_group(h, f0, g, i0 + f0, h->d_det.as<sc_detection>(), det_cap, d_cnt, h->d_counters.as<unsigned long long>() + (size_t)(i0 + f0) * SC_CNT_STRIDE);
+            if (rc != SC_OK) return rc;
+        }
     }
     const size_t cbytes = (size_t)nframes * SC_CNT_STRIDE * 8;
     SC_CUDA(h, h->h_stage.ensure(cbytes + 16));
