@@ -147,6 +147,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from surfcascade_b200 import capi
+    from surfcascade_b200 import dist as scdist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -177,9 +178,7 @@ def run_ours(args):
     cap = 1 << 16
     d_out = torch.zeros(cap * 24, dtype=torch.uint8, device=dev)
     d_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
-    gather_buf = torch.zeros(world * (cap * 24 // 8), dtype=torch.uint8, device=dev) if world > 1 else None
-    gather_cnt = torch.zeros(world, dtype=torch.int32, device=dev) if world > 1 else None
-    g_cap_bytes = cap * 24 // 8
+    g_cap_bytes = cap * 24 // 8  # 8192 records per rank per step cross NVLink (a 1080p frame yields ~500 raw windows)
 
     def step_device(s):
         x = dev_sets[s % n_sets]
@@ -187,8 +186,7 @@ def run_ours(args):
         if world > 1:
             # the one exchange step of the path: detection records to every rank (rank 0 groups them)
             with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(gather_cnt, d_cnt)
-                dist.all_gather_into_tensor(gather_buf, d_out[:g_cap_bytes])
+                scdist.gather_records(d_out[:g_cap_bytes], d_cnt)
 
     def step_host(s):
         x = host_sets[s % n_sets]

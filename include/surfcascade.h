@@ -90,6 +90,12 @@ int sc_set_cascade(sc_handle* h, const sc_cascade_desc* desc);
 /* Model::Load (Model.cpp:97-193) on a libconfig model.cfg, ExtractPatches (DenseSURFFeatureExtractor.cpp:49-63) on a
  * tmpl x tmpl template, flatten and upload. */
 int sc_load_model(sc_handle* h, const char* model_cfg_path, int tmpl);
+/* Host-only: Model::Load + flatten without touching a device.  Fills at most max_stages / max_weak entries and
+ * returns the number of stages (or a negative sc_status); *total_weak receives the weak classifier count. */
+int sc_model_flatten(const char* model_cfg_path, int tmpl, float* theta, int32_t* n_weak, int max_stages,
+                     sc_rect* rects, int32_t* patch_index, float* w /* [max_weak][33] */, double* bias, int max_weak, int* total_weak);
+/* Host-only: Model::Load followed by Model::Save (Model.cpp:21-95) to another path. */
+int sc_model_resave(const char* in_cfg_path, const char* out_cfg_path);
 /* Template pool: ExtractPatches. Returns the pool size (608 for tmpl 40); fills at most cap rects. */
 int sc_pool_patches(int tmpl, sc_rect* out, int cap);
 /* ProjectPatches (DenseSURFFeatureExtractor.cpp:486-508) for window side l at origin (0,0). */

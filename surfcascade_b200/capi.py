@@ -42,7 +42,7 @@ assert DETECTION_DTYPE.itemsize == 24
 EXPORTS = ["sc_create", "sc_destroy", "sc_last_error", "sc_version", "sc_set_cascade", "sc_load_model", "sc_pool_patches", "sc_project_patches",
            "sc_integral", "sc_features", "sc_window_sum", "sc_stage_scores", "sc_weak_predict", "sc_stage_predict", "sc_detect",
            "sc_detect_device", "sc_sync", "sc_last_counters", "sc_stream", "sc_launch_count", "sc_group_rectangles",
-           "sc_set_profiling", "sc_kernel_stats"]
+           "sc_set_profiling", "sc_kernel_stats", "sc_model_flatten", "sc_model_resave"]
 
 _lib = None
 
@@ -99,6 +99,32 @@ def params(base=40, step=0, scale=1.1, prefilter=6, skip_rule=True, force_all_st
 def counters_to_dict(c: Counters, n_stages: int) -> dict:
     return {"grid": c.grid, "visited": c.visited, "prefilter_pass": c.prefilter_pass, "weak_evals": c.weak_evals, "raw": c.raw,
             "evaluated": c.evaluated, "reach": [c.reach[i] for i in range(n_stages)]}
+
+
+def model_flatten(path: str, tmpl: int = 40) -> dict:
+    """Host-only Model::Load + flatten: {theta, n_weak, rects, patch_index, w, bias} as numpy arrays."""
+    L = lib()
+    L.sc_model_flatten.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                   C.POINTER(C.c_int)]
+    ms, mw = SC_MAX_STAGES, 2048
+    theta = np.zeros(ms, np.float32); n_weak = np.zeros(ms, np.int32); rects = np.zeros((mw, 4), np.int32); pidx = np.zeros(mw, np.int32)
+    w = np.zeros((mw, 33), np.float32); bias = np.zeros(mw, np.float64)
+    total = C.c_int(0)
+    s = L.sc_model_flatten(path.encode(), tmpl, theta.ctypes.data, n_weak.ctypes.data, ms, rects.ctypes.data, pidx.ctypes.data, w.ctypes.data,
+                           bias.ctypes.data, mw, C.byref(total))
+    if s < 0:
+        raise SurfCascadeError(s, f"cannot load {path}")
+    k = total.value
+    return {"theta": theta[:s].copy(), "n_weak": n_weak[:s].copy(), "rects": rects[:k].copy(), "patch_index": pidx[:k].copy(), "w": w[:k].copy(),
+            "bias": bias[:k].copy()}
+
+
+def model_resave(src: str, dst: str) -> None:
+    L = lib()
+    L.sc_model_resave.argtypes = [C.c_char_p, C.c_char_p]
+    rc = L.sc_model_resave(src.encode(), dst.encode())
+    if rc != SC_OK:
+        raise SurfCascadeError(rc, f"cannot re-save {src} -> {dst}")
 
 
 def pool_patches(tmpl: int = 40) -> np.ndarray:

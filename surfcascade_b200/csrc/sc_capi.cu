@@ -467,6 +467,32 @@ int sc_load_model(sc_handle* h, const char* path, int tmpl) {
     return sc_set_cascade(h, &d);
 }
 
+int sc_model_flatten(const char* path, int tmpl, float* theta, int32_t* n_weak, int max_stages, sc_rect* rects, int32_t* patch_index, float* w,
+                     double* bias, int max_weak, int* total_weak) {
+    if (!path) return SC_ERR_INVALID;
+    sc_host::FlatCascade fc;
+    std::string why;
+    if (!sc_host::load_flat_cascade(path, tmpl, &fc, &why)) return SC_ERR_IO;
+    const int S = (int)fc.theta.size(), T = (int)fc.bias.size();
+    if (total_weak) *total_weak = T;
+    for (int s = 0; s < S && s < max_stages; s++) {
+        if (theta) theta[s] = fc.theta[s];
+        if (n_weak) n_weak[s] = fc.n_weak[s];
+    }
+    for (int k = 0; k < T && k < max_weak; k++) {
+        if (rects) rects[k] = fc.rects[k];
+        if (patch_index) patch_index[k] = fc.patch_index[k];
+        if (w) memcpy(w + (size_t)k * 33, &fc.w[(size_t)k * 33], 33 * sizeof(float));
+        if (bias) bias[k] = fc.bias[k];
+    }
+    return S;
+}
+
+int sc_model_resave(const char* in_path, const char* out_path) {
+    if (!in_path || !out_path) return SC_ERR_INVALID;
+    return sc_host::resave_model(in_path, out_path) ? SC_OK : SC_ERR_IO;
+}
+
 int sc_pool_patches(int tmpl, sc_rect* out, int cap) {
     std::vector<sc_rect> pool;
     sc_host::pool_patches(tmpl, tmpl, &pool);

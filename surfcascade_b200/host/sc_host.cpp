@@ -155,7 +155,7 @@ void group_rectangles(std::vector<sc_rect>* rects, std::vector<double>* scores, 
 bool Access::flatten(CascadeClassifier& cc, int tmpl, FlatCascade* out, std::string* why) {
     std::vector<sc_rect> pool;
     pool_patches(tmpl, tmpl, &pool);
-    out->theta.clear(); out->n_weak.clear(); out->rects.clear(); out->w.clear(); out->bias.clear();
+    out->theta.clear(); out->n_weak.clear(); out->rects.clear(); out->patch_index.clear(); out->w.clear(); out->bias.clear();
     for (auto& st : cc.stage_classifiers) {
         GentleAdaboost* g = dynamic_cast<GentleAdaboost*>(st.get());
         if (!g) { if (why) *why = "stage is not a GentleAdaboost"; return false; }
@@ -164,12 +164,21 @@ bool Access::flatten(CascadeClassifier& cc, int tmpl, FlatCascade* out, std::str
         for (auto& wk : g->weak_classifiers) {
             if (wk->patch_index < 0 || wk->patch_index >= (int)pool.size()) { if (why) *why = "patch_index outside the template pool"; return false; }
             out->rects.push_back(pool[wk->patch_index]);
+            out->patch_index.push_back(wk->patch_index);
             out->w.insert(out->w.end(), wk->w, wk->w + 33);
             out->bias.push_back(wk->bias_);
         }
     }
     if (out->theta.empty()) { if (why) *why = "model holds no stages"; return false; }
     return true;
+}
+
+bool resave_model(const std::string& in_cfg, const std::string& out_cfg) {
+    CascadeClassifier cc;
+    Model in(in_cfg);
+    if (in.Load(cc) != EXIT_SUCCESS) return false;
+    Model out(out_cfg);
+    return out.Save(cc) == EXIT_SUCCESS;
 }
 
 bool load_flat_cascade(const std::string& model_cfg, int tmpl, FlatCascade* out, std::string* why) {

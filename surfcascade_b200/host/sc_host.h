@@ -37,9 +37,13 @@ struct FlatCascade {
     std::vector<float> theta;
     std::vector<int> n_weak;
     std::vector<sc_rect> rects;
+    std::vector<int> patch_index;
     std::vector<float> w;       // [total][33]
     std::vector<double> bias;
 };
+
+// Model::Load then Model::Save (round trip through this library's reader and writer)
+bool resave_model(const std::string& in_cfg, const std::string& out_cfg);
 
 // Model::Load + GetFittedPatchIndexes + dense_patches[patch_index], ObjDetector.cpp:108-130
 bool load_flat_cascade(const std::string& model_cfg, int tmpl, FlatCascade* out, std::string* why);

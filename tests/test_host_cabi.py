@@ -1,0 +1,103 @@
+"""CPU: the C-ABI library loads and exports every symbol include/surfcascade.h declares; host-only entry points
+(pool, projection, grouping, model file reader / writer) against the oracle.  No GPU compute here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import modelcfg as M
+from oracle import oracle as O
+from surfcascade_b200 import capi
+
+from conftest import MODEL_C1, ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "surfcascade.h")).read()
+    declared = set(re.findall(r"\b(sc_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    L = ctypes.CDLL(capi.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, f"declared in include/surfcascade.h but not exported: {missing}"
+    assert declared == set(capi.EXPORTS), (declared ^ set(capi.EXPORTS))
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.SurfCascadeError):
+        capi.Handle(0)
+
+
+def test_pool_and_projection_match_oracle():
+    pool = capi.pool_patches(40)
+    assert np.array_equal(pool, O.pool_patches(40))
+    for l in (40, 41, 44, 48, 53, 64, 97, 233, 1021):
+        assert np.array_equal(capi.project_patches(40, l, pool), O.project(40, l, pool)), l
+
+
+def test_model_reader_matches_oracle_parser():
+    got = capi.model_flatten(MODEL_C1, 40)
+    want = M.load(MODEL_C1)
+    assert np.array_equal(got["theta"].view(np.uint32), want.theta.view(np.uint32))
+    assert np.array_equal(got["n_weak"], want.n_weak) and np.array_equal(got["patch_index"], want.patch_index)
+    assert np.array_equal(got["w"].view(np.uint32), want.w.view(np.uint32)) and np.array_equal(got["bias"], want.bias)
+    assert np.array_equal(got["rects"], O.pool_patches(40)[want.patch_index])
+
+
+def test_model_writer_round_trips(tmp_path):
+    out = str(tmp_path / "resaved.cfg")
+    capi.model_resave(MODEL_C1, out)
+    a, b = capi.model_flatten(MODEL_C1, 40), capi.model_flatten(out, 40)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    # the oracle's parser (restating libconfig's grammar) reads the product's file to the same cascade
+    c = M.load(out)
+    assert np.array_equal(c.w.view(np.uint32), a["w"].view(np.uint32)) and np.array_equal(c.theta.view(np.uint32), a["theta"].view(np.uint32))
+    # and so does the reference's own libconfig-based loader, where it was compiled
+    from oracle import refbind as R
+    if R.available():
+        import ctypes as C
+        th = np.zeros(16, np.float32); nw = np.zeros(16, np.int32); pi = np.zeros(1024, np.int32); w = np.zeros((1024, 33), np.float32); bb = np.zeros(1024)
+        P = lambda x, t: x.ctypes.data_as(C.POINTER(t))
+        s = R.lib().ref_model_load(out.encode(), P(th, C.c_float), P(nw, C.c_int), 16, P(pi, C.c_int), P(w, C.c_float), P(bb, C.c_double), 1024)
+        k = int(nw[:s].sum())
+        assert s == len(a["theta"]) and np.array_equal(w[:k].view(np.uint32), a["w"].view(np.uint32)) and np.array_equal(pi[:k], a["patch_index"])
+
+
+def test_model_reader_error_behaviour(tmp_path):
+    """Model::Load semantics (Model.cpp:103-116,188-191): unreadable / unparsable -> failure; a missing setting ends the
+    load silently and keeps the stages completed so far."""
+    with pytest.raises(capi.SurfCascadeError):
+        capi.model_flatten(str(tmp_path / "missing.cfg"), 40)
+    bad = tmp_path / "bad.cfg"
+    bad.write_text("cascade_classifier : { max_stages_num = ; }")
+    with pytest.raises(capi.SurfCascadeError):
+        capi.model_flatten(str(bad), 40)
+    text = open(MODEL_C1).read()
+    # drop the LAST stage's theta: the reference keeps stages 0..n-2 and stops
+    idx = text.rfind("theta = ")
+    trunc = tmp_path / "trunc.cfg"
+    trunc.write_text(text[:idx] + "not_theta = " + text[idx + len("theta = "):])
+    full = capi.model_flatten(MODEL_C1, 40)
+    part = capi.model_flatten(str(trunc), 40)
+    assert len(part["theta"]) == len(full["theta"]) - 1
+    assert np.array_equal(part["w"], full["w"][:len(part["w"])])
+    assert len(M.load(str(trunc)).theta) == len(part["theta"])
+
+
+def test_group_rectangles_matches_oracle():
+    rng = np.random.default_rng(3)
+    for trial in range(40):
+        n = int(rng.integers(0, 80))
+        base = rng.integers(0, 300, size=(max(1, n // 5), 2))
+        xy = base[rng.integers(0, len(base), n)] + rng.integers(-5, 6, size=(n, 2)) if n else np.zeros((0, 2), np.int64)
+        l = rng.integers(40, 70, size=(n, 1))
+        rects = np.concatenate([xy, l, l], 1).astype(np.int32)
+        scores = rng.random(n) + 1.0
+        gr, gs = capi.group_rectangles(rects, scores)
+        wr, ws = O.group_rectangles(rects, scores)
+        assert np.array_equal(gr, wr) and np.array_equal(gs, ws)

@@ -1,0 +1,66 @@
+"""CPU: the oracle against the reference build itself (oracle/_ref), on fresh seeded inputs.  Skipped where the
+reference was never compiled (it needs /root/reference at build time; the .so travels with the snapshot)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from oracle import refbind as R
+from surfcascade_b200 import synth
+
+from conftest import MODEL_C1
+
+pytestmark = pytest.mark.skipif(not R.available(), reason="oracle/_ref not built")
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+@pytest.mark.parametrize("shape,seed", [((64, 64), 0), ((117, 203), 1), ((255, 257), 2)])
+def test_integral_and_channels(shape, seed):
+    for img in (synth.frame(*shape, seed), synth.noise_frame(*shape, seed)):
+        assert np.array_equal(O.channels(img), R.channels(img))
+        assert np.array_equal(bits(O.integral(img)), bits(R.integral(img)))
+
+
+def test_opencv_standin_matches_cv2():
+    """The stand-in cv::integral / cv::groupRectangles used to compile the reference against real OpenCV (cv2 wheel)."""
+    cv2 = pytest.importorskip("cv2")
+    img = synth.noise_frame(300, 500, 3)
+    ch = R.channels(img)
+    S = R.integral(img)
+    for c in range(8):
+        assert np.array_equal(bits(S[:, :, c]), bits(cv2.integral(ch[c], sdepth=cv2.CV_32F)))
+    rng = np.random.default_rng(0)
+    for trial in range(60):
+        n = int(rng.integers(1, 60))
+        base = rng.integers(0, 200, size=(max(1, n // 6), 2))
+        r = np.concatenate([base[rng.integers(0, len(base), n)] + rng.integers(-6, 7, size=(n, 2)), rng.integers(30, 60, size=(n, 1))], 1)
+        rects = np.stack([r[:, 0], r[:, 1], r[:, 2], r[:, 2]], 1).astype(np.int32)
+        want, _ = cv2.groupRectangles(rects.tolist(), 2, 0.2)
+        got, _ = O.group_rectangles(rects, np.ones(n))
+        assert sorted(map(tuple, np.asarray(want).reshape(-1, 4).tolist())) == sorted(map(tuple, got.tolist()))
+
+
+def test_features_bit_exact(oracle_cascade):
+    img = synth.frame(200, 300, 5)
+    S = O.integral(img)
+    pool = O.pool_patches(40)
+    for (x, y, l) in [(0, 0, 40), (3, 5, 53), (60, 0, 200), (11, 13, 171)]:
+        pr = R.project(40, [x, y, l, l], pool)
+        po = O.project(40, l, pool)
+        po[:, 0] += x; po[:, 1] += y
+        assert np.array_equal(pr, po)
+        fr, sr = R.features(img, pr)
+        fo, so = O.features(S, po)
+        assert np.array_equal(bits(fr), bits(fo)) and np.array_equal(bits(sr), bits(so))
+
+
+@pytest.mark.parametrize("shape,seed,base,threads", [((120, 160), 0, 40, 1), ((240, 320), 1, 40, 4), ((301, 517), 2, 70, 2), ((480, 640), 3, 40, 8)])
+def test_detect_identical(oracle_cascade, shape, seed, base, threads):
+    img = synth.frame(*shape, seed)
+    r = R.detect([img], MODEL_C1, base=base, nthreads=threads)
+    d = O.detect(O.integral(img), oracle_cascade, O.params(base=base, nthreads=threads))
+    assert np.array_equal(d.x, r.x) and np.array_equal(d.y, r.y) and np.array_equal(d.l, r.l) and np.array_equal(d.score, r.score)
+    c = r.counters[0]
+    assert (d.counters[O.C_VISITED], d.counters[O.C_PREFILTER], d.counters[O.C_WEAK], d.counters[O.C_RAW]) == (c[0], c[1], c[2], c[3])
