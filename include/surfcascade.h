@@ -121,6 +121,23 @@ int sc_weak_predict(sc_handle* h, const float* w, const double* bias, const floa
  * weak classifiers in order; *out = float32 running sum of their probabilities / n. */
 int sc_stage_predict(sc_handle* h, const float* w, const double* bias, const float* x, int n, float* out);
 
+/* ---- training-side pool evaluation (BASELINE config 5) ------------------------------------ */
+#define SC_POOL_HIST_BINS 21  /* 20 AUC thresholds (StageClassifier.cpp:59) + "below all" */
+/* Candidate scoring of one boosting round: GentleAdaboost.cpp:145-148 -> StageClassifier::Evaluate
+ * (StageClassifier.cpp:35-70) over GentleAdaboost::Predict (GentleAdaboost.cpp:233-245).  For every pool patch k the
+ * candidate weak classifier (Wcand[k], bias[k]) is appended to the T classifiers already chosen:
+ *   prob_n = float(prior_sum[n] + p_k(X[n][k])) / (T + 1),   auc[k] = trapezoid AUC over the 20 float thresholds.
+ * X [N][P][32] descriptors, labels [N] (non-zero = positive), Wcand [P][33], bias [P], prior_sum [N] or null, auc [P].
+ * All buffers in host memory. */
+int sc_pool_eval(sc_handle* h, const float* X, int N, int P, const uint8_t* labels, const float* Wcand, const double* bias,
+                 const float* prior_sum, int T, float* auc);
+/* The streaming half on device-resident shards (X, labels, prior_sum in device memory): adds this shard's level
+ * histograms into d_hist [P][2][SC_POOL_HIST_BINS] (uint32, caller-zeroed; class 1 = positive).  Asynchronous. */
+int sc_pool_hist_device(sc_handle* h, const float* d_X, int N, int P, const uint8_t* d_labels, const float* Wcand, const double* bias,
+                        const float* d_prior_sum, int T, uint32_t* d_hist);
+/* The epilogue: AUC of every candidate from (all-reduced) histograms in device memory; auc [P] in host memory. */
+int sc_pool_auc_device(sc_handle* h, const uint32_t* d_hist, int P, int64_t n_pos, int64_t n_neg, float* auc);
+
 /* ---- detection -------------------------------------------------------------------------------------- */
 /* The detect path of ObjDetector.cpp:165,174-219 on a batch of equally sized gray frames held in HOST memory:
  * upload, integral, scan, adaptive-stride replay, download.  Detections are sorted by (frame, l, y, x).

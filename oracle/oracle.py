@@ -180,3 +180,16 @@ def group_rectangles(rects, scores, thr: int = 2, eps: float = 0.2):
     out_r = np.zeros((max(n, 1), 4), np.int32); out_s = np.zeros(max(n, 1), np.float64)
     m = lib().so_group_rectangles(_p(r, C.c_int32), _p(s, C.c_double), n, thr, C.c_double(eps), _p(out_r, C.c_int32), _p(out_s, C.c_double), max(n, 1))
     return out_r[:m].copy(), out_s[:m].copy()
+
+
+def pool_eval(X, n_pos: int, Wcand, bias, prior_sum=None, T: int = 0) -> np.ndarray:
+    """AUC of every candidate weak classifier (row A9 / config C5).  X [N][P][32]."""
+    X = np.ascontiguousarray(X, np.float32)
+    N, P, _ = X.shape
+    Wcand = np.ascontiguousarray(Wcand, np.float32).reshape(P, 33)
+    bias = np.ascontiguousarray(bias, np.float64).reshape(P)
+    auc = np.zeros(P, np.float32)
+    ps = np.ascontiguousarray(prior_sum, np.float32) if prior_sum is not None else None
+    lib().so_pool_eval(_p(X, C.c_float), N, P, n_pos, _p(Wcand, C.c_float), _p(bias, C.c_double), _p(ps, C.c_float) if ps is not None else None, T,
+                       _p(auc, C.c_float))
+    return auc

@@ -289,6 +289,34 @@ int ref_detect_frames(const uint8_t* const* frames, int nframes, int W, int H, c
     return 0;
 }
 
+// Candidate scoring of one boosting round exactly as GentleAdaboost::Train does it (GentleAdaboost.cpp:145-148): the
+// stage holds the T already chosen weak classifiers (prev_* arrays), candidate k is pushed, StageClassifier::Evaluate
+// (StageClassifier.cpp:35-70) is called on the whole set, the candidate is popped.  X [N][P][32], positives first.
+int ref_pool_eval(const float* X, int N, int P, int n_pos, const float* Wcand, const double* bias, const int* prev_patch, const float* prev_w,
+                  const double* prev_bias, int T, float* auc) {
+    vector<vector<vector<float> > > Xv(N, vector<vector<float> >(P, vector<float>(32)));
+    for (int n = 0; n < N; n++)
+        for (int k = 0; k < P; k++) memcpy(Xv[n][k].data(), X + ((size_t)n * P + k) * 32, 32 * sizeof(float));
+    vector<bool> y(N, false);
+    for (int n = 0; n < n_pos; n++) y[n] = true;
+    GentleAdaboost stage(0.995f);
+    stage.n_total = N; stage.n_pos = n_pos; stage.n_neg = N - n_pos;
+    auto make = [](int patch, const float* w33, double b) {
+        std::shared_ptr<LogisticRegression> lr(new LogisticRegression(patch));
+        memcpy(lr->w, w33, 33 * sizeof(float));
+        lr->model_ = new model;
+        lr->model_->bias = b;
+        return lr;
+    };
+    for (int t = 0; t < T; t++) stage.weak_classifiers.push_back(make(prev_patch[t], prev_w + 33 * (size_t)t, prev_bias[t]));
+    for (int k = 0; k < P; k++) {
+        stage.weak_classifiers.push_back(make(k, Wcand + 33 * (size_t)k, bias[k]));
+        auc[k] = stage.Evaluate(Xv, y);
+        stage.weak_classifiers.pop_back();
+    }
+    return 0;
+}
+
 // The reference --train branch on PGM files: `prefix` is a directory ending in '/', the two
 // list files hold one file name per line relative to it.  Writes the model with Model::Save.
 // The extractor keeps function-local static cursors, so this can run ONCE per process.

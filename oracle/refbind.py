@@ -152,6 +152,27 @@ def train(prefix: str, pos_list: str, neg_list: str, out_cfg: str, verbose: bool
     return lib().ref_train(prefix.encode(), pos_list.encode(), neg_list.encode(), out_cfg.encode(), 1 if verbose else 0)
 
 
+def pool_eval(X, n_pos: int, Wcand, bias, prev_patch=(), prev_w=(), prev_bias=()) -> np.ndarray:
+    """GentleAdaboost::Train's candidate scoring (GentleAdaboost.cpp:145-148 -> StageClassifier::Evaluate)."""
+    X = np.ascontiguousarray(X, np.float32)
+    N, P, _ = X.shape
+    Wcand = np.ascontiguousarray(Wcand, np.float32).reshape(P, 33)
+    bias = np.ascontiguousarray(bias, np.float64).reshape(P)
+    pp = np.ascontiguousarray(prev_patch, np.int32).reshape(-1)
+    pw = np.ascontiguousarray(prev_w, np.float32).reshape(-1, 33) if len(pp) else np.zeros((1, 33), np.float32)
+    pb = np.ascontiguousarray(prev_bias, np.float64).reshape(-1) if len(pp) else np.zeros(1)
+    if not len(pp):
+        pp = np.zeros(1, np.int32)
+        T = 0
+    else:
+        T = len(pp)
+    auc = np.zeros(P, np.float32)
+    P_ = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    lib().ref_pool_eval(P_(X, C.c_float), N, P, n_pos, P_(Wcand, C.c_float), P_(bias, C.c_double), P_(pp, C.c_int32), P_(pw, C.c_float),
+                        P_(pb, C.c_double), T, P_(auc, C.c_float))
+    return auc
+
+
 def write_pgm(path: str, img: np.ndarray) -> None:
     img = np.ascontiguousarray(img, dtype=np.uint8)
     with open(path, "wb") as f:

@@ -386,3 +386,35 @@ int so_group_rectangles(const int32_t* r, const double* scores, int n, int thr, 
     free(parent); free(label); free(id); free(acc); free(members); free(best);
     return m;
 }
+
+/* ---- training-side pool evaluation (row A9, config C5) --------------------------------------------------- */
+
+/* Candidate scoring of one boosting round, GentleAdaboost.cpp:145-148: the candidate weak classifier k (on pool patch
+ * k) is appended to the T already chosen ones and StageClassifier::Evaluate (StageClassifier.cpp:35-70) computes the
+ * AUC of GentleAdaboost::Predict (GentleAdaboost.cpp:233-245) over all samples: prob_n = (prior_n + p_k(x_n[k])) / (T+1)
+ * in float, positives first; 20 float thresholds 1, 1-0.05f, ...; TPR/FPR by >=; trapezoid area in float.
+ * X [N][P][32], Wcand [P][33], bias [P], prior_sum [N] (float running sum of the T chosen outputs; NULL -> 0). */
+void so_pool_eval(const float* X, int N, int P, int n_pos, const float* Wcand, const double* bias, const float* prior_sum, int T, float* auc) {
+    int n_neg = N - n_pos;
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < P; k++) {
+        float area = 0.f, tpr_prev = 0.f, fpr_prev = 0.f;
+        int it = 0;
+        float* probs = (float*)malloc(sizeof(float) * (size_t)N);
+        for (int n = 0; n < N; n++) {
+            float sum = prior_sum ? prior_sum[n] : 0.f;
+            sum += so_weak(Wcand + 33 * (size_t)k, bias[k], X + ((size_t)n * P + k) * SO_DIM);
+            probs[n] = sum / (float)(T + 1);
+        }
+        for (float t = 1; t >= 0; t -= 0.05f, it++) {
+            long cp = 0, cn = 0;
+            for (int n = 0; n < n_pos; n++) cp += probs[n] >= t;
+            for (int n = n_pos; n < N; n++) cn += probs[n] >= t;
+            float tpr = cp / (float)n_pos, fpr = cn / (float)n_neg;
+            if (it > 0) area += (tpr + tpr_prev) * (fpr - fpr_prev) / 2;
+            tpr_prev = tpr; fpr_prev = fpr;
+        }
+        auc[k] = area;
+        free(probs);
+    }
+}

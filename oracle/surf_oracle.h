@@ -68,6 +68,9 @@ int64_t so_detect(const float* S, int W, int H, const so_cascade* c, const so_pa
 int so_group_rectangles(const int32_t* rects, const double* scores, int n, int thr, double eps,
                         int32_t* out_rects, double* out_scores, int cap);
 
+/* Candidate scoring for boosting (GentleAdaboost.cpp:145-148 -> StageClassifier::Evaluate, StageClassifier.cpp:35-70). */
+void so_pool_eval(const float* X, int N, int P, int n_pos, const float* Wcand, const double* bias, const float* prior_sum, int T, float* auc);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,7 +42,8 @@ assert DETECTION_DTYPE.itemsize == 24
 EXPORTS = ["sc_create", "sc_destroy", "sc_last_error", "sc_version", "sc_set_cascade", "sc_load_model", "sc_pool_patches", "sc_project_patches",
            "sc_integral", "sc_features", "sc_window_sum", "sc_stage_scores", "sc_weak_predict", "sc_stage_predict", "sc_detect",
            "sc_detect_device", "sc_sync", "sc_last_counters", "sc_stream", "sc_launch_count", "sc_group_rectangles",
-           "sc_set_profiling", "sc_kernel_stats", "sc_model_flatten", "sc_model_resave"]
+           "sc_set_profiling", "sc_kernel_stats", "sc_model_flatten", "sc_model_resave", "sc_pool_eval", "sc_pool_hist_device",
+           "sc_pool_auc_device"]
 
 _lib = None
 
@@ -241,6 +242,34 @@ class Handle:
         out = np.zeros(1, np.float32)
         self._check(lib().sc_stage_predict(self._h, w.ctypes.data, bias.ctypes.data, x.ctypes.data, len(w), out.ctypes.data))
         return float(out[0])
+
+    # ---- training-side pool evaluation ----
+    def pool_eval(self, X, labels, Wcand, bias, prior_sum=None, T: int = 0) -> np.ndarray:
+        """AUC of every candidate weak classifier; X [N][P][32] host array, labels [N] (non-zero = positive)."""
+        X = np.ascontiguousarray(X, np.float32)
+        N, P, _ = X.shape
+        labels = np.ascontiguousarray(labels, np.uint8).reshape(N)
+        Wcand = np.ascontiguousarray(Wcand, np.float32).reshape(P, 33); bias = np.ascontiguousarray(bias, np.float64).reshape(P)
+        ps = np.ascontiguousarray(prior_sum, np.float32).reshape(N) if prior_sum is not None else None
+        auc = np.zeros(P, np.float32)
+        L = lib()
+        L.sc_pool_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        self._check(L.sc_pool_eval(self._h, X.ctypes.data, N, P, labels.ctypes.data, Wcand.ctypes.data, bias.ctypes.data,
+                                   ps.ctypes.data if ps is not None else None, T, auc.ctypes.data))
+        return auc
+
+    def pool_hist_device(self, d_X: int, N: int, P: int, d_labels: int, Wcand, bias, d_prior: int | None, T: int, d_hist: int):
+        Wcand = np.ascontiguousarray(Wcand, np.float32).reshape(P, 33); bias = np.ascontiguousarray(bias, np.float64).reshape(P)
+        L = lib()
+        L.sc_pool_hist_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        self._check(L.sc_pool_hist_device(self._h, d_X, N, P, d_labels, Wcand.ctypes.data, bias.ctypes.data, d_prior, T, d_hist))
+
+    def pool_auc_device(self, d_hist: int, P: int, n_pos: int, n_neg: int) -> np.ndarray:
+        auc = np.zeros(P, np.float32)
+        L = lib()
+        L.sc_pool_auc_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p]
+        self._check(L.sc_pool_auc_device(self._h, d_hist, P, n_pos, n_neg, auc.ctypes.data))
+        return auc
 
     # ---- detection ----
     def detect(self, frames, prm: DetectParams | None = None, cap: int = 1 << 20):

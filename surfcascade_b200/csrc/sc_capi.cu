@@ -93,14 +93,15 @@ struct sc_handle {
     int cur_W = 0, cur_H = 0;
     ScLayout hook_lay{};
     DevBuf d_hook_img, d_hook_carry, d_hook_S;
+    DevBuf d_pool_w, d_pool_wb, d_pool_auc, d_pool_x, d_pool_aux;  // training-side pool evaluation
 
     // optional per-kernel timing with CUDA events on the handle's stream (bench.py's roofline leg)
     bool profiling = false;
     struct Span { int kid; cudaEvent_t a, b; };
     std::vector<Span> spans;
     std::vector<cudaEvent_t> event_pool;
-    double kernel_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int64_t kernel_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double kernel_ms[16] = {0};
+    int64_t kernel_launches[16] = {0};
 };
 
 namespace {
@@ -123,9 +124,9 @@ int cuda_fail(sc_handle* h, cudaError_t e, const char* what) {
         if (e_ != cudaSuccess) return cuda_fail((h), e_, #call); \
     } while (0)
 
-enum { K_CARRY = 0, K_WALK, K_STAGE0, K_STAGE, K_REPLAY, K_FINALIZE, K_EVENTS, K_COUNT };
+enum { K_CARRY = 0, K_WALK, K_STAGE0, K_STAGE, K_REPLAY, K_FINALIZE, K_EVENTS, K_POOL, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"k_strip_carry", "k_integral_walk", "k_scan_stage0", "k_scan_stage", "k_replay_rows", "k_finalize",
-                                            "k_row_events"};
+                                            "k_row_events", "k_pool_hist"};
 
 cudaEvent_t take_event(sc_handle* h) {
     cudaEvent_t e = nullptr;
@@ -405,7 +406,7 @@ void sc_destroy(sc_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     DevBuf* bufs[] = {&h->d_w, &h->d_wb, &h->d_plan, &h->d_geom, &h->d_img, &h->d_carry, &h->d_S, &h->d_multi, &h->d_pass, &h->d_visited,
-                      &h->d_rec, &h->d_idx[0], &h->d_idx[1], &h->d_small, &h->d_counters, &h->d_det, &h->d_start, &h->d_hook_img, &h->d_hook_carry, &h->d_hook_S};
+                      &h->d_rec, &h->d_idx[0], &h->d_idx[1], &h->d_small, &h->d_counters, &h->d_det, &h->d_start, &h->d_pool_w, &h->d_pool_wb, &h->d_pool_auc, &h->d_pool_x, &h->d_pool_aux, &h->d_hook_img, &h->d_hook_carry, &h->d_hook_S};
     for (DevBuf* b : bufs) b->release();
     h->h_stage.release();
     for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -650,6 +651,85 @@ int sc_weak_predict(sc_handle* h, const float* w, const double* bias, const floa
 }
 int sc_stage_predict(sc_handle* h, const float* w, const double* bias, const float* x, int n, float* out) {
     return predict_impl(h, w, bias, x, n, out, true);
+}
+
+static void pool_thresholds(float* thr) {
+    int i = 0;
+    for (float t = 1; t >= 0 && i < SC_POOL_LEVELS - 1; t -= 0.05f) thr[i++] = t;  // StageClassifier.cpp:59, auc_step = 0.05f
+    while (i < SC_POOL_LEVELS - 1) thr[i++] = -1.f;
+}
+
+int sc_pool_hist_device(sc_handle* h, const float* d_X, int N, int P, const uint8_t* d_labels, const float* Wcand, const double* bias,
+                        const float* d_prior_sum, int T, uint32_t* d_hist) {
+    if (!h || !d_X || !d_labels || !Wcand || !bias || !d_hist || N < 1 || P < 1 || T < 0) return fail(h, SC_ERR_INVALID, "bad arguments");
+    SC_CUDA(h, cudaSetDevice(h->device));
+    std::vector<float> w36((size_t)P * SC_W_PITCH, 0.f);
+    std::vector<double> wb(P);
+    for (int k = 0; k < P; k++) {
+        memcpy(&w36[(size_t)k * SC_W_PITCH], Wcand + (size_t)k * 33, 33 * sizeof(float));
+        wb[k] = (double)Wcand[(size_t)k * 33 + 32] * bias[k];
+    }
+    float thr[SC_POOL_LEVELS - 1];
+    pool_thresholds(thr);
+    SC_CUDA(h, h->d_pool_w.ensure(w36.size() * 4));
+    SC_CUDA(h, h->d_pool_wb.ensure((size_t)P * 8 + sizeof(thr)));
+    // synchronous small uploads: the stream may still be reading the previous call's copies
+    SC_CUDA(h, cudaStreamSynchronize(h->stream));
+    SC_CUDA(h, cudaMemcpy(h->d_pool_w.p, w36.data(), w36.size() * 4, cudaMemcpyHostToDevice));
+    SC_CUDA(h, cudaMemcpy(h->d_pool_wb.p, wb.data(), (size_t)P * 8, cudaMemcpyHostToDevice));
+    float* d_thr = reinterpret_cast<float*>(h->d_pool_wb.as<unsigned char>() + (size_t)P * 8);
+    SC_CUDA(h, cudaMemcpy(d_thr, thr, sizeof(thr), cudaMemcpyHostToDevice));
+    const int kchunks = (P + SC_POOL_KC - 1) / SC_POOL_KC;
+    const int nchunks = (N + SC_POOL_NC - 1) / SC_POOL_NC;
+    const int slices = std::max(1, std::min(nchunks, (h->n_sms * 4 + kchunks - 1) / kchunks));
+    {
+        KernelSpan ks(h, K_POOL);
+        sck::k_pool_hist<<<kchunks * slices, 256, 0, h->stream>>>(d_X, N, P, d_labels, h->d_pool_w.as<float>(), h->d_pool_wb.as<double>(), d_prior_sum,
+                                                                  (float)(T + 1), d_thr, slices, d_hist);
+    }
+    SC_CUDA(h, cudaGetLastError());
+    return SC_OK;
+}
+
+int sc_pool_auc_device(sc_handle* h, const uint32_t* d_hist, int P, int64_t n_pos, int64_t n_neg, float* auc) {
+    if (!h || !d_hist || !auc || P < 1 || n_pos < 1 || n_neg < 1) return fail(h, SC_ERR_INVALID, "bad arguments");
+    SC_CUDA(h, cudaSetDevice(h->device));
+    SC_CUDA(h, h->d_pool_auc.ensure((size_t)P * 4));
+    sck::k_pool_auc<<<(P + 127) / 128, 128, 0, h->stream>>>(d_hist, P, (float)n_pos, (float)n_neg, h->d_pool_auc.as<float>());
+    h->launches++;
+    SC_CUDA(h, cudaGetLastError());
+    SC_CUDA(h, cudaMemcpyAsync(auc, h->d_pool_auc.p, (size_t)P * 4, cudaMemcpyDeviceToHost, h->stream));
+    SC_CUDA(h, cudaStreamSynchronize(h->stream));
+    drain_spans(h);
+    return SC_OK;
+}
+
+int sc_pool_eval(sc_handle* h, const float* X, int N, int P, const uint8_t* labels, const float* Wcand, const double* bias, const float* prior_sum,
+                 int T, float* auc) {
+    if (!h || !X || !labels || !Wcand || !bias || !auc || N < 1 || P < 1) return fail(h, SC_ERR_INVALID, "bad arguments");
+    SC_CUDA(h, cudaSetDevice(h->device));
+    int64_t n_pos = 0;
+    for (int n = 0; n < N; n++) n_pos += labels[n] != 0;
+    if (n_pos == 0 || n_pos == N) return fail(h, SC_ERR_INVALID, "need both positive and negative samples");
+    const size_t hist_bytes = (size_t)P * 2 * SC_POOL_LEVELS * 4;
+    // stream X through a bounded device buffer in sample chunks
+    const size_t row = (size_t)P * 32 * 4;
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)N, ((size_t)1 << 30) / row));
+    SC_CUDA(h, h->d_pool_x.ensure((size_t)chunk * row));
+    SC_CUDA(h, h->d_pool_aux.ensure(hist_bytes + (size_t)chunk * 5 + 64));
+    uint32_t* d_hist = h->d_pool_aux.as<uint32_t>();
+    float* d_prior = reinterpret_cast<float*>(h->d_pool_aux.as<unsigned char>() + hist_bytes);
+    uint8_t* d_lab = h->d_pool_aux.as<unsigned char>() + hist_bytes + (size_t)chunk * 4;
+    SC_CUDA(h, cudaMemsetAsync(d_hist, 0, hist_bytes, h->stream));
+    for (int n0 = 0; n0 < N; n0 += chunk) {
+        const int m = std::min(chunk, N - n0);
+        SC_CUDA(h, cudaMemcpyAsync(h->d_pool_x.p, X + (size_t)n0 * P * 32, (size_t)m * row, cudaMemcpyHostToDevice, h->stream));
+        SC_CUDA(h, cudaMemcpyAsync(d_lab, labels + n0, (size_t)m, cudaMemcpyHostToDevice, h->stream));
+        if (prior_sum) SC_CUDA(h, cudaMemcpyAsync(d_prior, prior_sum + n0, (size_t)m * 4, cudaMemcpyHostToDevice, h->stream));
+        int rc = sc_pool_hist_device(h, h->d_pool_x.as<float>(), m, P, d_lab, Wcand, bias, prior_sum ? d_prior : nullptr, T, d_hist);
+        if (rc != SC_OK) return rc;
+    }
+    return sc_pool_auc_device(h, d_hist, P, n_pos, N - n_pos, auc);
 }
 
 int sc_detect_device(sc_handle* h, const uint8_t* d_frames, int nframes, int W, int H, const sc_detect_params* params, sc_detection* d_out,

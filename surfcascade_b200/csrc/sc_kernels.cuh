@@ -675,6 +675,102 @@ __global__ void k_weak_predict(const float* __restrict__ w36, const double* __re
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Training-side pool evaluation: candidate scoring of one boosting round,
+// GentleAdaboost.cpp:145-148 -> StageClassifier::Evaluate (StageClassifier.cpp:35-70) over
+// GentleAdaboost::Predict (GentleAdaboost.cpp:233-245).  HBM-bound stream over X [N][P][32].
+// ---------------------------------------------------------------------------------------------------------
+#define SC_POOL_LEVELS 21   // 20 thresholds 1, 1-0.05f, ... (float t = 1; t >= 0; t -= 0.05f) + "below all"
+#define SC_POOL_KC 32       // candidates per CTA tile
+#define SC_POOL_NC 8        // samples per CTA tile
+
+// hist[k][cls][level]: number of samples of class cls (1 = positive) whose stage probability with candidate k first
+// reaches threshold index `level` (level 20 = below every threshold)
+__global__ void __launch_bounds__(256) k_pool_hist(const float* __restrict__ X, int N, int P, const uint8_t* __restrict__ labels,
+                                                    const float* __restrict__ w36, const double* __restrict__ wb,
+                                                    const float* __restrict__ prior_sum, float inv_count_as_divisor,
+                                                    const float* __restrict__ thresholds, int sample_slices, uint32_t* __restrict__ hist) {
+    __shared__ float s_x[SC_POOL_NC * SC_POOL_KC][33];
+    __shared__ float s_w[SC_POOL_KC][33];
+    __shared__ double s_wb[SC_POOL_KC];
+    __shared__ float s_thr[SC_POOL_LEVELS - 1];
+    __shared__ uint32_t s_hist[SC_POOL_KC][2][SC_POOL_LEVELS];
+    const int tid = threadIdx.x;
+    const int kc = blockIdx.x / sample_slices, slice = blockIdx.x - kc * sample_slices;
+    const int k0 = kc * SC_POOL_KC;
+    for (int i = tid; i < SC_POOL_KC * 33; i += 256) {
+        const int k = i / 33, j = i - k * 33;
+        s_w[k][j] = (k0 + k < P) ? w36[(size_t)(k0 + k) * SC_W_PITCH + j] : 0.f;
+    }
+    if (tid < SC_POOL_KC) s_wb[tid] = (k0 + tid < P) ? wb[k0 + tid] : 0.0;
+    if (tid < SC_POOL_LEVELS - 1) s_thr[tid] = thresholds[tid];
+    for (int i = tid; i < SC_POOL_KC * 2 * SC_POOL_LEVELS; i += 256) (&s_hist[0][0][0])[i] = 0;
+    __syncthreads();
+    const int kl = tid & 31, nl = tid >> 5;
+    const int n_chunks = (N + SC_POOL_NC - 1) / SC_POOL_NC;
+    for (int chunk = slice; chunk < n_chunks; chunk += sample_slices) {
+        const int n0 = chunk * SC_POOL_NC;
+        // coalesced tile load: per sample 32 candidates x 128 B contiguous
+#pragma unroll
+        for (int it = 0; it < SC_POOL_NC; it++) {
+            const int n = n0 + it;
+            const int e = tid;                       // float4 index inside the 4 KB row: candidate e / 8, quad e % 8
+            const int k = e >> 3, q = e & 7;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < N && k0 + k < P) v = __ldg(reinterpret_cast<const float4*>(X + ((size_t)n * P + k0 + k) * 32) + q);
+            float* dst = &s_x[it * SC_POOL_KC + k][4 * q];
+            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+        }
+        __syncthreads();
+        const int n = n0 + nl;
+        if (n < N && k0 + kl < P) {
+            // LogisticRegression::Predict, same operation order as weak_predict()
+            const float* x = s_x[nl * SC_POOL_KC + kl];
+            const float* w = s_w[kl];
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                s0 = __fadd_rn(__fmul_rn(w[i], x[i]), s0);
+                s1 = __fadd_rn(__fmul_rn(w[i + 1], x[i + 1]), s1);
+                s2 = __fadd_rn(__fmul_rn(w[i + 2], x[i + 2]), s2);
+                s3 = __fadd_rn(__fmul_rn(w[i + 3], x[i + 3]), s3);
+            }
+            const float z32 = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
+            const double z = (double)z32 + s_wb[kl];
+            const float p = (float)(1.0 / (1.0 + exp(-z)));
+            // GentleAdaboost::Predict: float running sum (prior + candidate last), divided by the classifier count
+            const float prob = __fdiv_rn(__fadd_rn(prior_sum ? prior_sum[n] : 0.f, p), inv_count_as_divisor);
+            int level = 0;
+#pragma unroll
+            for (int i = 0; i < SC_POOL_LEVELS - 1; i++) level += !(prob >= s_thr[i]);  // thresholds decrease
+            atomicAdd(&s_hist[kl][labels[n] ? 1 : 0][level], 1u);
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < SC_POOL_KC * 2 * SC_POOL_LEVELS; i += 256) {
+        const int k = i / (2 * SC_POOL_LEVELS);
+        const uint32_t v = (&s_hist[0][0][0])[i];
+        if (v && k0 + k < P) atomicAdd(&hist[(size_t)k0 * 2 * SC_POOL_LEVELS + i], v);
+    }
+}
+
+// StageClassifier::Evaluate's trapezoid AUC from the level histograms (float arithmetic as StageClassifier.cpp:59-66)
+__global__ void k_pool_auc(const uint32_t* __restrict__ hist, int P, float n_pos, float n_neg, float* __restrict__ auc) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= P) return;
+    const uint32_t* hn = hist + (size_t)k * 2 * SC_POOL_LEVELS;  // class 0 = negatives
+    const uint32_t* hp = hn + SC_POOL_LEVELS;
+    unsigned long long cp = 0, cn = 0;
+    float area = 0.f, tpr_prev = 0.f, fpr_prev = 0.f;
+    for (int i = 0; i < SC_POOL_LEVELS - 1; i++) {
+        cp += hp[i]; cn += hn[i];  // samples with prob >= t_i
+        const float tpr = __fdiv_rn((float)cp, n_pos), fpr = __fdiv_rn((float)cn, n_neg);
+        if (i > 0) area = __fadd_rn(area, __fmul_rn(__fmul_rn(__fadd_rn(tpr, tpr_prev), __fsub_rn(fpr, fpr_prev)), 0.5f));
+        tpr_prev = tpr; fpr_prev = fpr;
+    }
+    auc[k] = area;
+}
+
 }  // namespace sck
 
 #endif

@@ -64,3 +64,26 @@ def test_detect_identical(oracle_cascade, shape, seed, base, threads):
     assert np.array_equal(d.x, r.x) and np.array_equal(d.y, r.y) and np.array_equal(d.l, r.l) and np.array_equal(d.score, r.score)
     c = r.counters[0]
     assert (d.counters[O.C_VISITED], d.counters[O.C_PREFILTER], d.counters[O.C_WEAK], d.counters[O.C_RAW]) == (c[0], c[1], c[2], c[3])
+
+
+def test_pool_eval():
+    """Row A9 / config 5: the oracle's candidate scoring against the reference's own StageClassifier::Evaluate."""
+    rng = np.random.default_rng(0)
+    pool = O.pool_patches(40)
+    P = 40
+    sel = np.linspace(0, 607, P).astype(int)
+    N, n_pos = 90, 40
+    X = np.zeros((N, P, 32), np.float32)
+    for n in range(N):
+        img = synth.positive(n) if n < n_pos else np.ascontiguousarray(synth.negative_frame(n)[:40, :40])
+        X[n] = O.features(O.integral(img), pool[sel])[0]
+    W = rng.normal(0, 1.2, size=(P, 33)).astype(np.float32)
+    b = np.ones(P)
+    assert np.array_equal(bits(O.pool_eval(X, n_pos, W, b)), bits(R.pool_eval(X, n_pos, W, b)))
+    prev_patch = [3, 17, 5]
+    prev_w = rng.normal(0, 1, size=(3, 33)).astype(np.float32)
+    prior = np.zeros(N, np.float32)
+    for t in range(3):
+        for n in range(N):
+            prior[n] = np.float32(prior[n] + np.float32(O.weak(prev_w[t], 1.0, X[n, prev_patch[t]])))
+    assert np.array_equal(bits(O.pool_eval(X, n_pos, W, b, prior, 3)), bits(R.pool_eval(X, n_pos, W, b, prev_patch, prev_w, [1.0] * 3)))
