@@ -179,7 +179,7 @@ int build_plan(sc_handle* h, int W, int H, const sc_detect_params& prm, std::vec
     p.W = W; p.H = H;
     p.step = prm.step > 0 ? prm.step : (prm.base > 20 ? prm.base / 20 : 1);
     p.lay = sc_host::make_layout(W, H, 2 * p.step, p.step);
-    if (p.lay.frame4 > 0x7fffffffLL) return fail(h, SC_ERR_INVALID, "frame too large for 32-bit layout offsets");
+    if (p.lay.hp > 4096 || p.lay.frame4 * 16 > 0xffffffffLL) return fail(h, SC_ERR_INVALID, "frame too large for the scan layout (plane rows of at most 4096 pixels, 4 GiB per frame)");
     p.n_stages = h->n_stages; p.total_weak = h->total_weak;
     p.use_prefilter = prm.prefilter >= 0; p.skip_rule = prm.skip_rule != 0; p.force_all = prm.force_all_stages != 0;
     p.n_strips = (W + SC_STRIP - 1) / SC_STRIP;
@@ -204,10 +204,10 @@ int build_plan(sc_handle* h, int W, int H, const sc_detect_params& prm, std::vec
         s.block_base = blocks; s.word_base = words; s.row_base = rows;
         for (int ph = 0; ph < 2; ph++) {
             const int x0 = ph * p.step;
-            s.pf[ph][0] = (int)sc_layout_index(p.lay, x0, 0);
-            s.pf[ph][1] = (int)sc_layout_index(p.lay, x0 + l, 0);
-            s.pf[ph][2] = (int)sc_layout_index(p.lay, x0, l);
-            s.pf[ph][3] = (int)sc_layout_index(p.lay, x0 + l, l);
+            s.pf[ph][0] = (uint32_t)(16 * sc_layout_index(p.lay, x0, 0));
+            s.pf[ph][1] = (uint32_t)(16 * sc_layout_index(p.lay, x0 + l, 0));
+            s.pf[ph][2] = (uint32_t)(16 * sc_layout_index(p.lay, x0, l));
+            s.pf[ph][3] = (uint32_t)(16 * sc_layout_index(p.lay, x0 + l, l));
         }
         blocks += s.tiles_x * tiles_y; words += s.wpr * s.ny; rows += s.ny;
         windows += (long long)s.nx * s.ny;
@@ -294,6 +294,28 @@ int run_integral(sc_handle* h, const uint8_t* d_img, int n) {
 }
 
 // Launches the whole path for `g` frames already in d_img (device).  Detections are appended to det / det_count.
+// The scan kernels are instantiated per half-row distance of the layout (sc_plan.h): 256 .. 4096 float4.
+template <typename... A>
+void launch_stage0(int hp, int grid, size_t smem, cudaStream_t st, A... a) {
+    switch (hp) {
+        case 256: sck::k_scan_stage0<256><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
+        case 512: sck::k_scan_stage0<512><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
+        case 1024: sck::k_scan_stage0<1024><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
+        case 2048: sck::k_scan_stage0<2048><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
+        default: sck::k_scan_stage0<4096><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
+    }
+}
+template <typename... A>
+void launch_stage(int hp, int grid, size_t smem, cudaStream_t st, A... a) {
+    switch (hp) {
+        case 256: sck::k_scan_stage<256><<<grid, 128, smem, st>>>(a...); break;
+        case 512: sck::k_scan_stage<512><<<grid, 128, smem, st>>>(a...); break;
+        case 1024: sck::k_scan_stage<1024><<<grid, 128, smem, st>>>(a...); break;
+        case 2048: sck::k_scan_stage<2048><<<grid, 128, smem, st>>>(a...); break;
+        default: sck::k_scan_stage<4096><<<grid, 128, smem, st>>>(a...); break;
+    }
+}
+
 // Scan of `g` frames whose integrals start at frame slot `s0` of d_S.
 int run_group(sc_handle* h, int s0, int g, int frame0, sc_detection* d_det, uint32_t det_cap, uint32_t* d_det_count,
               unsigned long long* d_counters) {
@@ -316,8 +338,8 @@ int run_group(sc_handle* h, int s0, int g, int frame0, sc_detection* d_det, uint
             const int rows0 = g * p.rows_per_frame;
             {
                 KernelSpan ks(h, K_STAGE0);
-                sck::k_scan_stage0<<<g * p.blocks_per_frame, SC_TILE_THREADS, smem, st>>>(dp, S, geom, w, wb, multi, h->d_pass.as<uint32_t>(), rec,
-                                                                                             small + SM_REC, h->rec_cap, 0, start_odd);
+                launch_stage0(p.lay.hp, g * p.blocks_per_frame, smem, st, dp, S, geom, w, wb, multi, h->d_pass.as<uint32_t>(), rec, small + SM_REC,
+                              h->rec_cap, 0, start_odd);
             }
             if (p.skip_rule) {
                 KernelSpan ks(h, K_EVENTS);
@@ -327,8 +349,8 @@ int run_group(sc_handle* h, int s0, int g, int frame0, sc_detection* d_det, uint
             }
             {
                 KernelSpan ks(h, K_STAGE0);
-                sck::k_scan_stage0<<<g * p.blocks_per_frame, SC_TILE_THREADS, smem, st>>>(dp, S, geom, w, wb, multi, h->d_pass.as<uint32_t>(), rec,
-                                                                                             small + SM_REC, h->rec_cap, 1, start_odd);
+                launch_stage0(p.lay.hp, g * p.blocks_per_frame, smem, st, dp, S, geom, w, wb, multi, h->d_pass.as<uint32_t>(), rec, small + SM_REC,
+                              h->rec_cap, 1, start_odd);
             }
         }
         const int tail_grid = h->n_sms * 8;
@@ -338,8 +360,8 @@ int run_group(sc_handle* h, int s0, int g, int frame0, sc_detection* d_det, uint
             const uint32_t* in_cnt = first ? small + SM_REC : small + SM_STAGE0 + (s - 1);
             const size_t smem = (size_t)p.n_weak[s] * (SC_W_PITCH * 4 + 8);
             KernelSpan ks(h, K_STAGE);
-            sck::k_scan_stage<<<tail_grid, 128, smem, st>>>(dp, s, S, geom, w, wb, multi, rec, in_idx, in_cnt, h->d_idx[s & 1].as<uint32_t>(),
-                                                             small + SM_STAGE0 + s, h->rec_cap);
+            launch_stage(p.lay.hp, tail_grid, smem, st, dp, s, S, geom, w, wb, multi, rec, in_idx, in_cnt, h->d_idx[s & 1].as<uint32_t>(),
+                         small + SM_STAGE0 + s, h->rec_cap);
         }
         const int rows = g * p.rows_per_frame;
         { KernelSpan ks(h, K_REPLAY); sck::k_replay_rows<<<(rows + 127) / 128, 128, 0, st>>>(dp, g, multi, h->d_pass.as<uint32_t>(), h->d_visited.as<uint32_t>(), d_counters); }

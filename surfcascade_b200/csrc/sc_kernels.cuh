@@ -96,9 +96,9 @@ __global__ void __launch_bounds__(128) k_integral_walk(const uint8_t* __restrict
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     // this lane's integral column X = x + 1: in-plane column and the plane column residue are fixed
     const int X = x + 1, px = X / L.sx, rx = X - px * L.sx;
-    if (valid) { float4* o = Sf + (size_t)rx * 2 * L.hps4 + px; o[0] = zero; o[L.hps4] = zero; }   // row Y = 0
-    if (s == 0 && lane == 0)                                                                       // column X = 0
-        for (int Y = 0; Y <= H; Y++) { float4* o = Sf + sc_layout_index(L, 0, Y); o[0] = zero; o[L.hps4] = zero; }
+    if (valid) { float4* o = Sf + (size_t)rx * L.plane4 + px; o[0] = zero; o[L.hp] = zero; }      // row Y = 0
+    if (s == 0 && lane == 0)                                                                      // column X = 0
+        for (int Y = 0; Y <= H; Y++) { float4* o = Sf + sc_layout_index(L, 0, Y); o[0] = zero; o[L.hp] = zero; }
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const int4* cr = reinterpret_cast<const int4*>(carry + (((size_t)f * H) * n_strips + s) * 8);
     const size_t cr_step = (size_t)n_strips * 2;
@@ -130,9 +130,9 @@ __global__ void __launch_bounds__(128) k_integral_walk(const uint8_t* __restrict
         }
         if (++ry == L.sy) { ry = 0; py++; }
         if (valid) {
-            float4* o = Sf + (size_t)(ry * L.sx + rx) * 2 * L.hps4 + (size_t)py * L.ppitch + px;
+            float4* o = Sf + (size_t)(ry * L.sx + rx) * L.plane4 + (size_t)py * L.ppitch + px;
             o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            o[L.hps4] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            o[L.hp] = make_float4(acc[4], acc[5], acc[6], acc[7]);
         }
         prev = cur; cur = next; next = nn; c_lo = n_lo; c_hi = n_hi;
     }
@@ -145,7 +145,7 @@ __global__ void k_export_integral(const float4* __restrict__ S, const ScLayout L
         const int Y = i / (W + 1), X = i - Y * (W + 1);
         const float4* p = S + sc_layout_index(L, X, Y);
         out[2 * (size_t)i] = p[0];
-        out[2 * (size_t)i + 1] = p[L.hps4];
+        out[2 * (size_t)i + 1] = p[L.hp];
     }
 }
 
@@ -154,20 +154,16 @@ __global__ void k_export_integral(const float4* __restrict__ S, const ScLayout L
 // ---------------------------------------------------------------------------------------------------------
 struct Px { float v[8]; };
 
-// p + idx float4s in ONE instruction (IMAD.WIDE.U32); plain pointer arithmetic costs 4-5 here because the compiler
-// re-associates the 64-bit sum.  Layout offsets are non-negative 32-bit element counts.
-__device__ __forceinline__ const float4* at(const float4* p, int idx) {
-    unsigned long long r;
-    asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(r) : "r"((unsigned)idx), "l"(p));
-    return reinterpret_cast<const float4*>(r);
-}
-
-// lo4 / hi4 already point at the window origin's element of the two half-planes
-__device__ __forceinline__ Px load_px(const float4* __restrict__ lo4, const float4* __restrict__ hi4, int idx) {
-    const float4 lo = __ldg(at(lo4, idx)), hi = __ldg(at(hi4, idx));
-    Px p;
-    p.v[0] = lo.x; p.v[1] = lo.y; p.v[2] = lo.z; p.v[3] = lo.w; p.v[4] = hi.x; p.v[5] = hi.y; p.v[6] = hi.z; p.v[7] = hi.w;
-    return p;
+// Corner addressing.  ScGeom / pf offsets are BYTE offsets (uint32) from the window's low-half element, so one corner
+// costs one 64-bit add (IADD3 + IADD3.X); the high half sits HP float4s further (sc_plan.h) and, with HP a template
+// constant, rides in the load's immediate field.  HP == 0 selects the run-time distance `hp` (parity hooks).
+template <int HP>
+__device__ __forceinline__ Px load_px(const char* __restrict__ base, uint32_t off, int hp) {
+    const float4* p = reinterpret_cast<const float4*>(base + off);
+    const float4 lo = __ldg(p), hi = __ldg(p + (HP ? HP : hp));
+    Px r;
+    r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w; r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+    return r;
 }
 
 // (A + D) - (B + C), CalcFeature, DenseSURFFeatureExtractor.cpp:385-412
@@ -190,26 +186,25 @@ __device__ __forceinline__ float sumsq_hadd(const float* v) {
     return s;
 }
 
-// CalcFeature + Normalize for one projected patch; `org` = layout index of the window origin.
-__device__ __forceinline__ void descriptor(const float4* __restrict__ lo4_, const float4* __restrict__ hi4_, int org, const ScGeom& g, float* v) {
-    const float4* lo4 = at(lo4_, org);
-    const float4* hi4 = at(hi4_, org);
+// CalcFeature + Normalize for one projected patch; `base` = address of the window's low-half element.
+template <int HP>
+__device__ __forceinline__ void descriptor(const char* __restrict__ base, const ScGeom& g, int hp, float* v) {
     if (g.shape == 0) {
         // 3 x 3 corner lattice, cells row-major (GetRectsFromPatch :360-377)
-        Px a0 = load_px(lo4, hi4, g.c[0]), a1 = load_px(lo4, hi4, g.c[1]), a2 = load_px(lo4, hi4, g.c[2]);
-        const Px b0 = load_px(lo4, hi4, g.c[3]), b1 = load_px(lo4, hi4, g.c[4]), b2 = load_px(lo4, hi4, g.c[5]);
+        Px a0 = load_px<HP>(base, g.c[0], hp), a1 = load_px<HP>(base, g.c[1], hp), a2 = load_px<HP>(base, g.c[2], hp);
+        const Px b0 = load_px<HP>(base, g.c[3], hp), b1 = load_px<HP>(base, g.c[4], hp), b2 = load_px<HP>(base, g.c[5], hp);
         cell_sum(a0, a1, b0, b1, v);
         cell_sum(a1, a2, b1, b2, v + 8);
-        a0 = load_px(lo4, hi4, g.c[6]); a1 = load_px(lo4, hi4, g.c[7]); a2 = load_px(lo4, hi4, g.c[8]);
+        a0 = load_px<HP>(base, g.c[6], hp); a1 = load_px<HP>(base, g.c[7], hp); a2 = load_px<HP>(base, g.c[8], hp);
         cell_sum(b0, b1, a0, a1, v + 16);
         cell_sum(b1, b2, a1, a2, v + 24);
     } else {
         // 2 x 5 corner lattice: four cells chained along the long side (4x1 wide or 1x4 tall; B and C swap roles
         // between the two, and fl(B + C) == fl(C + B))
-        Px t0 = load_px(lo4, hi4, g.c[0]), u0 = load_px(lo4, hi4, g.c[5]);
+        Px t0 = load_px<HP>(base, g.c[0], hp), u0 = load_px<HP>(base, g.c[5], hp);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const Px t1 = load_px(lo4, hi4, g.c[k + 1]), u1 = load_px(lo4, hi4, g.c[k + 6]);
+            const Px t1 = load_px<HP>(base, g.c[k + 1], hp), u1 = load_px<HP>(base, g.c[k + 6], hp);
             cell_sum(t0, t1, u0, u1, v + 8 * k);
             t0 = t1; u0 = u1;
         }
@@ -240,25 +235,30 @@ __device__ __forceinline__ float weak_predict(const float* v, const float* __res
     return (float)(1.0 / (1.0 + exp(-z)));
 }
 
-// GentleAdaboost::Predict2 (GentleAdaboost.cpp:247-261) of one stage on one window.
-__device__ __forceinline__ float stage_score(const float4* __restrict__ lo4, const float4* __restrict__ hi4, int org,
-                                             const ScGeom* __restrict__ geom, const float* __restrict__ w, const double* __restrict__ wb,
-                                             int n_weak) {
+// GentleAdaboost::Predict2 (GentleAdaboost.cpp:247-261) of one stage on one window; geometry is read as three 16-byte
+// vectors per weak classifier (shared or global memory).
+template <int HP>
+__device__ __forceinline__ float stage_score(const char* __restrict__ base, const ScGeom* __restrict__ geom, const float* __restrict__ w,
+                                             const double* __restrict__ wb, int n_weak, int hp) {
     float acc = 0.f;
     for (int q = 0; q < n_weak; q++) {
+        ScGeom g;
+        const uint4* gs = reinterpret_cast<const uint4*>(geom + q);
+        const uint4 g0 = gs[0], g1 = gs[1], g2 = gs[2];
+        g.c[0] = g0.x; g.c[1] = g0.y; g.c[2] = g0.z; g.c[3] = g0.w; g.c[4] = g1.x; g.c[5] = g1.y; g.c[6] = g1.z; g.c[7] = g1.w;
+        g.c[8] = g2.x; g.c[9] = g2.y; g.shape = g2.z; g.pad = 0;
         float v[32];
-        descriptor(lo4, hi4, org, geom[q], v);
+        descriptor<HP>(base, g, hp, v);
         acc = __fadd_rn(acc, weak_predict(v, w + q * SC_W_PITCH, wb[q]));
     }
     return __fdiv_rn(acc, (float)n_weak);
 }
 
-// DenseSURFFeatureExtractor::sum (:351-358) and the compare at ObjDetector.cpp:188; pf = layout offsets of the corners
-// (0,0) (l,0) (0,l) (l,l)
-__device__ __forceinline__ float window_sum(const float4* __restrict__ lo4, int org, const int* pf) {
-    const float4* p = at(lo4, org);
-    const float4 a = __ldg(at(p, pf[0])), b = __ldg(at(p, pf[1]));
-    const float4 c = __ldg(at(p, pf[2])), d = __ldg(at(p, pf[3]));
+// DenseSURFFeatureExtractor::sum (:351-358) and the compare at ObjDetector.cpp:188; pf = byte offsets of the corners
+// (0,0) (l,0) (0,l) (l,l) from the window's low-half element
+__device__ __forceinline__ float window_sum(const char* __restrict__ base, const uint32_t* pf) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(base + pf[0])), b = __ldg(reinterpret_cast<const float4*>(base + pf[1]));
+    const float4 c = __ldg(reinterpret_cast<const float4*>(base + pf[2])), d = __ldg(reinterpret_cast<const float4*>(base + pf[3]));
     const float s0 = __fsub_rn(__fadd_rn(a.x, d.x), __fadd_rn(b.x, c.x));
     const float s1 = __fsub_rn(__fadd_rn(a.y, d.y), __fadd_rn(b.y, c.y));
     const float s2 = __fsub_rn(__fadd_rn(a.z, d.z), __fadd_rn(b.z, c.z));
@@ -284,6 +284,7 @@ __device__ __forceinline__ uint32_t spread16(uint32_t x) {  // bit i (i < 16) ->
 }
 
 // phase 0: lattice columns gx = 2j, every row.  phase 1: gx = 2j + 1, only gx >= start_odd[row].
+template <int HP>
 __global__ void __launch_bounds__(SC_TILE_THREADS, 3) k_scan_stage0(const ScPlan* __restrict__ plan, const float4* __restrict__ S,
                                                                   const ScGeom* __restrict__ geom_all, const float* __restrict__ w_all,
                                                                   const double* __restrict__ wb_all, uint32_t* __restrict__ multi_bits,
@@ -320,12 +321,11 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, 3) k_scan_stage0(const ScPlan
         if (!__syncthreads_or(need)) return;
     }
     const int n_weak = plan->n_weak[0], total_weak = plan->total_weak;
-    const int ppitch = plan->lay.ppitch;
+    constexpr int ppitch = 2 * HP;
     const float4* lo4 = S + (size_t)f * plan->lay.frame4;
-    const float4* hi4 = lo4 + plan->lay.hps4;
-    float* sw = reinterpret_cast<float*>(s_dyn);                                       // [n_weak][36]
-    double* swb = reinterpret_cast<double*>(s_dyn + (size_t)n_weak * SC_W_PITCH * 4);  // [n_weak]
-    ScGeom* sg = reinterpret_cast<ScGeom*>(swb + n_weak);                              // [n_weak]
+    ScGeom* sg = reinterpret_cast<ScGeom*>(s_dyn);                                                          // [n_weak] 48 B each
+    float* sw = reinterpret_cast<float*>(s_dyn + (size_t)n_weak * sizeof(ScGeom));                          // [n_weak][36]
+    double* swb = reinterpret_cast<double*>(s_dyn + (size_t)n_weak * (sizeof(ScGeom) + SC_W_PITCH * 4));    // [n_weak]
     for (int i = tid; i < n_weak * SC_W_PITCH; i += SC_TILE_THREADS) sw[i] = w_all[i];
     for (int i = tid; i < n_weak; i += SC_TILE_THREADS) {
         swb[i] = wb_all[i];
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, 3) k_scan_stage0(const ScPlan
             bool valid = gx < nx && gy < ny;
             if (phase) valid = valid && gx >= s_start[row];
             bool pass = false;
-            if (valid) pass = use_pf ? (window_sum(lo4, gy * ppitch + j, s_sc.pf[phase]) > thr) : true;
+            if (valid) pass = use_pf ? (window_sum(reinterpret_cast<const char*>(lo4 + (gy * ppitch + j)), s_sc.pf[phase]) > thr) : true;
             const uint32_t m = __ballot_sync(0xffffffffu, pass);
             const uint32_t fail = __ballot_sync(0xffffffffu, valid && !pass);
             uint32_t base = 0;
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, 3) k_scan_stage0(const ScPlan
             const int row = code >> 6, half = (code >> 5) & 1, ln = code & 31;
             const int j = tx * SC_TILE_X + half * 32 + ln;
             const int gx = 2 * j + phase, gy = ty * SC_TILE_Y + row;
-            const float score = stage_score(lo4, hi4, gy * ppitch + j, sg, sw, swb, n_weak);
+            const float score = stage_score<HP>(reinterpret_cast<const char*>(lo4 + (gy * ppitch + j)), sg, sw, swb, n_weak, HP);
             const bool rejected = score < theta0;
             if (rejected && rejected_skips(score, 0, n_stages)) atomicOr(&s_multi[row][2 * half + (ln >> 4)], 1u << (2 * (ln & 15) + phase));
             push = !rejected || force;
@@ -442,6 +442,7 @@ __global__ void __launch_bounds__(128) k_row_events(const ScPlan* __restrict__ p
 // ---------------------------------------------------------------------------------------------------------
 // Stages 1..N-1 on compacted index lists
 // ---------------------------------------------------------------------------------------------------------
+template <int HP>
 __global__ void __launch_bounds__(128) k_scan_stage(const ScPlan* __restrict__ plan, int stage, const float4* __restrict__ S,
                                                      const ScGeom* __restrict__ geom_all, const float* __restrict__ w_all,
                                                      const double* __restrict__ wb_all, uint32_t* __restrict__ multi_bits,
@@ -456,7 +457,8 @@ __global__ void __launch_bounds__(128) k_scan_stage(const ScPlan* __restrict__ p
     for (int i = threadIdx.x; i < n_weak; i += blockDim.x) swb[i] = wb_all[wbase + i];
     __syncthreads();
     const uint32_t count = min(*in_count, cap);
-    const int n_stages = plan->n_stages, ppitch = plan->lay.ppitch;
+    const int n_stages = plan->n_stages;
+    constexpr int ppitch = 2 * HP;
     const bool force = plan->force_all != 0, last = stage == n_stages - 1;
     const float theta = plan->theta[stage];
     const int lane = threadIdx.x & 31;
@@ -471,8 +473,8 @@ __global__ void __launch_bounds__(128) k_scan_stage(const ScPlan* __restrict__ p
             const int f = r.fs >> 8, si = r.fs & 0xff;
             const int gy = r.yx >> 16, gx = r.yx & 0xffff;
             const float4* lo4 = S + (size_t)f * plan->lay.frame4;
-            const float score = stage_score(lo4, lo4 + plan->lay.hps4, gy * ppitch + (gx >> 1),
-                                            geom_all + ((size_t)(gx & 1) * plan->n_scales + si) * total_weak + wbase, sw, swb, n_weak);
+            const float score = stage_score<HP>(reinterpret_cast<const char*>(lo4 + (gy * ppitch + (gx >> 1))),
+                                                geom_all + ((size_t)(gx & 1) * plan->n_scales + si) * total_weak + wbase, sw, swb, n_weak, HP);
             if (r.rej < 0) {
                 const bool rejected = score < theta;
                 if (rejected) {
@@ -614,28 +616,28 @@ __global__ void k_features(const float4* __restrict__ S, const ScLayout L, const
     if (i >= n) return;
     const int4 r = rects[i];  // x, y, w, h
     const int pitch = L.ppitch;
-    const int org = r.y * pitch + r.x;
-    const float4* hi4 = S + L.hps4;
+    const char* base = reinterpret_cast<const char*>(S + ((size_t)r.y * pitch + r.x));
     if (sums) {
-        const int pf[4] = {0, r.z, r.w * pitch, r.w * pitch + r.z};
-        sums[i] = window_sum(S, org, pf);
+        const uint32_t pf[4] = {0u, 16u * r.z, 16u * (uint32_t)(r.w * pitch), 16u * (uint32_t)(r.w * pitch + r.z)};
+        sums[i] = window_sum(base, pf);
     }
     if (out) {
         ScGeom g;
+        g.pad = 0;
         if (r.z == r.w) {
             const int ce = r.z / 2;
             g.shape = 0;
             for (int b = 0; b < 3; b++)
-                for (int a = 0; a < 3; a++) g.c[3 * b + a] = b * ce * pitch + a * ce;
+                for (int a = 0; a < 3; a++) g.c[3 * b + a] = 16u * (uint32_t)(b * ce * pitch + a * ce);
             g.c[9] = 0;
         } else {
             const int ce = min(r.z, r.w);
             const int along = r.z > r.w ? ce : ce * pitch, across = r.z > r.w ? ce * pitch : ce;
             g.shape = 1;
-            for (int k = 0; k < 5; k++) { g.c[k] = k * along; g.c[5 + k] = k * along + across; }
+            for (int k = 0; k < 5; k++) { g.c[k] = 16u * (uint32_t)(k * along); g.c[5 + k] = 16u * (uint32_t)(k * along + across); }
         }
         float v[32];
-        descriptor(S, hi4, org, g, v);
+        descriptor<0>(base, g, L.hp, v);
         for (int k = 0; k < 32; k++) out[(size_t)i * 32 + k] = v[k];
     }
 }
@@ -646,11 +648,11 @@ __global__ void k_stage_scores(const ScPlan* __restrict__ plan, const float4* __
     // geom_win: [n][total_weak] geometry projected for each explicit window's side (host-built, layout step 1)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int org = wins[3 * i + 1] * plan->lay.ppitch + wins[3 * i];
+    const char* base = reinterpret_cast<const char*>(S + ((size_t)wins[3 * i + 1] * plan->lay.ppitch + wins[3 * i]));
     for (int s = 0; s < plan->n_stages; s++) {
         const int wb = plan->weak_base[s];
-        out[(size_t)i * plan->n_stages + s] = stage_score(S, S + plan->lay.hps4, org, geom_win + (size_t)i * plan->total_weak + wb,
-                                                          w_all + (size_t)wb * SC_W_PITCH, wb_all + wb, plan->n_weak[s]);
+        out[(size_t)i * plan->n_stages + s] = stage_score<0>(base, geom_win + (size_t)i * plan->total_weak + wb, w_all + (size_t)wb * SC_W_PITCH,
+                                                             wb_all + wb, plan->n_weak[s], plan->lay.hp);
     }
 }
 

@@ -27,12 +27,17 @@
 //   fully coalesced 512-byte loads.  Detection plans deinterleave rows by sy = lattice step and columns by
 //   sx = 2 * step, because one launch of the scan walks lattice columns of a single parity (2j or 2j + 1, see
 //   SC_TILE_X): consecutive j are then consecutive float4s.  The explicit-rect hooks use sx = sy = 1.
+//   The two halves of a plane are interleaved row by row at a power-of-two distance hp: a plane row is
+//   [hp float4: channels 0-3][hp float4: channels 4-7], so the second 16-byte load of a corner is the first one's
+//   address plus a compile-time constant (the scan kernels are instantiated per hp) and costs no address arithmetic.
 struct ScLayout {
     int sx, sy;            // column / row deinterleave factors
-    int ppitch;            // float4 elements per plane row   = roundup(ceil((W+1)/sx), 8)
+    int hp;                // float4 elements per half-row: power of two >= ceil((W+1)/sx), one of 256..4096
+    int ppitch;            // float4 elements per plane row   = 2 * hp
     int prows;             // plane rows                      = ceil((H+1)/sy)
-    long long hps4;        // float4 elements per half-plane  = ppitch * prows
-    long long frame4;      // float4 elements per frame       = sx*sy*2*hps4 rounded up to 16
+    int pad;
+    long long plane4;      // float4 elements per plane       = prows * ppitch
+    long long frame4;      // float4 elements per frame       = sx * sy * plane4
 };
 
 struct ScScale {
@@ -44,8 +49,8 @@ struct ScScale {
     int block_base;   // first stage-0 CTA of this scale inside a frame
     int word_base;    // first bitmask word of this scale inside a frame
     int row_base;     // first lattice row of this scale inside a frame (replay threads)
-    int pf[2][4];     // per column parity: layout offsets of the prefilter corners (0,0) (l,0) (0,l) (l,l) relative to
-                      // the layout index gy * ppitch + (gx >> 1) of the window
+    uint32_t pf[2][4];  // per column parity: byte offsets of the prefilter corners (0,0) (l,0) (0,l) (l,l) relative to
+                        // the window's layout element gy * ppitch + (gx >> 1)
     int pad[3];
 };
 
@@ -73,8 +78,9 @@ struct ScPlan {
 // patch's corner lattice relative to the window's layout index gy * ppitch + (gx >> 1)  [hooks: y * ppitch + x].
 //   shape 0, square 2x2 cells: c[3*b + a], a, b in 0..2   (corner (ox + a*ce, oy + b*ce))
 //   shape 1, long 4x1 / 1x4  : c[k] first line, c[5 + k] second line, k in 0..4 along the cell chain
+// Offsets are BYTES (float4 index * 16), unsigned 32-bit: frames up to 4 GiB of integral image.
 struct ScGeom {
-    int c[10];
+    uint32_t c[10];
     int shape;
     int pad;
 };
@@ -99,7 +105,7 @@ enum { SC_CNT_VISITED = 0, SC_CNT_PREFILTER = 1, SC_CNT_RAW = 2, SC_CNT_EVALODD 
 // layout index (float4 units, low half) of integral pixel (X, Y)
 SC_HD long long sc_layout_index(const ScLayout& L, int X, int Y) {
     const int px = X / L.sx, rx = X - px * L.sx, py = Y / L.sy, ry = Y - py * L.sy;
-    return (long long)(ry * L.sx + rx) * 2 * L.hps4 + (long long)py * L.ppitch + px;
+    return (long long)(ry * L.sx + rx) * L.plane4 + (long long)py * L.ppitch + px;
 }
 
 #endif

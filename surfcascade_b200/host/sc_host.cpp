@@ -52,7 +52,7 @@ bool project_geom(int tmpl, int l, const sc_rect& patch, const ScLayout& L, int 
         if (ce < 1) return false;
         g->shape = 0;
         for (int b = 0; b < 3; b++)
-            for (int a = 0; a < 3; a++) g->c[3 * b + a] = (int)sc_layout_index(L, r.x + a * ce, r.y + b * ce);
+            for (int a = 0; a < 3; a++) g->c[3 * b + a] = (uint32_t)(16 * sc_layout_index(L, r.x + a * ce, r.y + b * ce));
     } else {
         const int ce = std::min(r.w, r.h);
         if (ce < 1 || std::max(r.w, r.h) != 4 * ce) return false;
@@ -61,8 +61,8 @@ bool project_geom(int tmpl, int l, const sc_rect& patch, const ScLayout& L, int 
         for (int k = 0; k < 5; k++) {
             // first line: the chain of corners along the long side; second line: one cell edge across
             const int x0 = r.x + (wide ? k * ce : 0), y0 = r.y + (wide ? 0 : k * ce);
-            g->c[k] = (int)sc_layout_index(L, x0, y0);
-            g->c[5 + k] = (int)sc_layout_index(L, x0 + (wide ? 0 : ce), y0 + (wide ? ce : 0));
+            g->c[k] = (uint32_t)(16 * sc_layout_index(L, x0, y0));
+            g->c[5 + k] = (uint32_t)(16 * sc_layout_index(L, x0 + (wide ? 0 : ce), y0 + (wide ? ce : 0)));
         }
     }
     return true;
@@ -73,10 +73,13 @@ ScLayout make_layout(int W, int H, int sx, int sy) {
     L.sx = sx < 1 ? 1 : sx;
     L.sy = sy < 1 ? 1 : sy;
     const int cols = (W + 1 + L.sx - 1) / L.sx;
-    L.ppitch = (cols + 7) / 8 * 8;
+    L.hp = 256;
+    while (L.hp < cols) L.hp *= 2;  // callers reject hp > 4096 (no kernel instantiation)
+    L.ppitch = 2 * L.hp;
     L.prows = (H + 1 + L.sy - 1) / L.sy;
-    L.hps4 = (long long)L.ppitch * L.prows;
-    L.frame4 = ((long long)L.sx * L.sy * 2 * L.hps4 + 15) / 16 * 16;
+    L.pad = 0;
+    L.plane4 = (long long)L.ppitch * L.prows;
+    L.frame4 = (long long)L.sx * L.sy * L.plane4;
     return L;
 }
 
