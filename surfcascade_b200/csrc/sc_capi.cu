@@ -83,7 +83,17 @@ struct sc_handle {
     int group_frames = 0;       // frames one scan group holds (records, bitmasks)
     int int_frames = 0;         // frames one integral super-group holds (images, carries, integral images)
     uint32_t rec_cap = 0;
-    DevBuf d_img, d_carry, d_S, d_multi, d_pass, d_visited, d_start, d_rec, d_idx[2], d_small, d_counters, d_det;
+    DevBuf d_img, d_carry, d_S, d_counters, d_det, d_detcount;
+    // Scan groups alternate between two lanes (stream + private bitmasks / records) so that one group's small tail
+    // kernels (later stages, replay, finalize) overlap the next group's stage 0.
+    struct Lane {
+        cudaStream_t st = nullptr;
+        cudaEvent_t done = nullptr;
+        DevBuf d_multi, d_pass, d_visited, d_start, d_rec, d_idx[2], d_small;
+    };
+    Lane lanes[2];
+    int n_lanes = 0;
+    cudaEvent_t ev_integral = nullptr;
     HostBuf h_stage;
     std::vector<sc_counters> last_counters;
     int last_nframes = 0;
@@ -139,14 +149,15 @@ struct KernelSpan {
     sc_handle* h;
     int kid;
     cudaEvent_t a = nullptr;
-    KernelSpan(sc_handle* h_, int kid_) : h(h_), kid(kid_) {
+    cudaStream_t st;
+    KernelSpan(sc_handle* h_, int kid_, cudaStream_t st_ = nullptr) : h(h_), kid(kid_), st(st_ ? st_ : h_->stream) {
         h->launches++;
-        if (h->profiling) { a = take_event(h); cudaEventRecord(a, h->stream); }
+        if (h->profiling) { a = take_event(h); cudaEventRecord(a, st); }
     }
     ~KernelSpan() {
         if (a) {
             cudaEvent_t b = take_event(h);
-            cudaEventRecord(b, h->stream);
+            cudaEventRecord(b, st);
             h->spans.push_back(sc_handle::Span{kid, a, b});
         }
     }
@@ -259,22 +270,31 @@ int ensure_group_buffers(sc_handle* h, int want_frames, bool own_images) {
     const size_t int_frame = (size_t)p.lay.frame4 * 16 + (size_t)p.H * p.n_strips * 32 + (size_t)p.W * p.H;
     int gi = (int)std::max<size_t>(1, std::min<size_t>(32, ((size_t)4 << 30) / std::max<size_t>(int_frame, 1)));
     gi = std::max(g, std::min(gi, std::max(want_frames, 1)));
-    if (g <= h->group_frames && gi <= h->int_frames) return SC_OK;
     g = std::max(g, h->group_frames);
     gi = std::max(gi, h->int_frames);
     const unsigned long long recs = (unsigned long long)p.windows_per_frame * g;
     if (recs > 0xfffffff0ull) return fail(h, SC_ERR_INVALID, "too many windows per group");
+    const int want_lanes = std::max(h->n_lanes, (want_frames > g && recs * per_rec < ((size_t)3 << 30)) ? 2 : 1);
+    if (g <= h->group_frames && gi <= h->int_frames && want_lanes <= h->n_lanes) return SC_OK;
     if (own_images) SC_CUDA(h, h->d_img.ensure(align256((size_t)gi * p.W * p.H)));
     SC_CUDA(h, h->d_carry.ensure(align256((size_t)gi * p.H * p.n_strips * 32)));
     SC_CUDA(h, h->d_S.ensure((size_t)gi * p.lay.frame4 * 16));
-    SC_CUDA(h, h->d_multi.ensure(align256((size_t)g * p.words_per_frame * 4 + 4)));
-    SC_CUDA(h, h->d_pass.ensure(align256((size_t)g * p.words_per_frame * 4 + 4)));
-    SC_CUDA(h, h->d_visited.ensure(align256((size_t)g * p.words_per_frame * 4 + 4)));
-    SC_CUDA(h, h->d_start.ensure(align256((size_t)g * p.rows_per_frame * 4 + 4)));
-    SC_CUDA(h, h->d_rec.ensure(align256(std::max<size_t>(recs, 1) * sizeof(ScRecord))));
-    SC_CUDA(h, h->d_idx[0].ensure(align256(std::max<size_t>(recs, 1) * 4)));
-    SC_CUDA(h, h->d_idx[1].ensure(align256(std::max<size_t>(recs, 1) * 4)));
-    SC_CUDA(h, h->d_small.ensure(SM_WORDS * 4));
+    // a second lane only when more than one scan group can be in flight and the worst-case record arrays stay modest
+    h->n_lanes = want_lanes;
+    for (int li = 0; li < h->n_lanes; li++) {
+        sc_handle::Lane& L = h->lanes[li];
+        if (!L.st) SC_CUDA(h, cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+        if (!L.done) SC_CUDA(h, cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+        SC_CUDA(h, L.d_multi.ensure(align256((size_t)g * p.words_per_frame * 4 + 4)));
+        SC_CUDA(h, L.d_pass.ensure(align256((size_t)g * p.words_per_frame * 4 + 4)));
+        SC_CUDA(h, L.d_visited.ensure(align256((size_t)g * p.words_per_frame * 4 + 4)));
+        SC_CUDA(h, L.d_start.ensure(align256((size_t)g * p.rows_per_frame * 4 + 4)));
+        SC_CUDA(h, L.d_rec.ensure(align256(std::max<size_t>(recs, 1) * sizeof(ScRecord))));
+        SC_CUDA(h, L.d_idx[0].ensure(align256(std::max<size_t>(recs, 1) * 4)));
+        SC_CUDA(h, L.d_idx[1].ensure(align256(std::max<size_t>(recs, 1) * 4)));
+        SC_CUDA(h, L.d_small.ensure(SM_WORDS * 4));
+    }
+    if (!h->ev_integral) SC_CUDA(h, cudaEventCreateWithFlags(&h->ev_integral, cudaEventDisableTiming));
     h->rec_cap = (uint32_t)recs;
     h->group_frames = g;
     h->int_frames = gi;
@@ -317,59 +337,78 @@ void launch_stage(int hp, int grid, size_t smem, cudaStream_t st, A... a) {
 }
 
 // Scan of `g` frames whose integrals start at frame slot `s0` of d_S.
-int run_group(sc_handle* h, int s0, int g, int frame0, sc_detection* d_det, uint32_t det_cap, uint32_t* d_det_count,
+int run_group(sc_handle* h, sc_handle::Lane& L, int s0, int g, int frame0, sc_detection* d_det, uint32_t det_cap, uint32_t* d_det_count,
               unsigned long long* d_counters) {
     const ScPlan& p = h->plan;
     const ScPlan* dp = h->d_plan.as<ScPlan>();
-    cudaStream_t st = h->stream;
-    uint32_t* small = h->d_small.as<uint32_t>();
+    cudaStream_t st = L.st;
+    uint32_t* small = L.d_small.as<uint32_t>();
     SC_CUDA(h, cudaMemsetAsync(small, 0, (SM_DET) * 4, st));  // rec + stage counts; det count is the caller's
     float4* S = h->d_S.as<float4>() + (size_t)s0 * p.lay.frame4;
     if (p.n_scales > 0 && p.n_stages > 0) {
         const ScGeom* geom = h->d_geom.as<ScGeom>();
         const float* w = h->d_w.as<float>();
         const double* wb = h->d_wb.as<double>();
-        uint32_t* multi = h->d_multi.as<uint32_t>();
-        ScRecord* rec = h->d_rec.as<ScRecord>();
+        uint32_t* multi = L.d_multi.as<uint32_t>();
+        uint32_t* pass = L.d_pass.as<uint32_t>();
+        uint32_t* visited = L.d_visited.as<uint32_t>();
+        ScRecord* rec = L.d_rec.as<ScRecord>();
         {
             // even lattice columns everywhere, then the odd columns the reference's stride can reach
             const size_t smem = (size_t)p.n_weak[0] * (SC_W_PITCH * 4 + 8 + sizeof(ScGeom));
-            int* start_odd = h->d_start.as<int>();
+            int* start_odd = L.d_start.as<int>();
             const int rows0 = g * p.rows_per_frame;
             {
-                KernelSpan ks(h, K_STAGE0);
-                launch_stage0(p.lay.hp, g * p.blocks_per_frame, smem, st, dp, S, geom, w, wb, multi, h->d_pass.as<uint32_t>(), rec, small + SM_REC,
-                              h->rec_cap, 0, start_odd);
+                KernelSpan ks(h, K_STAGE0, st);
+                launch_stage0(p.lay.hp, g * p.blocks_per_frame, smem, st, dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, 0, start_odd);
             }
             if (p.skip_rule) {
-                KernelSpan ks(h, K_EVENTS);
+                KernelSpan ks(h, K_EVENTS, st);
                 sck::k_row_events<<<(rows0 + 127) / 128, 128, 0, st>>>(dp, g, multi, start_odd, d_counters);
             } else {
                 SC_CUDA(h, cudaMemsetAsync(start_odd, 0, (size_t)rows0 * 4, st));  // every odd column is visited
             }
             {
-                KernelSpan ks(h, K_STAGE0);
-                launch_stage0(p.lay.hp, g * p.blocks_per_frame, smem, st, dp, S, geom, w, wb, multi, h->d_pass.as<uint32_t>(), rec, small + SM_REC,
-                              h->rec_cap, 1, start_odd);
+                KernelSpan ks(h, K_STAGE0, st);
+                launch_stage0(p.lay.hp, g * p.blocks_per_frame, smem, st, dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, 1, start_odd);
             }
         }
         const int tail_grid = h->n_sms * 8;
         for (int s = 1; s < p.n_stages; s++) {
             const bool first = s == 1 || p.force_all;
-            const uint32_t* in_idx = first ? nullptr : h->d_idx[(s - 1) & 1].as<uint32_t>();
+            const uint32_t* in_idx = first ? nullptr : L.d_idx[(s - 1) & 1].as<uint32_t>();
             const uint32_t* in_cnt = first ? small + SM_REC : small + SM_STAGE0 + (s - 1);
             const size_t smem = (size_t)p.n_weak[s] * (SC_W_PITCH * 4 + 8);
-            KernelSpan ks(h, K_STAGE);
-            launch_stage(p.lay.hp, tail_grid, smem, st, dp, s, S, geom, w, wb, multi, rec, in_idx, in_cnt, h->d_idx[s & 1].as<uint32_t>(),
+            KernelSpan ks(h, K_STAGE, st);
+            launch_stage(p.lay.hp, tail_grid, smem, st, dp, s, S, geom, w, wb, multi, rec, in_idx, in_cnt, L.d_idx[s & 1].as<uint32_t>(),
                          small + SM_STAGE0 + s, h->rec_cap);
         }
         const int rows = g * p.rows_per_frame;
-        { KernelSpan ks(h, K_REPLAY); sck::k_replay_rows<<<(rows + 127) / 128, 128, 0, st>>>(dp, g, multi, h->d_pass.as<uint32_t>(), h->d_visited.as<uint32_t>(), d_counters); }
-        { KernelSpan ks(h, K_FINALIZE);
-          sck::k_finalize<<<h->n_sms * 4, 128, 0, st>>>(dp, rec, small + SM_REC, h->rec_cap, h->d_visited.as<uint32_t>(), d_counters,
+        { KernelSpan ks(h, K_REPLAY, st); sck::k_replay_rows<<<(rows + 127) / 128, 128, 0, st>>>(dp, g, multi, pass, visited, d_counters); }
+        { KernelSpan ks(h, K_FINALIZE, st);
+          sck::k_finalize<<<h->n_sms * 4, 128, 0, st>>>(dp, rec, small + SM_REC, h->rec_cap, visited, d_counters,
                                                          reinterpret_cast<sck::ScDetOut*>(d_det), d_det_count, det_cap, frame0); }
     }
     SC_CUDA(h, cudaGetLastError());
+    return SC_OK;
+}
+
+// All scan groups of one integral super-group (ni frames at slots 0..ni-1 of d_S), alternating over the lanes.  The
+// integral was enqueued on the main stream; the lanes wait for it and the main stream waits for the lanes.
+int run_scan_groups(sc_handle* h, int ni, int frame0, sc_detection* d_det, uint32_t det_cap, uint32_t* d_det_count, unsigned long long* d_counters) {
+    const int lanes = h->profiling ? 1 : h->n_lanes;  // per-kernel event timing wants the kernels back to back
+    SC_CUDA(h, cudaEventRecord(h->ev_integral, h->stream));
+    for (int li = 0; li < lanes; li++) SC_CUDA(h, cudaStreamWaitEvent(h->lanes[li].st, h->ev_integral, 0));
+    int k = 0;
+    for (int f0 = 0; f0 < ni; f0 += h->group_frames, k++) {
+        const int g = std::min(h->group_frames, ni - f0);
+        int rc = run_group(h, h->lanes[k % lanes], f0, g, frame0 + f0, d_det, det_cap, d_det_count, d_counters + (size_t)f0 * SC_CNT_STRIDE);
+        if (rc != SC_OK) return rc;
+    }
+    for (int li = 0; li < lanes; li++) {
+        SC_CUDA(h, cudaEventRecord(h->lanes[li].done, h->lanes[li].st));
+        SC_CUDA(h, cudaStreamWaitEvent(h->stream, h->lanes[li].done, 0));
+    }
     return SC_OK;
 }
 
@@ -427,8 +466,14 @@ void sc_destroy(sc_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
-    DevBuf* bufs[] = {&h->d_w, &h->d_wb, &h->d_plan, &h->d_geom, &h->d_img, &h->d_carry, &h->d_S, &h->d_multi, &h->d_pass, &h->d_visited,
-                      &h->d_rec, &h->d_idx[0], &h->d_idx[1], &h->d_small, &h->d_counters, &h->d_det, &h->d_start, &h->d_pool_w, &h->d_pool_wb, &h->d_pool_auc, &h->d_pool_x, &h->d_pool_aux, &h->d_hook_img, &h->d_hook_carry, &h->d_hook_S};
+    for (auto& L : h->lanes) {
+        if (L.st) { cudaStreamSynchronize(L.st); cudaStreamDestroy(L.st); }
+        if (L.done) cudaEventDestroy(L.done);
+        DevBuf* lb[] = {&L.d_multi, &L.d_pass, &L.d_visited, &L.d_start, &L.d_rec, &L.d_idx[0], &L.d_idx[1], &L.d_small};
+        for (DevBuf* b : lb) b->release();
+    }
+    if (h->ev_integral) cudaEventDestroy(h->ev_integral);
+    DevBuf* bufs[] = {&h->d_w, &h->d_wb, &h->d_plan, &h->d_geom, &h->d_img, &h->d_carry, &h->d_S, &h->d_counters, &h->d_det, &h->d_detcount, &h->d_pool_w, &h->d_pool_wb, &h->d_pool_auc, &h->d_pool_x, &h->d_pool_aux, &h->d_hook_img, &h->d_hook_carry, &h->d_hook_S};
     for (DevBuf* b : bufs) b->release();
     h->h_stage.release();
     for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -771,11 +816,8 @@ int sc_detect_device(sc_handle* h, const uint8_t* d_frames, int nframes, int W, 
         const int ni = std::min(h->int_frames, nframes - i0);
         rc = run_integral(h, d_frames + (size_t)i0 * W * H, ni);
         if (rc != SC_OK) return rc;
-        for (int f0 = 0; f0 < ni; f0 += h->group_frames) {
-            const int g = std::min(h->group_frames, ni - f0);
-            rc = run_group(h, f0, g, i0 + f0, d_out, det_cap, d_n, h->d_counters.as<unsigned long long>() + (size_t)(i0 + f0) * SC_CNT_STRIDE);
-            if (rc != SC_OK) return rc;
-        }
+        rc = run_scan_groups(h, ni, i0, d_out, det_cap, d_n, h->d_counters.as<unsigned long long>() + (size_t)i0 * SC_CNT_STRIDE);
+        if (rc != SC_OK) return rc;
     }
     SC_CUDA(h, h->h_stage.ensure((size_t)nframes * SC_CNT_STRIDE * 8));
     SC_CUDA(h, cudaMemcpyAsync(h->h_stage.p, h->d_counters.p, (size_t)nframes * SC_CNT_STRIDE * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -827,7 +869,8 @@ int sc_detect(sc_handle* h, const uint8_t* const* frames, int nframes, int W, in
     SC_CUDA(h, h->d_det.ensure((size_t)det_cap * sizeof(sc_detection)));
     SC_CUDA(h, h->d_counters.ensure((size_t)nframes * SC_CNT_STRIDE * 8));
     SC_CUDA(h, cudaMemsetAsync(h->d_counters.p, 0, (size_t)nframes * SC_CNT_STRIDE * 8, h->stream));
-    uint32_t* d_cnt = h->d_small.as<uint32_t>() + SM_DET;
+    SC_CUDA(h, h->d_detcount.ensure(256));
+    uint32_t* d_cnt = h->d_detcount.as<uint32_t>();
     SC_CUDA(h, cudaMemsetAsync(d_cnt, 0, 4, h->stream));
     for (int i0 = 0; i0 < nframes; i0 += h->int_frames) {
         const int ni = std::min(h->int_frames, nframes - i0);
@@ -835,11 +878,8 @@ int sc_detect(sc_handle* h, const uint8_t* const* frames, int nframes, int W, in
             SC_CUDA(h, cudaMemcpy2DAsync(h->d_img.as<uint8_t>() + (size_t)k * W * H, W, frames[i0 + k], stride, W, H, cudaMemcpyHostToDevice, h->stream));
         rc = run_integral(h, h->d_img.as<uint8_t>(), ni);
         if (rc != SC_OK) return rc;
-        for (int f0 = 0; f0 < ni; f0 += h->group_frames) {
-            const int g = std::min(h->group_frames, ni - f0);
-            rc = run_group(h, f0, g, i0 + f0, h->d_det.as<sc_detection>(), det_cap, d_cnt, h->d_counters.as<unsigned long long>() + (size_t)(i0 + f0) * SC_CNT_STRIDE);
-            if (rc != SC_OK) return rc;
-        }
+        rc = run_scan_groups(h, ni, i0, h->d_det.as<sc_detection>(), det_cap, d_cnt, h->d_counters.as<unsigned long long>() + (size_t)i0 * SC_CNT_STRIDE);
+        if (rc != SC_OK) return rc;
     }
     const size_t cbytes = (size_t)nframes * SC_CNT_STRIDE * 8;
     SC_CUDA(h, h->h_stage.ensure(cbytes + 16));
