@@ -34,7 +34,8 @@ def stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB] + [os.path.join(HERE, f) for f in CU + CPP]
+    extra = os.environ.get("SC_EXTRA_NVCC", "").split()  # tuning experiments, e.g. -DSC_STAGE0_MIN_CTAS=4
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", LIB] + [os.path.join(HERE, f) for f in CU + CPP]
     subprocess.check_call(cmd)
     if os.path.exists(os.path.join(HERE, "host", "ObjDetector.cpp")):
         subprocess.check_call([_nvcc()] + NVCC_FLAGS + ["-o", CLI, os.path.join(HERE, "host", "ObjDetector.cpp"), "-L", HERE, "-lsurfcascade_b200",

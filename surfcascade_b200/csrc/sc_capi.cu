@@ -94,6 +94,8 @@ struct sc_handle {
     Lane lanes[2];
     int n_lanes = 0;
     cudaEvent_t ev_integral = nullptr;
+    std::vector<cudaEvent_t> ev_chunk;   // per pipeline chunk: [2c] upload done, [2c+1] integral done
+    cudaStream_t copy_st = nullptr;      // host-frame uploads (sc_detect)
     HostBuf h_stage;
     std::vector<sc_counters> last_counters;
     int last_nframes = 0;
@@ -301,14 +303,16 @@ int ensure_group_buffers(sc_handle* h, int want_frames, bool own_images) {
     return SC_OK;
 }
 
-// Channels + integral images of `n` frames (device images) into d_S
-int run_integral(sc_handle* h, const uint8_t* d_img, int n) {
+// Channels + integral images of `n` frames (device images) into frame slots slot0.. of d_S, on the main stream
+int run_integral(sc_handle* h, const uint8_t* d_img, int n, int slot0) {
     const ScPlan& p = h->plan;
     cudaStream_t st = h->stream;
     const int rows = n * p.H;
-    { KernelSpan ks(h, K_CARRY); sck::k_strip_carry<<<(rows + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, n, h->d_carry.as<int>()); }
+    int* carry = h->d_carry.as<int>() + (size_t)slot0 * p.H * p.n_strips * 8;
+    float4* S = h->d_S.as<float4>() + (size_t)slot0 * p.lay.frame4;
+    { KernelSpan ks(h, K_CARRY); sck::k_strip_carry<<<(rows + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, n, carry); }
     const int warps = n * p.n_strips;
-    { KernelSpan ks(h, K_WALK); sck::k_integral_walk<<<(warps + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, n, h->d_carry.as<int>(), h->d_S.as<float4>(), p.lay); }
+    { KernelSpan ks(h, K_WALK); sck::k_integral_walk<<<(warps + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, n, carry, S, p.lay); }
     SC_CUDA(h, cudaGetLastError());
     return SC_OK;
 }
@@ -395,15 +399,55 @@ int run_group(sc_handle* h, sc_handle::Lane& L, int s0, int g, int frame0, sc_de
 
 // All scan groups of one integral super-group (ni frames at slots 0..ni-1 of d_S), alternating over the lanes.  The
 // integral was enqueued on the main stream; the lanes wait for it and the main stream waits for the lanes.
-int run_scan_groups(sc_handle* h, int ni, int frame0, sc_detection* d_det, uint32_t det_cap, uint32_t* d_det_count, unsigned long long* d_counters) {
+//
+// One super-group of ni frames as a three-deep pipeline over chunks of SC_ICHUNK frames:
+//   copy stream : host frames -> d_img            (host path only; `frames` non-null)
+//   main stream : channels + integral of chunk c   (waits for its copy)
+//   lanes       : scan groups of chunk c           (wait for its integral)
+// so the upload and the integral of chunk c+1 run under the scan of chunk c.
+#define SC_ICHUNK 16   // measured: 8-frame chunks lose more in the integral kernel than the upload overlap gains
+int run_supergroup(sc_handle* h, const uint8_t* const* frames, int stride, const uint8_t* d_frames, int ni, int frame0, sc_detection* d_det,
+                   uint32_t det_cap, uint32_t* d_det_count, unsigned long long* d_counters) {
+    const ScPlan& p = h->plan;
     const int lanes = h->profiling ? 1 : h->n_lanes;  // per-kernel event timing wants the kernels back to back
-    SC_CUDA(h, cudaEventRecord(h->ev_integral, h->stream));
-    for (int li = 0; li < lanes; li++) SC_CUDA(h, cudaStreamWaitEvent(h->lanes[li].st, h->ev_integral, 0));
-    int k = 0;
-    for (int f0 = 0; f0 < ni; f0 += h->group_frames, k++) {
-        const int g = std::min(h->group_frames, ni - f0);
-        int rc = run_group(h, h->lanes[k % lanes], f0, g, frame0 + f0, d_det, det_cap, d_det_count, d_counters + (size_t)f0 * SC_CNT_STRIDE);
+    // device-resident frames: one integral launch over the whole super-group is fastest (nothing to overlap it with
+    // but the scan, which it only slows down); host frames: chunks, so that uploads hide under the scan
+    const int ich = (h->profiling || !frames) ? ni : SC_ICHUNK;
+    const int nch = (ni + ich - 1) / ich;
+    while ((int)h->ev_chunk.size() < 2 * nch) {
+        cudaEvent_t e = nullptr;
+        SC_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->ev_chunk.push_back(e);
+    }
+    if (frames && !h->copy_st) SC_CUDA(h, cudaStreamCreateWithFlags(&h->copy_st, cudaStreamNonBlocking));
+    if (frames) {
+        // the image buffer may still be read by the previous super-group's integral: order the copies after it
+        SC_CUDA(h, cudaEventRecord(h->ev_integral, h->stream));
+        SC_CUDA(h, cudaStreamWaitEvent(h->copy_st, h->ev_integral, 0));
+    }
+    for (int c = 0; c < nch; c++) {
+        const int c0 = c * ich, n = std::min(ich, ni - c0);
+        const uint8_t* img = d_frames ? d_frames + (size_t)c0 * p.W * p.H : h->d_img.as<uint8_t>() + (size_t)c0 * p.W * p.H;
+        if (frames) {
+            for (int k = 0; k < n; k++)
+                SC_CUDA(h, cudaMemcpy2DAsync(h->d_img.as<uint8_t>() + (size_t)(c0 + k) * p.W * p.H, p.W, frames[c0 + k], stride, p.W, p.H,
+                                             cudaMemcpyHostToDevice, h->copy_st));
+            SC_CUDA(h, cudaEventRecord(h->ev_chunk[2 * c], h->copy_st));
+            SC_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[2 * c], 0));
+        }
+        int rc = run_integral(h, img, n, c0);
         if (rc != SC_OK) return rc;
+        SC_CUDA(h, cudaEventRecord(h->ev_chunk[2 * c + 1], h->stream));
+    }
+    int k = 0;
+    for (int c = 0; c < nch; c++) {
+        const int c0 = c * ich, n = std::min(ich, ni - c0);
+        for (int li = 0; li < lanes; li++) SC_CUDA(h, cudaStreamWaitEvent(h->lanes[li].st, h->ev_chunk[2 * c + 1], 0));
+        for (int f0 = c0; f0 < c0 + n; f0 += h->group_frames, k++) {
+            const int g = std::min(h->group_frames, c0 + n - f0);
+            int rc = run_group(h, h->lanes[k % lanes], f0, g, frame0 + f0, d_det, det_cap, d_det_count, d_counters + (size_t)f0 * SC_CNT_STRIDE);
+            if (rc != SC_OK) return rc;
+        }
     }
     for (int li = 0; li < lanes; li++) {
         SC_CUDA(h, cudaEventRecord(h->lanes[li].done, h->lanes[li].st));
@@ -441,6 +485,29 @@ bool det_less(const sc_detection& a, const sc_detection& b) {
     return a.x < b.x;
 }
 
+// Order detections by (frame, l, y, x): LSD radix sort on a packed 64-bit key (16 bits per field; frame is taken
+// modulo 65536 per pass, larger batches fall back to a comparison sort).
+void sort_detections(sc_detection* d, size_t n) {
+    if (n < 2) return;
+    bool packable = true;
+    for (size_t i = 0; i < n && packable; i++)
+        packable = (uint32_t)d[i].frame < 65536u && (uint32_t)d[i].l < 65536u && (uint32_t)d[i].y < 65536u && (uint32_t)d[i].x < 65536u;
+    if (!packable || n < 64) { std::sort(d, d + n, det_less); return; }
+    std::vector<sc_detection> tmp(n);
+    std::vector<uint32_t> count(65536);
+    sc_detection *src = d, *dst = tmp.data();
+    for (int pass = 0; pass < 4; pass++) {  // x, y, l, frame
+        std::fill(count.begin(), count.end(), 0u);
+        auto digit = [pass](const sc_detection& e) -> uint32_t { return (uint32_t)(pass == 0 ? e.x : pass == 1 ? e.y : pass == 2 ? e.l : e.frame); };
+        for (size_t i = 0; i < n; i++) count[digit(src[i])]++;
+        uint32_t run = 0;
+        for (uint32_t& c : count) { const uint32_t k = c; c = run; run += k; }
+        for (size_t i = 0; i < n; i++) dst[count[digit(src[i])]++] = src[i];
+        std::swap(src, dst);
+    }
+    // four passes: the result is back in d
+}
+
 }  // namespace
 
 extern "C" {
@@ -473,6 +540,8 @@ void sc_destroy(sc_handle* h) {
         for (DevBuf* b : lb) b->release();
     }
     if (h->ev_integral) cudaEventDestroy(h->ev_integral);
+    for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
+    if (h->copy_st) { cudaStreamSynchronize(h->copy_st); cudaStreamDestroy(h->copy_st); }
     DevBuf* bufs[] = {&h->d_w, &h->d_wb, &h->d_plan, &h->d_geom, &h->d_img, &h->d_carry, &h->d_S, &h->d_counters, &h->d_det, &h->d_detcount, &h->d_pool_w, &h->d_pool_wb, &h->d_pool_auc, &h->d_pool_x, &h->d_pool_aux, &h->d_hook_img, &h->d_hook_carry, &h->d_hook_S};
     for (DevBuf* b : bufs) b->release();
     h->h_stage.release();
@@ -814,9 +883,8 @@ int sc_detect_device(sc_handle* h, const uint8_t* d_frames, int nframes, int W, 
     const uint32_t det_cap = (uint32_t)std::min<size_t>(cap, 0xffffffffu);
     for (int i0 = 0; i0 < nframes; i0 += h->int_frames) {
         const int ni = std::min(h->int_frames, nframes - i0);
-        rc = run_integral(h, d_frames + (size_t)i0 * W * H, ni);
-        if (rc != SC_OK) return rc;
-        rc = run_scan_groups(h, ni, i0, d_out, det_cap, d_n, h->d_counters.as<unsigned long long>() + (size_t)i0 * SC_CNT_STRIDE);
+        rc = run_supergroup(h, nullptr, 0, d_frames + (size_t)i0 * W * H, ni, i0, d_out, det_cap, d_n,
+                            h->d_counters.as<unsigned long long>() + (size_t)i0 * SC_CNT_STRIDE);
         if (rc != SC_OK) return rc;
     }
     SC_CUDA(h, h->h_stage.ensure((size_t)nframes * SC_CNT_STRIDE * 8));
@@ -874,11 +942,8 @@ int sc_detect(sc_handle* h, const uint8_t* const* frames, int nframes, int W, in
     SC_CUDA(h, cudaMemsetAsync(d_cnt, 0, 4, h->stream));
     for (int i0 = 0; i0 < nframes; i0 += h->int_frames) {
         const int ni = std::min(h->int_frames, nframes - i0);
-        for (int k = 0; k < ni; k++)
-            SC_CUDA(h, cudaMemcpy2DAsync(h->d_img.as<uint8_t>() + (size_t)k * W * H, W, frames[i0 + k], stride, W, H, cudaMemcpyHostToDevice, h->stream));
-        rc = run_integral(h, h->d_img.as<uint8_t>(), ni);
-        if (rc != SC_OK) return rc;
-        rc = run_scan_groups(h, ni, i0, h->d_det.as<sc_detection>(), det_cap, d_cnt, h->d_counters.as<unsigned long long>() + (size_t)i0 * SC_CNT_STRIDE);
+        rc = run_supergroup(h, frames + i0, stride, nullptr, ni, i0, h->d_det.as<sc_detection>(), det_cap, d_cnt,
+                            h->d_counters.as<unsigned long long>() + (size_t)i0 * SC_CNT_STRIDE);
         if (rc != SC_OK) return rc;
     }
     const size_t cbytes = (size_t)nframes * SC_CNT_STRIDE * 8;
@@ -895,7 +960,7 @@ int sc_detect(sc_handle* h, const uint8_t* const* frames, int nframes, int W, in
     if (found > cap) return fail(h, SC_ERR_CAPACITY, "detection buffer too small");
     if (found) {
         SC_CUDA(h, cudaMemcpy(out, h->d_det.p, (size_t)found * sizeof(sc_detection), cudaMemcpyDeviceToHost));
-        std::sort(out, out + found, det_less);
+        sort_detections(out, found);
     }
     return SC_OK;
 }

@@ -102,39 +102,59 @@ __global__ void __launch_bounds__(128) k_integral_walk(const uint8_t* __restrict
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const int4* cr = reinterpret_cast<const int4*>(carry + (((size_t)f * H) * n_strips + s) * 8);
     const size_t cr_step = (size_t)n_strips * 2;
+    // Rows are processed in blocks of RB with the next block's inputs (pixel rows and strip carries) loaded a whole
+    // block ahead: the walk is one dependent chain per warp, and with one row of lookahead every row waited on L2.
+    constexpr int RB = SC_WALK_RB;
     Row3 prev = load_row3(base, xp, xc, xn), cur = prev;
-    Row3 next = load_row3(base + (size_t)min(1, H - 1) * W, xp, xc, xn);
-    int4 c_lo = __ldg(cr), c_hi = __ldg(cr + 1);
+    Row3 nx[RB];
+    int4 clo[RB], chi[RB];
+#pragma unroll
+    for (int i = 0; i < RB; i++) {
+        nx[i] = load_row3(base + (size_t)min(1 + i, H - 1) * W, xp, xc, xn);
+        const int yq = min(i, H - 1);
+        clo[i] = __ldg(cr + (size_t)yq * cr_step); chi[i] = __ldg(cr + (size_t)yq * cr_step + 1);
+    }
     int py = 0, ry = 0;  // plane row / residue of Y = y + 1, advanced incrementally
-    for (int y = 0; y < H; y++) {
-        // prefetch the next iteration's inputs before the dependent shuffle chain
-        const Row3 nn = load_row3(base + (size_t)min(y + 2, H - 1) * W, xp, xc, xn);
-        const int yq = min(y + 1, H - 1);
-        const int4 n_lo = __ldg(cr + (size_t)yq * cr_step), n_hi = __ldg(cr + (size_t)yq * cr_step + 1);
-        uint32_t p[4];
-        channel_pairs(prev, cur, next, p);
-        if (!valid) { p[0] = p[1] = p[2] = p[3] = 0; }
+    for (int y0 = 0; y0 < H; y0 += RB) {
+        Row3 pn[RB];
+        int4 plo[RB], phi[RB];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
+        for (int i = 0; i < RB; i++) {
+            pn[i] = load_row3(base + (size_t)min(y0 + RB + 1 + i, H - 1) * W, xp, xc, xn);
+            const int yq = min(y0 + RB + i, H - 1);
+            plo[i] = __ldg(cr + (size_t)yq * cr_step); phi[i] = __ldg(cr + (size_t)yq * cr_step + 1);
+        }
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, p[k], d);
-                if (lane >= d) p[k] += t;
+        for (int i = 0; i < RB; i++) {
+            if (y0 + i < H) {
+                uint32_t p[4];
+                channel_pairs(prev, cur, nx[i], p);
+                if (!valid) { p[0] = p[1] = p[2] = p[3] = 0; }
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t t = __shfl_up_sync(0xffffffffu, p[k], d);
+                        if (lane >= d) p[k] += t;
+                    }
+                }
+                const int cy[8] = {clo[i].x, clo[i].y, clo[i].z, clo[i].w, chi[i].x, chi[i].y, chi[i].z, chi[i].w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    acc[2 * k] = __fadd_rn(acc[2 * k], (float)(cy[2 * k] + (int)(p[k] & 0xffffu)));
+                    acc[2 * k + 1] = __fadd_rn(acc[2 * k + 1], (float)(cy[2 * k + 1] + (int)(p[k] >> 16)));
+                }
+                if (++ry == L.sy) { ry = 0; py++; }
+                if (valid) {
+                    float4* o = Sf + (size_t)(ry * L.sx + rx) * L.plane4 + (size_t)py * L.ppitch + px;
+                    o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                    o[L.hp] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                }
+                prev = cur; cur = nx[i];
             }
         }
-        const int cy[8] = {c_lo.x, c_lo.y, c_lo.z, c_lo.w, c_hi.x, c_hi.y, c_hi.z, c_hi.w};
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            acc[2 * k] = __fadd_rn(acc[2 * k], (float)(cy[2 * k] + (int)(p[k] & 0xffffu)));
-            acc[2 * k + 1] = __fadd_rn(acc[2 * k + 1], (float)(cy[2 * k + 1] + (int)(p[k] >> 16)));
-        }
-        if (++ry == L.sy) { ry = 0; py++; }
-        if (valid) {
-            float4* o = Sf + (size_t)(ry * L.sx + rx) * L.plane4 + (size_t)py * L.ppitch + px;
-            o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            o[L.hp] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-        }
-        prev = cur; cur = next; next = nn; c_lo = n_lo; c_hi = n_hi;
+        for (int i = 0; i < RB; i++) { nx[i] = pn[i]; clo[i] = plo[i]; chi[i] = phi[i]; }
     }
 }
 
@@ -285,7 +305,7 @@ __device__ __forceinline__ uint32_t spread16(uint32_t x) {  // bit i (i < 16) ->
 
 // phase 0: lattice columns gx = 2j, every row.  phase 1: gx = 2j + 1, only gx >= start_odd[row].
 template <int HP>
-__global__ void __launch_bounds__(SC_TILE_THREADS, 3) k_scan_stage0(const ScPlan* __restrict__ plan, const float4* __restrict__ S,
+__global__ void __launch_bounds__(SC_TILE_THREADS, SC_STAGE0_MIN_CTAS) k_scan_stage0(const ScPlan* __restrict__ plan, const float4* __restrict__ S,
                                                                   const ScGeom* __restrict__ geom_all, const float* __restrict__ w_all,
                                                                   const double* __restrict__ wb_all, uint32_t* __restrict__ multi_bits,
                                                                   uint32_t* __restrict__ pass_bits, ScRecord* __restrict__ rec,

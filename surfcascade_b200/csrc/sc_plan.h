@@ -15,9 +15,15 @@
 #define SC_TILE_X 64
 #define SC_TILE_Y 16
 #define SC_TILE_THREADS 256
+#ifndef SC_STAGE0_MIN_CTAS
+#define SC_STAGE0_MIN_CTAS 3   // 80 registers: 3 CTAs (24 warps) per SM; 4 forces 64 registers and spills (measured slower)
+#endif
 
-// Integral strips: one warp walks one 32-column strip down the frame.
+// Integral strips: one warp walks one 32-column strip down the frame, SC_WALK_RB rows per prefetch block.
 #define SC_STRIP 32
+#ifndef SC_WALK_RB
+#define SC_WALK_RB 4
+#endif
 
 // Integral-image layout in HBM ("lattice-deinterleaved, half-split"):
 //   the reference keeps 8 interleaved floats (32 B) per pixel; a warp of 32 neighbouring windows on a step-s
