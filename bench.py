@@ -56,7 +56,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -270,10 +270,24 @@ def run_ours(args):
         carry_ms, _ = stats.get("k_strip_carry", (0.0, 0))
         total_k_ms = sum(v[0] for v in stats.values()) or 1.0
         weak_ref = mean(lambda x: x.weak_evals)
-        alg_scan_bytes = 32.0 * (4.0 * grid + 10.0 * weak_ref)  # this cascade's stage-0 patches are all 1x4 / 4x1 (10 corners)
+        vis_ref = mean(lambda x: x.visited)
+        # 32 B x (4 x prefilters + C_shape x weak evaluations) with the REFERENCE's counts (visited windows);
+        # model_c1.cfg's stage-0 patches are all 1x4 / 4x1 (10 corners), later stages are < 1 % of the evaluations
+        alg_scan_bytes = 32.0 * (4.0 * vis_ref + 10.0 * weak_ref)
         scan_gbs = alg_scan_bytes * frames_timed / (st0_ms / 1e3) / 1e9 if st0_ms else None
         alg_int_bytes = W * H + 32.0 * (W + 1) * (H + 1)
         int_gbs = alg_int_bytes * frames_timed / ((walk_ms + carry_ms) / 1e3) / 1e9 if walk_ms else None
+        traffic_scan = traffic_int = None
+        try:  # DRAM bytes per launch from the committed ncu --set full capture (profiles/), 8 frames per launch
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["dram_bytes_per_launch"]
+            traffic_scan = tj["k_scan_stage0_phase0"] + tj["k_scan_stage0_phase1"]
+            traffic_int = tj["k_integral_walk"]
+        except Exception:
+            pass
+        try:
+            l2_peak = h.probe_gather(64 << 20, 5)
+        except Exception:
+            l2_peak = None
         cpu = None
         if world == 1:
             try:
@@ -299,12 +313,16 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"kernel": "k_scan_stage0", "bound": "hbm", "achieved": scan_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": (scan_gbs / peak) if scan_gbs else None, "traffic": None,
-                         "note": "algorithmic gather bytes 32 B x (4 x grid windows + 10 x reference weak evals) per frame over the kernel's CUDA-event time; the gather is served by L1/L2, so this is a cache-resident rate set against the HBM copy peak (" + peak_src + "); the kernel is issue-bound, see DESIGN.md",
-                         "share_of_step": st0_ms / total_k_ms},
+                         "frac": (scan_gbs / peak) if scan_gbs else None, "traffic": traffic_scan,
+                         "traffic_note": "dram__bytes_read+write of the two k_scan_stage0 launches (even, odd columns) of one 8-frame scan group, ncu --set full, profiles/r1_traffic.json",
+                         "algorithmic_bytes_per_launch": alg_scan_bytes * 8,
+                         "note": "algorithmic gather bytes = 32 B x (4 x reference-visited windows + 10 x reference weak evaluations) over the kernel's CUDA-event time (both parity launches); the gather is served by L1/L2, not HBM, so this is a cache-resident rate set against the HBM copy peak (" + peak_src + "); the kernel is co-limited by issue slots and the L1 data pipe (ncu: 67 % / 66 %), see DESIGN.md",
+                         "share_of_step": st0_ms / total_k_ms,
+                         "l2_sector_gather_peak_gbs": l2_peak, "frac_of_l2_sector_gather_peak": (scan_gbs / l2_peak) if (scan_gbs and l2_peak) else None},
             "roofline_integral": {"kernel": "k_strip_carry+k_integral_walk", "bound": "hbm", "achieved": int_gbs, "peak": peak, "unit": "GB/s",
-                                  "frac": (int_gbs / peak) if int_gbs else None, "traffic": None, "share_of_step": (walk_ms + carry_ms) / total_k_ms,
-                                  "algorithmic_bytes_per_frame": alg_int_bytes},
+                                  "frac": (int_gbs / peak) if int_gbs else None, "traffic": traffic_int,
+                                  "traffic_note": "dram bytes of one 8-frame k_integral_walk launch (ncu); bench launches cover 32 frames",
+                                  "share_of_step": (walk_ms + carry_ms) / total_k_ms, "algorithmic_bytes_per_frame": alg_int_bytes},
             "kernel_ms_per_frame": {k: v[0] / frames_timed for k, v in stats.items()},
             "profiled_pass_ms_per_step": ms_prof / args.steps,
             "cpu_baseline": cpu,
@@ -318,7 +336,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32, help="1080p frames per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

@@ -161,6 +161,9 @@ int64_t sc_launch_count(const sc_handle* h);
  * sc_kernel_stats enumerates kernels by id 0,1,..; returns 1 past the last id.  Times are accumulated at sc_sync /
  * at the end of sc_detect. */
 int sc_set_profiling(sc_handle* h, int on);
+/* Measurement probe, no product role: GB/s of random 32-byte sector gathers (two 16-byte loads each, like one corner
+ * fetch) from a zeroed device table of table_bytes.  Tables below ~100 MB stay L2-resident on B200. */
+int sc_probe_gather(sc_handle* h, size_t table_bytes, int iters, double* gbps);
 int sc_kernel_stats(sc_handle* h, int kernel_id, const char** name, double* ms, int64_t* launches, int reset);
 
 /* ---- host-side grouping (next row N1) ------------------------------------------------------------------ */

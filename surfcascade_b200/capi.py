@@ -43,7 +43,7 @@ EXPORTS = ["sc_create", "sc_destroy", "sc_last_error", "sc_version", "sc_set_cas
            "sc_integral", "sc_features", "sc_window_sum", "sc_stage_scores", "sc_weak_predict", "sc_stage_predict", "sc_detect",
            "sc_detect_device", "sc_sync", "sc_last_counters", "sc_stream", "sc_launch_count", "sc_group_rectangles",
            "sc_set_profiling", "sc_kernel_stats", "sc_model_flatten", "sc_model_resave", "sc_pool_eval", "sc_pool_hist_device",
-           "sc_pool_auc_device"]
+           "sc_pool_auc_device", "sc_probe_gather"]
 
 _lib = None
 
@@ -312,6 +312,14 @@ class Handle:
             out[name.value.decode()] = (ms.value, n.value)
             k += 1
         return out
+
+    def probe_gather(self, table_bytes: int, iters: int = 10) -> float:
+        """GB/s of random 32-byte sector gathers from a table of table_bytes (L2-resident below ~100 MB)."""
+        L = lib()
+        L.sc_probe_gather.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
+        g = C.c_double(0)
+        self._check(L.sc_probe_gather(self._h, table_bytes, iters, C.byref(g)))
+        return g.value
 
     def sync(self):
         self._check(lib().sc_sync(self._h))

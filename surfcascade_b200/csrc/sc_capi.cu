@@ -901,6 +901,31 @@ int sc_sync(sc_handle* h) {
     return SC_OK;
 }
 
+int sc_probe_gather(sc_handle* h, size_t table_bytes, int iters, double* gbps) {
+    if (!h || !gbps || table_bytes < 4096 || iters < 1) return fail(h, SC_ERR_INVALID, "bad arguments");
+    SC_CUDA(h, cudaSetDevice(h->device));
+    DevBuf tab, sink;
+    SC_CUDA(h, tab.ensure(table_bytes));
+    SC_CUDA(h, sink.ensure(256));
+    SC_CUDA(h, cudaMemsetAsync(tab.p, 0, table_bytes, h->stream));
+    const uint32_t n_sectors = (uint32_t)std::min<size_t>(table_bytes / 32, 0x0fffffffu);
+    const int per_thread = 64, grid = h->n_sms * 32;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    for (int w = 0; w < 2; w++) sck::k_probe_gather<<<grid, 256, 0, h->stream>>>(tab.as<float4>(), n_sectors, per_thread, sink.as<float>());
+    cudaEventRecord(a, h->stream);
+    for (int i = 0; i < iters; i++) sck::k_probe_gather<<<grid, 256, 0, h->stream>>>(tab.as<float4>(), n_sectors, per_thread, sink.as<float>());
+    cudaEventRecord(b, h->stream);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    tab.release(); sink.release();
+    if (e != cudaSuccess) return cuda_fail(h, e, "sc_probe_gather");
+    *gbps = (double)grid * 256 * per_thread * 32.0 * iters / (ms * 1e6);
+    return SC_OK;
+}
+
 int sc_set_profiling(sc_handle* h, int on) {
     if (!h) return SC_ERR_INVALID;
     h->profiling = on != 0;

@@ -697,6 +697,25 @@ __global__ void k_weak_predict(const float* __restrict__ w36, const double* __re
     }
 }
 
+// Measurement probe (no product role): every thread gathers `per_thread` random 32-byte sectors (two 16-byte loads, as
+// a corner fetch does) from a table of n_sectors sectors; establishes the L2 / HBM sector-gather ceiling that
+// MEASURED_PEAKS.json lacks.
+__global__ void __launch_bounds__(256) k_probe_gather(const float4* __restrict__ table, uint32_t n_sectors, int per_thread, float* __restrict__ sink) {
+    uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    float acc = 0.f;
+    for (int i = 0; i < per_thread; i += 4) {
+        uint32_t idx[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { s = s * 1664525u + 1013904223u; idx[k] = (uint32_t)(((unsigned long long)(s >> 4) * n_sectors) >> 28); }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float4 a = __ldg(table + 2 * (size_t)idx[k]), b = __ldg(table + 2 * (size_t)idx[k] + 1);
+            acc += a.x + b.w;
+        }
+    }
+    if (acc == 123.456f) sink[0] = acc;  // keep the loads alive
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Training-side pool evaluation: candidate scoring of one boosting round,
 // GentleAdaboost.cpp:145-148 -> StageClassifier::Evaluate (StageClassifier.cpp:35-70) over
