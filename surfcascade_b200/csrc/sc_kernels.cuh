@@ -206,9 +206,9 @@ __device__ __forceinline__ float sumsq_hadd(const float* v) {
     return s;
 }
 
-// CalcFeature + Normalize for one projected patch; `base` = address of the window's low-half element.
+// CalcFeature's 32 box sums for one projected patch; `base` = address of the window's low-half element.
 template <int HP>
-__device__ __forceinline__ void descriptor(const char* __restrict__ base, const ScGeom& g, int hp, float* v) {
+__device__ __forceinline__ void box_sums(const char* __restrict__ base, const ScGeom& g, int hp, float* v) {
     if (g.shape == 0) {
         // 3 x 3 corner lattice, cells row-major (GetRectsFromPatch :360-377)
         Px a0 = load_px<HP>(base, g.c[0], hp), a1 = load_px<HP>(base, g.c[1], hp), a2 = load_px<HP>(base, g.c[2], hp);
@@ -229,6 +229,12 @@ __device__ __forceinline__ void descriptor(const char* __restrict__ base, const 
             t0 = t1; u0 = u1;
         }
     }
+}
+
+// CalcFeature + Normalize (DenseSURFFeatureExtractor.cpp:379-457), bit-exact.
+template <int HP>
+__device__ __forceinline__ void descriptor(const char* __restrict__ base, const ScGeom& g, int hp, float* v) {
+    box_sums<HP>(base, g, hp, v);
     const float theta = 0.353553385f;  // 2 / sqrtf(32.f), DenseSURFFeatureExtractor.h:36
     const float t = __fmul_rn(__fsqrt_rn(sumsq_hadd(v)), theta);
     const float t2 = -t;
