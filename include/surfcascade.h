@@ -157,6 +157,13 @@ void* sc_stream(sc_handle* h);
 /* Number of kernel launches issued by this handle so far. */
 int64_t sc_launch_count(const sc_handle* h);
 
+/* Parity hook of the stage-0 certified fast filter (csrc/sc_kernels.cuh): for explicit windows {x, y, l} on the image of the
+ * last sc_integral, the float sum of the fast weak-classifier outputs of stage 0, the float sum of the reference-arithmetic
+ * outputs (GentleAdaboost::Predict2's accumulator, GentleAdaboost.cpp:247-261), and the distance budget the scan's
+ * decision limits are built from.  Windows further than the budget from a threshold are decided by the fast sum; all
+ * others are re-evaluated exactly, so the filter never changes a result. */
+int sc_stage0_fast_check(sc_handle* h, const int32_t* wins, int n, float* fast_sum, float* exact_sum, double* margin);
+
 /* Optional per-kernel timing (CUDA events on the handle's stream around every launch of the detect path).
  * sc_kernel_stats enumerates kernels by id 0,1,..; returns 1 past the last id.  Times are accumulated at sc_sync /
  * at the end of sc_detect. */
@@ -164,6 +171,9 @@ int sc_set_profiling(sc_handle* h, int on);
 /* Measurement probe, no product role: GB/s of random 32-byte sector gathers (two 16-byte loads each, like one corner
  * fetch) from a zeroed device table of table_bytes.  Tables below ~100 MB stay L2-resident on B200. */
 int sc_probe_gather(sc_handle* h, size_t table_bytes, int iters, double* gbps);
+/* Measurement probe, no product role: GB/s of coalesced 16-byte loads (512 contiguous bytes per warp) streaming over a
+ * device table of table_bytes; mode 0 = L2-only loads (ld.global.cg), 1 = L1-allocating loads.  L2 -> SM ceiling. */
+int sc_probe_stream(sc_handle* h, size_t table_bytes, int iters, int mode, double* gbps);
 int sc_kernel_stats(sc_handle* h, int kernel_id, const char** name, double* ms, int64_t* launches, int reset);
 
 /* ---- host-side grouping (next row N1) ------------------------------------------------------------------ */

@@ -43,7 +43,7 @@ EXPORTS = ["sc_create", "sc_destroy", "sc_last_error", "sc_version", "sc_set_cas
            "sc_integral", "sc_features", "sc_window_sum", "sc_stage_scores", "sc_weak_predict", "sc_stage_predict", "sc_detect",
            "sc_detect_device", "sc_sync", "sc_last_counters", "sc_stream", "sc_launch_count", "sc_group_rectangles",
            "sc_set_profiling", "sc_kernel_stats", "sc_model_flatten", "sc_model_resave", "sc_pool_eval", "sc_pool_hist_device",
-           "sc_pool_auc_device", "sc_probe_gather"]
+           "sc_pool_auc_device", "sc_probe_gather", "sc_probe_stream", "sc_stage0_fast_check"]
 
 _lib = None
 
@@ -229,6 +229,15 @@ class Handle:
         self._check(lib().sc_stage_scores(self._h, w.ctypes.data, len(w), out.ctypes.data))
         return out
 
+    def stage0_fast_check(self, wins):
+        """(fast_sum [n], exact_sum [n], margin) of stage 0 for windows {x, y, l} on the last integral()."""
+        wins = np.ascontiguousarray(wins, np.int32).reshape(-1, 3)
+        fs = np.zeros(len(wins), np.float32); es = np.zeros(len(wins), np.float32); m = C.c_double(0)
+        L = lib()
+        L.sc_stage0_fast_check.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+        self._check(L.sc_stage0_fast_check(self._h, wins.ctypes.data, len(wins), fs.ctypes.data, es.ctypes.data, C.byref(m)))
+        return fs, es, m.value
+
     def weak_predict(self, w, bias, x) -> np.ndarray:
         w = np.ascontiguousarray(w, np.float32).reshape(-1, 33); x = np.ascontiguousarray(x, np.float32).reshape(-1, 32)
         bias = np.ascontiguousarray(bias, np.float64).reshape(-1)
@@ -319,6 +328,14 @@ class Handle:
         L.sc_probe_gather.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
         g = C.c_double(0)
         self._check(L.sc_probe_gather(self._h, table_bytes, iters, C.byref(g)))
+        return g.value
+
+    def probe_stream(self, table_bytes: int, iters: int = 10, mode: int = 0) -> float:
+        """GB/s of coalesced 16-byte loads over a table of table_bytes; mode 0 = L2-only loads, 1 = L1-allocating."""
+        L = lib()
+        L.sc_probe_stream.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        g = C.c_double(0)
+        self._check(L.sc_probe_stream(self._h, table_bytes, iters, mode, C.byref(g)))
         return g.value
 
     def sync(self):

@@ -78,6 +78,10 @@ struct sc_handle {
     sc_detect_params pparams{};
     ScPlan plan{};
     DevBuf d_plan, d_geom;
+    // stage-0 certified fast filter (sc_plan.h ScFastParams): one parameter block per column parity
+    bool allow_fast = true;     // SC_DISABLE_FAST=1 in the environment forces the exact-only kernel (A/B tests)
+    bool use_fast = false;
+    ScFastParams fast[2];
 
     // group buffers
     int group_frames = 0;       // frames one scan group holds (records, bitmasks)
@@ -182,6 +186,20 @@ sc_detect_params default_params() {
     return p;
 }
 
+// Distance budget between the fast filter's sum of weak outputs and the reference arithmetic's, stage 0
+// (sc_kernels.cuh "Error budget", doubled), plus the float summations and the division by n on both sides.
+double fast_margin(const sc_handle* h) {
+    const double u = 5.9604644775390625e-8;  // 2^-24
+    const int n0 = h->n_weak[0];
+    double margin = 0.0;
+    for (int q = 0; q < n0; q++) {
+        double n2 = 0.0;
+        for (int i = 0; i < 32; i++) n2 += (double)h->w[(size_t)q * 33 + i] * h->w[(size_t)q * 33 + i];
+        margin += 2.0 * (0.25 * 121.0 * u * std::sqrt(n2) + 1.5e-6);
+    }
+    return margin + (double)n0 * n0 * 4.0 * u + 8.0 * u * n0;
+}
+
 // Scale ladder, lattice and per-(scale, weak) projected geometry.  Host arithmetic mirrors ObjDetector.cpp:139,174,180
 // and ProjectPatches / GetRectsFromPatch (DenseSURFFeatureExtractor.cpp:486-508, 360-377) operation for operation.
 int build_plan(sc_handle* h, int W, int H, const sc_detect_params& prm, std::vector<ScGeom>* geom_out) {
@@ -237,6 +255,34 @@ int build_plan(sc_handle* h, int W, int H, const sc_detect_params& prm, std::vec
                 if (!sc_host::project_geom(h->tmpl, p.sc[i].l, h->rects[k], p.lay, ph * p.step,
                                            &(*geom_out)[((size_t)ph * nsc + i) * h->total_weak + k]))
                     return fail(h, SC_ERR_INVALID, "weak classifier patch is not 2x2 / 4x1 / 1x4 cells after projection");
+
+    // Certified fast filter for stage 0 (sc_kernels.cuh, "Error budget").  Limits are on the float sum of the fast weak outputs.
+    const int n0 = h->n_weak[0];
+    h->use_fast = h->allow_fast && !p.force_all && n0 <= SC_F_MAXW && nsc >= 1;
+    if (h->use_fast) {
+        const double margin = fast_margin(h);
+        const double tau = 0.5 * h->n_stages - 1.0;           // rejected at stage 0: multi == 2  <=>  score < tau (ObjDetector.cpp:201,214)
+        for (int ph = 0; ph < 2; ph++) {
+            ScFastParams& fp = h->fast[ph];
+            memset(&fp, 0, sizeof(fp));
+            fp.n_weak = n0; fp.n_scales = nsc; fp.blocks_per_frame = std::max(blocks, 1);
+            fp.lim_reject = std::nextafterf((float)((double)n0 * h->theta[0] - margin), -INFINITY);
+            fp.lim_skip = std::nextafterf((float)((double)n0 * tau - margin), -INFINITY);
+            fp.lim_noskip = std::nextafterf((float)((double)n0 * tau + margin), INFINITY);
+            for (int q = 0; q < n0; q++) {
+                fp.wb[q] = (float)((double)h->w[(size_t)q * 33 + 32] * h->bias[q]);
+                memcpy(fp.w[q], &h->w[(size_t)q * 33], 32 * sizeof(float));
+            }
+            for (int i = 0; i < nsc; i++) {
+                fp.block_base[i] = p.sc[i].block_base;
+                for (int q = 0; q < n0; q++) {
+                    const ScGeom& g = (*geom_out)[((size_t)ph * nsc + i) * h->total_weak + q];
+                    for (int k = 0; k < 10; k++) fp.geom[i][q][k] = g.c[k];
+                    fp.geom[i][q][10] = (uint32_t)g.shape;
+                }
+            }
+        }
+    }
     return SC_OK;
 }
 
@@ -319,15 +365,20 @@ int run_integral(sc_handle* h, const uint8_t* d_img, int n, int slot0) {
 
 // Launches the whole path for `g` frames already in d_img (device).  Detections are appended to det / det_count.
 // The scan kernels are instantiated per half-row distance of the layout (sc_plan.h): 256 .. 4096 float4.
-template <typename... A>
-void launch_stage0(int hp, int grid, size_t smem, cudaStream_t st, A... a) {
+template <bool FAST, typename... A>
+void launch_stage0_hp(int hp, int grid, size_t smem, cudaStream_t st, A... a) {
     switch (hp) {
-        case 256: sck::k_scan_stage0<256><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
-        case 512: sck::k_scan_stage0<512><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
-        case 1024: sck::k_scan_stage0<1024><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
-        case 2048: sck::k_scan_stage0<2048><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
-        default: sck::k_scan_stage0<4096><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
+        case 256: sck::k_scan_stage0<256, FAST><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
+        case 512: sck::k_scan_stage0<512, FAST><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
+        case 1024: sck::k_scan_stage0<1024, FAST><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
+        case 2048: sck::k_scan_stage0<2048, FAST><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
+        default: sck::k_scan_stage0<4096, FAST><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
     }
+}
+template <typename... A>
+void launch_stage0(bool fast, int hp, int grid, size_t smem, cudaStream_t st, A... a) {
+    if (fast) launch_stage0_hp<true>(hp, grid, smem, st, a...);
+    else launch_stage0_hp<false>(hp, grid, smem, st, a...);
 }
 template <typename... A>
 void launch_stage(int hp, int grid, size_t smem, cudaStream_t st, A... a) {
@@ -364,7 +415,7 @@ int run_group(sc_handle* h, sc_handle::Lane& L, int s0, int g, int frame0, sc_de
             const int rows0 = g * p.rows_per_frame;
             {
                 KernelSpan ks(h, K_STAGE0, st);
-                launch_stage0(p.lay.hp, g * p.blocks_per_frame, smem, st, dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, 0, start_odd);
+                launch_stage0(h->use_fast, p.lay.hp, g * p.blocks_per_frame, smem, st, h->fast[0], dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, 0, start_odd);
             }
             if (p.skip_rule) {
                 KernelSpan ks(h, K_EVENTS, st);
@@ -374,7 +425,7 @@ int run_group(sc_handle* h, sc_handle::Lane& L, int s0, int g, int frame0, sc_de
             }
             {
                 KernelSpan ks(h, K_STAGE0, st);
-                launch_stage0(p.lay.hp, g * p.blocks_per_frame, smem, st, dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, 1, start_odd);
+                launch_stage0(h->use_fast, p.lay.hp, g * p.blocks_per_frame, smem, st, h->fast[1], dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, 1, start_odd);
             }
         }
         const int tail_grid = h->n_sms * 8;
@@ -525,6 +576,8 @@ int sc_create(int device, sc_handle** out) {
     h->device = device;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return SC_ERR_CUDA; }
     cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device);
+    const char* nofast = getenv("SC_DISABLE_FAST");
+    h->allow_fast = !(nofast && nofast[0] == '1');
     *out = h;
     return SC_OK;
 }
@@ -707,7 +760,17 @@ static int features_impl(sc_handle* h, const sc_rect* rects, int n, float* out, 
 int sc_features(sc_handle* h, const sc_rect* rects, int n, float* out) { return out ? features_impl(h, rects, n, out, nullptr) : SC_ERR_INVALID; }
 int sc_window_sum(sc_handle* h, const sc_rect* rects, int n, float* out) { return out ? features_impl(h, rects, n, nullptr, out) : SC_ERR_INVALID; }
 
-int sc_stage_scores(sc_handle* h, const int32_t* wins, int n, float* out) {
+static int stage_scores_impl(sc_handle* h, const int32_t* wins, int n, float* out, float* out2, bool fast_check);
+
+int sc_stage_scores(sc_handle* h, const int32_t* wins, int n, float* out) { return stage_scores_impl(h, wins, n, out, nullptr, false); }
+
+int sc_stage0_fast_check(sc_handle* h, const int32_t* wins, int n, float* fast_sum, float* exact_sum, double* margin) {
+    if (!fast_sum || !exact_sum) return SC_ERR_INVALID;
+    if (margin && h && h->have_cascade) *margin = fast_margin(h);
+    return stage_scores_impl(h, wins, n, fast_sum, exact_sum, true);
+}
+
+static int stage_scores_impl(sc_handle* h, const int32_t* wins, int n, float* out, float* out2, bool fast_check) {
     if (!h || !wins || !out || n < 0) return SC_ERR_INVALID;
     if (!h->have_integral) return fail(h, SC_ERR_STATE, "sc_integral has not been called");
     if (!h->have_cascade) return fail(h, SC_ERR_STATE, "no cascade loaded");
@@ -730,17 +793,25 @@ int sc_stage_scores(sc_handle* h, const int32_t* wins, int n, float* out) {
     cudaError_t e = d_p.ensure(sizeof(ScPlan));
     if (e == cudaSuccess) e = d_g.ensure(geom.size() * sizeof(ScGeom));
     if (e == cudaSuccess) e = d_w.ensure((size_t)n * 3 * sizeof(int));
-    if (e == cudaSuccess) e = d_o.ensure((size_t)n * h->n_stages * sizeof(float));
+    const size_t out_floats = fast_check ? (size_t)n * 2 : (size_t)n * h->n_stages;
+    if (e == cudaSuccess) e = d_o.ensure(out_floats * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_p.p, &mini, sizeof(ScPlan), cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_g.p, geom.data(), geom.size() * sizeof(ScGeom), cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_w.p, wins, (size_t)n * 3 * sizeof(int), cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess) {
-        sck::k_stage_scores<<<(n + 63) / 64, 64, 0, h->stream>>>(d_p.as<ScPlan>(), h->d_hook_S.as<float4>(), d_g.as<ScGeom>(), h->d_w.as<float>(),
-                                                                  h->d_wb.as<double>(), d_w.as<int>(), n, d_o.as<float>());
+        if (fast_check)
+            sck::k_stage0_fast_check<<<(n + 63) / 64, 64, 0, h->stream>>>(d_p.as<ScPlan>(), h->d_hook_S.as<float4>(), d_g.as<ScGeom>(), h->d_w.as<float>(),
+                                                                           h->d_wb.as<double>(), d_w.as<int>(), n, d_o.as<float>(), d_o.as<float>() + n);
+        else
+            sck::k_stage_scores<<<(n + 63) / 64, 64, 0, h->stream>>>(d_p.as<ScPlan>(), h->d_hook_S.as<float4>(), d_g.as<ScGeom>(), h->d_w.as<float>(),
+                                                                      h->d_wb.as<double>(), d_w.as<int>(), n, d_o.as<float>());
         h->launches++;
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_o.p, (size_t)n * h->n_stages * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && fast_check) {
+        e = cudaMemcpyAsync(out, d_o.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out2, d_o.as<float>() + n, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+    } else if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_o.p, (size_t)n * h->n_stages * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     d_p.release(); d_g.release(); d_w.release(); d_o.release();
     if (e != cudaSuccess) return cuda_fail(h, e, "sc_stage_scores");
@@ -923,6 +994,31 @@ int sc_probe_gather(sc_handle* h, size_t table_bytes, int iters, double* gbps) {
     tab.release(); sink.release();
     if (e != cudaSuccess) return cuda_fail(h, e, "sc_probe_gather");
     *gbps = (double)grid * 256 * per_thread * 32.0 * iters / (ms * 1e6);
+    return SC_OK;
+}
+
+int sc_probe_stream(sc_handle* h, size_t table_bytes, int iters, int mode, double* gbps) {
+    if (!h || !gbps || table_bytes < (1u << 20) || iters < 1) return fail(h, SC_ERR_INVALID, "bad arguments");
+    SC_CUDA(h, cudaSetDevice(h->device));
+    DevBuf tab, sink;
+    SC_CUDA(h, tab.ensure(table_bytes));
+    SC_CUDA(h, sink.ensure(256));
+    SC_CUDA(h, cudaMemsetAsync(tab.p, 0, table_bytes, h->stream));
+    const uint32_t n4 = (uint32_t)std::min<size_t>(table_bytes / 16, 0x3fffffffu);
+    const int per_thread = 64, grid = h->n_sms * 16;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    for (int w = 0; w < 2; w++) sck::k_probe_stream<<<grid, 256, 0, h->stream>>>(tab.as<float4>(), n4, per_thread, mode, sink.as<float>());
+    cudaEventRecord(a, h->stream);
+    for (int i = 0; i < iters; i++) sck::k_probe_stream<<<grid, 256, 0, h->stream>>>(tab.as<float4>(), n4, per_thread, mode, sink.as<float>());
+    cudaEventRecord(b, h->stream);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    tab.release(); sink.release();
+    if (e != cudaSuccess) return cuda_fail(h, e, "sc_probe_stream");
+    *gbps = (double)grid * 256 * per_thread * 16.0 * iters / (ms * 1e6);
     return SC_OK;
 }
 

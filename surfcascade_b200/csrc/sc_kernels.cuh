@@ -274,17 +274,37 @@ __device__ __forceinline__ float stage_score(const char* __restrict__ base, cons
         g.c[0] = g0.x; g.c[1] = g0.y; g.c[2] = g0.z; g.c[3] = g0.w; g.c[4] = g1.x; g.c[5] = g1.y; g.c[6] = g1.z; g.c[7] = g1.w;
         g.c[8] = g2.x; g.c[9] = g2.y; g.shape = g2.z; g.pad = 0;
         float v[32];
+#ifdef SC_EXP_LOADS_ONLY   // tuning experiment: loads + box sums only (wrong results), to see what the memory system alone allows
+        box_sums<HP>(base, g, hp, v);
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i++) t += v[i];
+        acc += (t == 12345.678f) ? 1.f : 0.f;
+#else
         descriptor<HP>(base, g, hp, v);
         acc = __fadd_rn(acc, weak_predict(v, w + q * SC_W_PITCH, wb[q]));
+#endif
     }
     return __fdiv_rn(acc, (float)n_weak);
 }
 
 // DenseSURFFeatureExtractor::sum (:351-358) and the compare at ObjDetector.cpp:188; pf = byte offsets of the corners
 // (0,0) (l,0) (0,l) (l,l) from the window's low-half element
+// 16-byte read-only load that does not allocate in L1: the prefilter's four corners are used once, the descriptor
+// corners that follow have short-distance reuse worth keeping
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+#ifdef SC_PF_NOALLOC
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
 __device__ __forceinline__ float window_sum(const char* __restrict__ base, const uint32_t* pf) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(base + pf[0])), b = __ldg(reinterpret_cast<const float4*>(base + pf[1]));
-    const float4 c = __ldg(reinterpret_cast<const float4*>(base + pf[2])), d = __ldg(reinterpret_cast<const float4*>(base + pf[3]));
+    const float4 a = ldg_stream(reinterpret_cast<const float4*>(base + pf[0])), b = ldg_stream(reinterpret_cast<const float4*>(base + pf[1]));
+    const float4 c = ldg_stream(reinterpret_cast<const float4*>(base + pf[2])), d = ldg_stream(reinterpret_cast<const float4*>(base + pf[3]));
     const float s0 = __fsub_rn(__fadd_rn(a.x, d.x), __fadd_rn(b.x, c.x));
     const float s1 = __fsub_rn(__fadd_rn(a.y, d.y), __fadd_rn(b.y, c.y));
     const float s2 = __fsub_rn(__fadd_rn(a.z, d.z), __fadd_rn(b.z, c.z));
@@ -295,6 +315,102 @@ __device__ __forceinline__ float window_sum(const char* __restrict__ base, const
 // multi == 2 for a window rejected at stage p with stage score s (ObjDetector.cpp:201,214)
 __device__ __forceinline__ bool rejected_skips(float s, int p, int n_stages) {
     return ((double)s + (double)p + 1.0) / (double)n_stages < 0.5;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Certified fast filter for stage 0.
+//
+// 99.7 % of the windows that reach stage 0 are rejected there, and for a rejected window the reference's outputs
+// depend on the stage score only through two comparisons (score < theta, and the `multi` rule of ObjDetector.cpp:214).
+// fast_weak() evaluates the same real-valued function as descriptor() + weak_predict() -- on the SAME box sums, which
+// are computed with the reference's own float operations -- but with packed FFMA2 / FADD2 arithmetic, a saturating-FMA
+// clip, MUFU rsqrt / ex2 / rcp and a float sigmoid: ~200 instructions instead of ~690.  Its distance to the reference
+// arithmetic is bounded (below), so a window whose fast sum is further than that bound from both decision thresholds
+// is decided for certain; every other window (all survivors among them) is re-evaluated with the exact path.  The
+// window set, the scores of survivors and every counter are therefore identical to the exact-only kernel's.
+//
+// Error budget per weak classifier (u = 2^-24).  Both paths start from identical v[32].  With x = clip(v) / |clip(v)|:
+//   reference: sums of squares carry <= 12u relative, sqrt / divide / products 1u each -> every x_i within 30u |x_i|
+//              of the real value; the 4-lane dot adds <= 11u sum |w_i x_i|                -> |dz| <= 41u |w|_2 |x|_2
+//   fast     : FFMA2 sums <= 17u, rsqrt.approx 2 ulp, saturating FMA 2^-25 absolute on g in [-0.5, 0.5] with
+//              |g|_2 >= 0.5                                                              -> |dz| <= 80u |w|_2
+//   sigmoid  : slope <= 1/4; ex2.approx / rcp.approx / float rounding                    -> |dp| <= 1.5e-6 absolute
+// so |p_fast - p_ref| <= 0.25 * 121u * |w|_2 + 1.5e-6.  The host doubles this (ScFastParams.lim_*), and
+// tests/test_gpu_parity.py measures the actual distance on ~10^6 windows (it is ~50x smaller than the budget).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; sub.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// cell_sum() on channel pairs: the same two additions and one subtraction per channel, two channels per instruction
+__device__ __forceinline__ void cell_sum_p(const Px& A, const Px& B, const Px& C, const Px& D, float* v) {
+#pragma unroll
+    for (int c = 0; c < 8; c += 2) {
+        const float2 r = sub2(add2(make_float2(A.v[c], A.v[c + 1]), make_float2(D.v[c], D.v[c + 1])),
+                              add2(make_float2(B.v[c], B.v[c + 1]), make_float2(C.v[c], C.v[c + 1])));
+        v[c] = r.x; v[c + 1] = r.y;
+    }
+}
+
+// box_sums() with packed cell sums (bit-identical values)
+template <int HP>
+__device__ __forceinline__ void box_sums_p(const char* __restrict__ base, const ScGeom& g, int hp, float* v) {
+    if (g.shape == 0) {
+        Px a0 = load_px<HP>(base, g.c[0], hp), a1 = load_px<HP>(base, g.c[1], hp), a2 = load_px<HP>(base, g.c[2], hp);
+        const Px b0 = load_px<HP>(base, g.c[3], hp), b1 = load_px<HP>(base, g.c[4], hp), b2 = load_px<HP>(base, g.c[5], hp);
+        cell_sum_p(a0, a1, b0, b1, v);
+        cell_sum_p(a1, a2, b1, b2, v + 8);
+        a0 = load_px<HP>(base, g.c[6], hp); a1 = load_px<HP>(base, g.c[7], hp); a2 = load_px<HP>(base, g.c[8], hp);
+        cell_sum_p(b0, b1, a0, a1, v + 16);
+        cell_sum_p(b1, b2, a1, a2, v + 24);
+    } else {
+        Px t0 = load_px<HP>(base, g.c[0], hp), u0 = load_px<HP>(base, g.c[5], hp);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const Px t1 = load_px<HP>(base, g.c[k + 1], hp), u1 = load_px<HP>(base, g.c[k + 6], hp);
+            cell_sum_p(t0, t1, u0, u1, v + 8 * k);
+            t0 = t1; u0 = u1;
+        }
+    }
+}
+
+// Normalize + LogisticRegression::Predict on box sums v, approximate arithmetic (error budget above).
+// With t = theta |v| the clip is  clip(v_i) = 2t g_i,  g_i = sat(v_i / (2t) + 1/2) - 1/2  (one saturating FMA and one add);
+// the common factor 2t cancels in  z = w . clip(v) / |clip(v)| = (w . g) / sqrt(|g|^2 + eps / (2t)^2).
+template <typename WT>
+__device__ __forceinline__ float fast_tail(const float* v, const WT& w, float wb) {
+    float2 s = make_float2(FLT_EPSILON, 0.f);
+#pragma unroll
+    for (int i = 0; i < 16; i++) s = fma2(make_float2(v[2 * i], v[2 * i + 1]), make_float2(v[2 * i], v[2 * i + 1]), s);
+    const float a = __fmul_rn(rsqrt_approx(__fadd_rn(s.x, s.y)), 1.41421354f);  // 1 / (2 t) = 1 / (2 * 0.353553385 * |v|)
+    float2 sg = make_float2(__fmul_rn(FLT_EPSILON, __fmul_rn(a, a)), 0.f), d = make_float2(0.f, 0.f);
+    const float2 mh = make_float2(-0.5f, -0.5f);
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const float2 g = add2(make_float2(__saturatef(__fmaf_rn(v[2 * i], a, 0.5f)), __saturatef(__fmaf_rn(v[2 * i + 1], a, 0.5f))), mh);
+        sg = fma2(g, g, sg);
+        d = fma2(g, make_float2(w[2 * i], w[2 * i + 1]), d);
+    }
+    const float z = __fmaf_rn(__fadd_rn(d.x, d.y), rsqrt_approx(__fadd_rn(sg.x, sg.y)), wb);
+    return rcp_approx(__fadd_rn(1.f, ex2_approx(__fmul_rn(z, -1.44269502f))));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -310,8 +426,11 @@ __device__ __forceinline__ uint32_t spread16(uint32_t x) {  // bit i (i < 16) ->
 }
 
 // phase 0: lattice columns gx = 2j, every row.  phase 1: gx = 2j + 1, only gx >= start_odd[row].
-template <int HP>
-__global__ void __launch_bounds__(SC_TILE_THREADS, SC_STAGE0_MIN_CTAS) k_scan_stage0(const ScPlan* __restrict__ plan, const float4* __restrict__ S,
+//
+// FAST: the certified fast filter (above) runs on the prefilter survivors first and only what it cannot decide goes
+// through the exact arithmetic; fp carries its weights / geometry / limits in the constant bank.  !FAST ignores fp.
+template <int HP, bool FAST>
+__global__ void __launch_bounds__(SC_TILE_THREADS, SC_STAGE0_MIN_CTAS) k_scan_stage0(const __grid_constant__ ScFastParams fp, const ScPlan* __restrict__ plan, const float4* __restrict__ S,
                                                                   const ScGeom* __restrict__ geom_all, const float* __restrict__ w_all,
                                                                   const double* __restrict__ wb_all, uint32_t* __restrict__ multi_bits,
                                                                   uint32_t* __restrict__ pass_bits, ScRecord* __restrict__ rec,
@@ -320,17 +439,24 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, SC_STAGE0_MIN_CTAS) k_scan_st
     __shared__ uint32_t s_multi[SC_TILE_Y][4];
     __shared__ uint32_t s_pass[SC_TILE_Y][4];
     __shared__ uint16_t s_list[SC_TILE_X * SC_TILE_Y];
+    __shared__ uint16_t s_list2[FAST ? SC_TILE_X * SC_TILE_Y : 1];
     __shared__ int s_start[SC_TILE_Y];
-    __shared__ uint32_t s_count;
+    __shared__ uint32_t s_count, s_count2;
     __shared__ ScScale s_sc;
     extern __shared__ __align__(16) unsigned char s_dyn[];  // stage-0 weights, wb, geometry
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int f = blockIdx.x / plan->blocks_per_frame;
-    const int b = blockIdx.x - f * plan->blocks_per_frame;
-    int si = 0;
-    while (si + 1 < plan->n_scales && plan->sc[si + 1].block_base <= b) si++;
-    if (tid == 0) { s_count = 0; s_sc = plan->sc[si]; }
+    int f, b, si = 0;
+    if (FAST) {  // uniform-datapath version of the same lookup (constant bank)
+        f = blockIdx.x / fp.blocks_per_frame;
+        b = blockIdx.x - f * fp.blocks_per_frame;
+        while (si + 1 < fp.n_scales && fp.block_base[si + 1] <= b) si++;
+    } else {
+        f = blockIdx.x / plan->blocks_per_frame;
+        b = blockIdx.x - f * plan->blocks_per_frame;
+        while (si + 1 < plan->n_scales && plan->sc[si + 1].block_base <= b) si++;
+    }
+    if (tid == 0) { s_count = 0; s_count2 = 0; s_sc = plan->sc[si]; }
     __syncthreads();
     const int nx = s_sc.nx, ny = s_sc.ny;
     const int tb = b - s_sc.block_base;
@@ -362,9 +488,11 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, SC_STAGE0_MIN_CTAS) k_scan_st
     {
         const float thr = s_sc.thr;
         const bool use_pf = plan->use_prefilter != 0;
+        constexpr int NW = SC_TILE_THREADS / 32;
+        static_assert(SC_TILE_Y % NW == 0 && 4 * SC_TILE_Y <= SC_TILE_THREADS, "stage-0 tile shape");
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int row = warp + 8 * (i >> 1), half = i & 1;
+        for (int i = 0; i < 2 * (SC_TILE_Y / NW); i++) {
+            const int row = warp + NW * (i >> 1), half = i & 1;
             const int j = tx * SC_TILE_X + half * 32 + lane;
             const int gx = 2 * j + phase, gy = ty * SC_TILE_Y + row;
             bool valid = gx < nx && gy < ny;
@@ -387,8 +515,47 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, SC_STAGE0_MIN_CTAS) k_scan_st
     }
     __syncthreads();
 
-    // phase B: stage 0 on the dense list
-    const uint32_t count = s_count;
+    // phase B1: certified fast filter on the dense list; what it cannot decide is compacted into s_list2
+    if (FAST) {
+        const uint32_t n_pass = s_count;
+        for (uint32_t i0 = 0; i0 < n_pass; i0 += SC_TILE_THREADS) {
+            const uint32_t i = i0 + tid;
+            bool undecided = false;
+            uint32_t code = 0;
+            if (i < n_pass) {
+                code = s_list[i];
+                const int row = code >> 6, half = (code >> 5) & 1, ln = code & 31;
+                const int j = tx * SC_TILE_X + half * 32 + ln;
+                const int gy = ty * SC_TILE_Y + row;
+                const char* base = reinterpret_cast<const char*>(lo4 + (gy * ppitch + j));
+                float sum = 0.f;
+#pragma unroll 1
+                for (int q = 0; q < fp.n_weak; q++) {
+                    ScGeom g;
+#pragma unroll
+                    for (int k = 0; k < 10; k++) g.c[k] = fp.geom[si][q][k];
+                    g.shape = (int)fp.geom[si][q][10]; g.pad = 0;
+                    float v[32];
+                    box_sums_p<HP>(base, g, HP, v);
+                    sum = __fadd_rn(sum, fast_tail(v, fp.w[q], fp.wb[q]));
+                }
+                if (sum < fp.lim_reject && sum < fp.lim_skip) atomicOr(&s_multi[row][2 * half + (ln >> 4)], 1u << (2 * (ln & 15) + phase));
+                else undecided = !(sum < fp.lim_reject && sum >= fp.lim_noskip);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, undecided);
+            if (m) {
+                uint32_t base2 = 0;
+                if (lane == 0) base2 = atomicAdd(&s_count2, __popc(m));
+                base2 = __shfl_sync(0xffffffffu, base2, 0);
+                if (undecided) s_list2[base2 + __popc(m & ((1u << lane) - 1u))] = (uint16_t)code;
+            }
+        }
+        __syncthreads();
+    }
+
+    // phase B: stage 0 with the reference's arithmetic on the dense list (FAST: on what the filter left undecided)
+    const uint32_t count = FAST ? s_count2 : s_count;
+    const uint16_t* list = FAST ? s_list2 : s_list;
     const float theta0 = plan->theta[0];
     const int n_stages = plan->n_stages;
     const bool force = plan->force_all != 0;
@@ -398,7 +565,7 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, SC_STAGE0_MIN_CTAS) k_scan_st
         ScRecord r;
         r.fs = 0; r.yx = 0; r.rej = 0; r.score = 0;
         if (i < count) {
-            const uint32_t code = s_list[i];
+            const uint32_t code = list[i];
             const int row = code >> 6, half = (code >> 5) & 1, ln = code & 31;
             const int j = tx * SC_TILE_X + half * 32 + ln;
             const int gx = 2 * j + phase, gy = ty * SC_TILE_Y + row;
@@ -682,6 +849,29 @@ __global__ void k_stage_scores(const ScPlan* __restrict__ plan, const float4* __
     }
 }
 
+// Parity hook of the stage-0 fast filter: for explicit windows, the float sum of the fast weak outputs and the float sum
+// of the reference-arithmetic weak outputs (GentleAdaboost::Predict2's accumulator before the division).
+__global__ void k_stage0_fast_check(const ScPlan* __restrict__ plan, const float4* __restrict__ S, const ScGeom* __restrict__ geom_win,
+                                    const float* __restrict__ w_all, const double* __restrict__ wb_all, const int* __restrict__ wins, int n,
+                                    float* __restrict__ fast_sum, float* __restrict__ exact_sum) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const char* base = reinterpret_cast<const char*>(S + ((size_t)wins[3 * i + 1] * plan->lay.ppitch + wins[3 * i]));
+    float fs = 0.f, es = 0.f;
+    for (int q = 0; q < plan->n_weak[0]; q++) {
+        const ScGeom g = geom_win[(size_t)i * plan->total_weak + q];
+        float wl[32];
+#pragma unroll
+        for (int k = 0; k < 32; k++) wl[k] = w_all[(size_t)q * SC_W_PITCH + k];
+        float v[32];
+        box_sums_p<0>(base, g, plan->lay.hp, v);
+        fs = __fadd_rn(fs, fast_tail(v, wl, (float)wb_all[q]));
+        descriptor<0>(base, g, plan->lay.hp, v);
+        es = __fadd_rn(es, weak_predict(v, w_all + (size_t)q * SC_W_PITCH, wb_all[q]));
+    }
+    fast_sum[i] = fs; exact_sum[i] = es;
+}
+
 // LogisticRegression::Predict on explicit (weights, descriptor) pairs; with `mean` non-null thread 0 also folds
 // the probabilities in order into GentleAdaboost::Predict2's float32 mean.
 __global__ void k_weak_predict(const float* __restrict__ w36, const double* __restrict__ wb, const float* __restrict__ x, int n,
@@ -720,6 +910,26 @@ __global__ void __launch_bounds__(256) k_probe_gather(const float4* __restrict__
         }
     }
     if (acc == 123.456f) sink[0] = acc;  // keep the loads alive
+}
+
+// Measurement probe (no product role): coalesced 16-byte loads (512 contiguous bytes per warp, as one corner fetch of the
+// scan in the half-split layout) streaming over an L2-resident table; mode 0 = ld.global.cg (L2 only), 1 = ld.global.nc
+// (allocates in L1).  Establishes the L2 -> SM bandwidth ceiling the scan's sector traffic is set against.
+__global__ void __launch_bounds__(256) k_probe_stream(const float4* __restrict__ table, uint32_t n4, int per_thread, int mode, float* __restrict__ sink) {
+    float acc = 0.f;
+    uint32_t pos = (uint32_t)(((unsigned long long)blockIdx.x * per_thread * 256u) % n4) + threadIdx.x;
+    for (int i = 0; i < per_thread; i += 4) {
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t p = pos + (uint32_t)(i + k) * 256u;
+            p = p >= n4 ? p % n4 : p;
+            v[k] = mode ? __ldg(table + p) : __ldcg(table + p);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc += v[k].x + v[k].w;
+    }
+    if (acc == 123.456f) sink[0] = acc;
 }
 
 // ---------------------------------------------------------------------------------------------------------

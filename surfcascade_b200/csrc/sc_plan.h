@@ -13,8 +13,12 @@
 // the even columns until the first window that does not skip; the scan therefore evaluates the even columns first
 // (phase 0) and the odd columns only from that window on (phase 1), about 56-58 % of the lattice at 1080p.
 #define SC_TILE_X 64
+#ifndef SC_TILE_Y
 #define SC_TILE_Y 16
-#define SC_TILE_THREADS 256
+#endif
+#ifndef SC_TILE_THREADS
+#define SC_TILE_THREADS 256   // SC_TILE_Y must be a multiple of the warp count; 4 * SC_TILE_Y <= SC_TILE_THREADS
+#endif
 #ifndef SC_STAGE0_MIN_CTAS
 #define SC_STAGE0_MIN_CTAS 3   // 80 registers: 3 CTAs (24 warps) per SM; 4 forces 64 registers and spills (measured slower)
 #endif
@@ -89,6 +93,23 @@ struct ScGeom {
     uint32_t c[10];
     int shape;
     int pad;
+};
+
+// Stage-0 fast filter (k_scan_stage0f): everything one launch needs, passed BY VALUE as a __grid_constant__ kernel
+// parameter so that weights and corner offsets are read through the constant bank into uniform registers (no shared-
+// memory wavefronts, no per-thread registers).  Used when the stage has at most SC_F_MAXW weak classifiers.
+#define SC_F_MAXW 6
+struct ScFastParams {
+    int n_weak, n_scales, blocks_per_frame, pad0;
+    // certified decisions on the float sum of the fast weak outputs (see fast_weak() for the error budget):
+    //   sum <  lim_reject                  -> the reference's stage score is < theta for certain
+    //   sum <  lim_skip / >= lim_noskip    -> the rejected window's `multi` is 2 / 1 for certain
+    // anything else is re-evaluated with the reference's exact arithmetic
+    float lim_reject, lim_skip, lim_noskip, pad1;
+    float wb[8];                                         // float(w[32] * bias)
+    int block_base[SC_PLAN_MAX_SCALES];                  // first stage-0 CTA of every scale inside a frame
+    float w[SC_F_MAXW][32];
+    uint32_t geom[SC_PLAN_MAX_SCALES][SC_F_MAXW][12];    // ScGeom of (this launch's column parity, scale, weak)
 };
 
 // Device record of a window that passed stage 0 (or of every window in force_all mode).

@@ -1,0 +1,94 @@
+"""GPU: the stage-0 certified fast filter (csrc/sc_kernels.cuh) never changes a result.
+
+1. Its distance to the reference arithmetic stays inside the budget the decision limits are built from (measured on
+   ~4*10^5 windows of textured and pure-noise frames; the bar is a quarter of the budget).
+2. The scan with the filter equals the exact-only scan (SC_DISABLE_FAST=1) bit for bit: detections, scores, counters.
+3. Cascades cut and re-thresholded so that the filter's three decisions (reject, skip, no-skip) all sit inside the
+   score distribution still match the oracle: theta at the median stage-0 score (half of the windows go through the
+   exact path), 1 / 2 / 3 stages (the `multi` rule of a stage-0 reject is never / never / score-dependent).
+"""
+import dataclasses
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from surfcascade_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _windows(h, w, n, rng):
+    out = []
+    for _ in range(n):
+        l = int(rng.integers(40, min(h, w)))
+        out.append((int(rng.integers(0, w - l + 1)), int(rng.integers(0, h - l + 1)), l))
+    return np.array(out, np.int32)
+
+
+@pytest.mark.parametrize("kind", ["frame", "noise", "flat"])
+def test_fast_sum_within_budget(gpu_handle, kind):
+    h, w = 480, 640
+    img = {"frame": lambda: synth.frame(h, w, 21), "noise": lambda: synth.noise_frame(h, w, 22),
+           "flat": lambda: np.full((h, w), 77, np.uint8)}[kind]()
+    if kind == "flat":
+        img[100:140, 200:260] = 200  # mostly zero descriptors (eps-dominated norms), one edge
+    gpu_handle.integral(img, want_output=False)
+    wins = _windows(h, w, 150000 if kind != "flat" else 20000, np.random.default_rng(3))
+    fs, es, margin = gpu_handle.stage0_fast_check(wins)
+    assert np.isfinite(fs).all() and np.isfinite(es).all()
+    err = np.abs(fs.astype(np.float64) - es.astype(np.float64)).max()
+    assert 0 < margin < 1e-3
+    assert err < margin / 4, f"fast filter error {err:.3e} vs budget {margin:.3e}"
+
+
+def _exact_only_handle(model):
+    os.environ["SC_DISABLE_FAST"] = "1"
+    try:
+        h = capi.Handle(0)
+    finally:
+        del os.environ["SC_DISABLE_FAST"]
+    h.load_model(model, 40)
+    return h
+
+
+def test_filtered_scan_equals_exact_only_scan(gpu_handle, model_c1):
+    hx = _exact_only_handle(model_c1)
+    try:
+        for frames, prm in [([synth.frame(1080, 1920, 31)], capi.params()),
+                            ([synth.frame(240, 320, s) for s in range(4)] + [synth.noise_frame(240, 320, 7)], capi.params()),
+                            ([synth.frame(301, 517, 4)], capi.params(base=70)),
+                            ([synth.frame(200, 260, 6)], capi.params(skip_rule=False)),
+                            ([synth.frame(200, 260, 6)], capi.params(prefilter=-1, step=1))]:
+            a, ca = gpu_handle.detect(frames, prm)
+            b, cb = hx.detect(frames, prm)
+            assert a.tobytes() == b.tobytes()
+            for x, y in zip(ca, cb):
+                assert bytes(x) == bytes(y)
+    finally:
+        hx.close()
+
+
+@pytest.mark.parametrize("n_stages,theta0", [(4, 0.29), (3, None), (3, 0.50), (2, None), (1, None), (1, 0.29)])
+def test_recut_cascades_match_oracle(oracle_cascade, n_stages, theta0):
+    c = oracle_cascade.c
+    k = int(c.n_weak[:n_stages].sum())
+    theta = c.theta[:n_stages].copy()
+    if theta0 is not None:
+        theta[0] = np.float32(theta0)
+    cut = dataclasses.replace(c, theta=theta, n_weak=c.n_weak[:n_stages].copy(), patch_index=c.patch_index[:k].copy(), w=c.w[:k].copy(),
+                              bias=c.bias[:k].copy())
+    bc = O.BoundCascade(cut)
+    h = capi.Handle(0)
+    try:
+        h.set_cascade(40, bc.theta, bc.n_weak, bc.rects, bc.w, bc.bias)
+        for img in (synth.frame(240, 320, 41), synth.noise_frame(120, 160, 42)):
+            dets, cnts = h.detect([img], capi.params(), cap=1 << 20)
+            want = O.detect(O.integral(img), bc, O.params(base=40, nthreads=8), cap=1 << 20)
+            assert cnts[0].visited == want.counters[O.C_VISITED] and cnts[0].prefilter_pass == want.counters[O.C_PREFILTER]
+            assert [cnts[0].reach[s] for s in range(n_stages)] == [int(want.counters[O.C_REACH0 + s]) for s in range(n_stages)]
+            assert np.array_equal(dets["x"], want.x) and np.array_equal(dets["y"], want.y) and np.array_equal(dets["l"], want.l)
+            np.testing.assert_allclose(dets["score"], want.score, rtol=1e-6, atol=0)
+    finally:
+        h.close()
