@@ -93,7 +93,7 @@ struct sc_handle {
     struct Lane {
         cudaStream_t st = nullptr;
         cudaEvent_t done = nullptr;
-        DevBuf d_multi, d_pass, d_visited, d_start, d_rec, d_idx[2], d_small;
+        DevBuf d_multi, d_pass, d_visited, d_start, d_rec, d_idx[2], d_small, d_chunks;  // d_chunks: work list of k_scan_odd (32-window runs of reachable odd columns)
     };
     Lane lanes[2];
     int n_lanes = 0;
@@ -123,7 +123,7 @@ struct sc_handle {
 namespace {
 
 // d_small layout (uint32): [0] rec_count, [1..16] per-stage index-list counts, [17] det_count
-enum { SM_REC = 0, SM_STAGE0 = 1, SM_DET = 17, SM_WORDS = 32 };
+enum { SM_REC = 0, SM_STAGE0 = 1, SM_DET = 17, SM_CHUNKS = 18, SM_CURSOR = 19, SM_WORDS = 32 };
 
 int fail(sc_handle* h, int code, const std::string& msg) {
     if (h) h->err = msg;
@@ -140,9 +140,9 @@ int cuda_fail(sc_handle* h, cudaError_t e, const char* what) {
         if (e_ != cudaSuccess) return cuda_fail((h), e_, #call); \
     } while (0)
 
-enum { K_CARRY = 0, K_WALK, K_STAGE0, K_STAGE, K_REPLAY, K_FINALIZE, K_EVENTS, K_POOL, K_COUNT };
+enum { K_CARRY = 0, K_WALK, K_STAGE0, K_STAGE, K_REPLAY, K_FINALIZE, K_EVENTS, K_POOL, K_STAGE0_ODD, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"k_strip_carry", "k_integral_walk", "k_scan_stage0", "k_scan_stage", "k_replay_rows", "k_finalize",
-                                            "k_row_events", "k_pool_hist"};
+                                            "k_row_events", "k_pool_hist", "k_scan_stage0_odd"};
 
 cudaEvent_t take_event(sc_handle* h) {
     cudaEvent_t e = nullptr;
@@ -341,6 +341,7 @@ int ensure_group_buffers(sc_handle* h, int want_frames, bool own_images) {
         SC_CUDA(h, L.d_idx[0].ensure(align256(std::max<size_t>(recs, 1) * 4)));
         SC_CUDA(h, L.d_idx[1].ensure(align256(std::max<size_t>(recs, 1) * 4)));
         SC_CUDA(h, L.d_small.ensure(SM_WORDS * 4));
+        SC_CUDA(h, L.d_chunks.ensure(align256(((size_t)g * (p.windows_per_frame / 64 + p.rows_per_frame) + 64) * 4)));
     }
     if (!h->ev_integral) SC_CUDA(h, cudaEventCreateWithFlags(&h->ev_integral, cudaEventDisableTiming));
     h->rec_cap = (uint32_t)recs;
@@ -417,14 +418,31 @@ int run_group(sc_handle* h, sc_handle::Lane& L, int s0, int g, int frame0, sc_de
                 KernelSpan ks(h, K_STAGE0, st);
                 launch_stage0(h->use_fast, p.lay.hp, g * p.blocks_per_frame, smem, st, h->fast[0], dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, 0, start_odd);
             }
+            // odd columns: with the adaptive stride they are reachable only as ragged row suffixes -> list of 32-window runs
+            // and persistent warps (k_scan_odd); without it (or without the fast filter) the tile kernel does them all
+            const bool odd_list = p.skip_rule && h->use_fast;
             if (p.skip_rule) {
+                if (odd_list) SC_CUDA(h, cudaMemsetAsync(small + SM_CHUNKS, 0, 8, st));
                 KernelSpan ks(h, K_EVENTS, st);
-                sck::k_row_events<<<(rows0 + 127) / 128, 128, 0, st>>>(dp, g, multi, start_odd, d_counters);
+                sck::k_row_events<<<(rows0 + 127) / 128, 128, 0, st>>>(dp, g, multi, start_odd, d_counters, odd_list ? L.d_chunks.as<uint32_t>() : nullptr,
+                                                                        small + SM_CHUNKS);
             } else {
                 SC_CUDA(h, cudaMemsetAsync(start_odd, 0, (size_t)rows0 * 4, st));  // every odd column is visited
             }
-            {
-                KernelSpan ks(h, K_STAGE0, st);
+            KernelSpan ks(h, K_STAGE0_ODD, st);
+            if (odd_list) {
+                const int grid = h->n_sms * SC_STAGE0_MIN_CTAS;
+                switch (p.lay.hp) {
+#define SC_ODD(HPV) sck::k_scan_odd<HPV><<<grid, 256, 0, st>>>(h->fast[1], dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, start_odd, \
+                                                            L.d_chunks.as<uint32_t>(), small + SM_CHUNKS, small + SM_CURSOR)
+                    case 256: SC_ODD(256); break;
+                    case 512: SC_ODD(512); break;
+                    case 1024: SC_ODD(1024); break;
+                    case 2048: SC_ODD(2048); break;
+                    default: SC_ODD(4096); break;
+#undef SC_ODD
+                }
+            } else {
                 launch_stage0(h->use_fast, p.lay.hp, g * p.blocks_per_frame, smem, st, h->fast[1], dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, 1, start_odd);
             }
         }
@@ -589,7 +607,7 @@ void sc_destroy(sc_handle* h) {
     for (auto& L : h->lanes) {
         if (L.st) { cudaStreamSynchronize(L.st); cudaStreamDestroy(L.st); }
         if (L.done) cudaEventDestroy(L.done);
-        DevBuf* lb[] = {&L.d_multi, &L.d_pass, &L.d_visited, &L.d_start, &L.d_rec, &L.d_idx[0], &L.d_idx[1], &L.d_small};
+        DevBuf* lb[] = {&L.d_multi, &L.d_pass, &L.d_visited, &L.d_start, &L.d_rec, &L.d_idx[0], &L.d_idx[1], &L.d_small, &L.d_chunks};
         for (DevBuf* b : lb) b->release();
     }
     if (h->ev_integral) cudaEventDestroy(h->ev_integral);
@@ -1005,12 +1023,19 @@ int sc_probe_stream(sc_handle* h, size_t table_bytes, int iters, int mode, doubl
     SC_CUDA(h, sink.ensure(256));
     SC_CUDA(h, cudaMemsetAsync(tab.p, 0, table_bytes, h->stream));
     const uint32_t n4 = (uint32_t)std::min<size_t>(table_bytes / 16, 0x3fffffffu);
-    const int per_thread = 64, grid = h->n_sms * 16;
+    // mode bit 0: 0 = ld.global.cg, 1 = ld.global.nc; bits 1..: independent loads in flight per thread (0 -> 4, 1 -> 8, 2 -> 16)
+    const int per_thread = 64, grid = h->n_sms * 32, unroll = mode >> 1;
+    mode &= 1;
+    auto launch = [&]() {
+        if (unroll == 2) sck::k_probe_stream<16><<<grid, 256, 0, h->stream>>>(tab.as<float4>(), n4, per_thread, mode, sink.as<float>());
+        else if (unroll == 1) sck::k_probe_stream<8><<<grid, 256, 0, h->stream>>>(tab.as<float4>(), n4, per_thread, mode, sink.as<float>());
+        else sck::k_probe_stream<4><<<grid, 256, 0, h->stream>>>(tab.as<float4>(), n4, per_thread, mode, sink.as<float>());
+    };
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
-    for (int w = 0; w < 2; w++) sck::k_probe_stream<<<grid, 256, 0, h->stream>>>(tab.as<float4>(), n4, per_thread, mode, sink.as<float>());
+    for (int w = 0; w < 2; w++) launch();
     cudaEventRecord(a, h->stream);
-    for (int i = 0; i < iters; i++) sck::k_probe_stream<<<grid, 256, 0, h->stream>>>(tab.as<float4>(), n4, per_thread, mode, sink.as<float>());
+    for (int i = 0; i < iters; i++) launch();
     cudaEventRecord(b, h->stream);
     cudaError_t e = cudaStreamSynchronize(h->stream);
     float ms = 0.f;

@@ -96,9 +96,9 @@ __global__ void __launch_bounds__(128) k_integral_walk(const uint8_t* __restrict
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     // this lane's integral column X = x + 1: in-plane column and the plane column residue are fixed
     const int X = x + 1, px = X / L.sx, rx = X - px * L.sx;
-    if (valid) { float4* o = Sf + (size_t)rx * L.plane4 + px; o[0] = zero; o[L.hp] = zero; }      // row Y = 0
+    if (valid) { float4* o = Sf + (size_t)rx * L.plane4 + SC_COL(px); o[0] = zero; o[SC_HI(L.hp)] = zero; }      // row Y = 0
     if (s == 0 && lane == 0)                                                                      // column X = 0
-        for (int Y = 0; Y <= H; Y++) { float4* o = Sf + sc_layout_index(L, 0, Y); o[0] = zero; o[L.hp] = zero; }
+        for (int Y = 0; Y <= H; Y++) { float4* o = Sf + sc_layout_index(L, 0, Y); o[0] = zero; o[SC_HI(L.hp)] = zero; }
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const int4* cr = reinterpret_cast<const int4*>(carry + (((size_t)f * H) * n_strips + s) * 8);
     const size_t cr_step = (size_t)n_strips * 2;
@@ -146,9 +146,9 @@ __global__ void __launch_bounds__(128) k_integral_walk(const uint8_t* __restrict
                 }
                 if (++ry == L.sy) { ry = 0; py++; }
                 if (valid) {
-                    float4* o = Sf + (size_t)(ry * L.sx + rx) * L.plane4 + (size_t)py * L.ppitch + px;
+                    float4* o = Sf + (size_t)(ry * L.sx + rx) * L.plane4 + (size_t)py * L.ppitch + SC_COL(px);
                     o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                    o[L.hp] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                    o[SC_HI(L.hp)] = make_float4(acc[4], acc[5], acc[6], acc[7]);
                 }
                 prev = cur; cur = nx[i];
             }
@@ -165,7 +165,7 @@ __global__ void k_export_integral(const float4* __restrict__ S, const ScLayout L
         const int Y = i / (W + 1), X = i - Y * (W + 1);
         const float4* p = S + sc_layout_index(L, X, Y);
         out[2 * (size_t)i] = p[0];
-        out[2 * (size_t)i + 1] = p[L.hp];
+        out[2 * (size_t)i + 1] = p[SC_HI(L.hp)];
     }
 }
 
@@ -180,6 +180,12 @@ struct Px { float v[8]; };
 template <int HP>
 __device__ __forceinline__ Px load_px(const char* __restrict__ base, uint32_t off, int hp) {
     const float4* p = reinterpret_cast<const float4*>(base + off);
+#if SC_PAIRED
+    Px q;  // one 256-bit load: both halves of the pixel
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(q.v[0]), "=f"(q.v[1]), "=f"(q.v[2]), "=f"(q.v[3]), "=f"(q.v[4]), "=f"(q.v[5]), "=f"(q.v[6]), "=f"(q.v[7]) : "l"(p));
+    return q;
+#endif
     const float4 lo = __ldg(p), hi = __ldg(p + (HP ? HP : hp));
     Px r;
     r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w; r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
@@ -436,6 +442,7 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, SC_STAGE0_MIN_CTAS) k_scan_st
                                                                   uint32_t* __restrict__ pass_bits, ScRecord* __restrict__ rec,
                                                                   uint32_t* __restrict__ rec_count, uint32_t rec_cap, int phase,
                                                                   const int* __restrict__ start_odd) {
+    const uint32_t block = blockIdx.x;
     __shared__ uint32_t s_multi[SC_TILE_Y][4];
     __shared__ uint32_t s_pass[SC_TILE_Y][4];
     __shared__ uint16_t s_list[SC_TILE_X * SC_TILE_Y];
@@ -448,12 +455,12 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, SC_STAGE0_MIN_CTAS) k_scan_st
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int f, b, si = 0;
     if (FAST) {  // uniform-datapath version of the same lookup (constant bank)
-        f = blockIdx.x / fp.blocks_per_frame;
-        b = blockIdx.x - f * fp.blocks_per_frame;
+        f = block / fp.blocks_per_frame;
+        b = block - f * fp.blocks_per_frame;
         while (si + 1 < fp.n_scales && fp.block_base[si + 1] <= b) si++;
     } else {
-        f = blockIdx.x / plan->blocks_per_frame;
-        b = blockIdx.x - f * plan->blocks_per_frame;
+        f = block / plan->blocks_per_frame;
+        b = block - f * plan->blocks_per_frame;
         while (si + 1 < plan->n_scales && plan->sc[si + 1].block_base <= b) si++;
     }
     if (tid == 0) { s_count = 0; s_count2 = 0; s_sc = plan->sc[si]; }
@@ -498,7 +505,7 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, SC_STAGE0_MIN_CTAS) k_scan_st
             bool valid = gx < nx && gy < ny;
             if (phase) valid = valid && gx >= s_start[row];
             bool pass = false;
-            if (valid) pass = use_pf ? (window_sum(reinterpret_cast<const char*>(lo4 + (gy * ppitch + j)), s_sc.pf[phase]) > thr) : true;
+            if (valid) pass = use_pf ? (window_sum(reinterpret_cast<const char*>(lo4 + (gy * ppitch + SC_COL(j))), s_sc.pf[phase]) > thr) : true;
             const uint32_t m = __ballot_sync(0xffffffffu, pass);
             const uint32_t fail = __ballot_sync(0xffffffffu, valid && !pass);
             uint32_t base = 0;
@@ -521,13 +528,13 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, SC_STAGE0_MIN_CTAS) k_scan_st
         for (uint32_t i0 = 0; i0 < n_pass; i0 += SC_TILE_THREADS) {
             const uint32_t i = i0 + tid;
             bool undecided = false;
-            uint32_t code = 0;
+            uint32_t code = 0, word = 0xffffffffu, bit = 0;
             if (i < n_pass) {
                 code = s_list[i];
                 const int row = code >> 6, half = (code >> 5) & 1, ln = code & 31;
                 const int j = tx * SC_TILE_X + half * 32 + ln;
                 const int gy = ty * SC_TILE_Y + row;
-                const char* base = reinterpret_cast<const char*>(lo4 + (gy * ppitch + j));
+                const char* base = reinterpret_cast<const char*>(lo4 + (gy * ppitch + SC_COL(j)));
                 float sum = 0.f;
 #pragma unroll 1
                 for (int q = 0; q < fp.n_weak; q++) {
@@ -539,9 +546,10 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, SC_STAGE0_MIN_CTAS) k_scan_st
                     box_sums_p<HP>(base, g, HP, v);
                     sum = __fadd_rn(sum, fast_tail(v, fp.w[q], fp.wb[q]));
                 }
-                if (sum < fp.lim_reject && sum < fp.lim_skip) atomicOr(&s_multi[row][2 * half + (ln >> 4)], 1u << (2 * (ln & 15) + phase));
+                if (sum < fp.lim_reject && sum < fp.lim_skip) { word = (uint32_t)(row * 4 + 2 * half + (ln >> 4)); bit = 1u << (2 * (ln & 15) + phase); }
                 else undecided = !(sum < fp.lim_reject && sum >= fp.lim_noskip);
             }
+            if (bit) atomicOr(&s_multi[word >> 2][word & 3], bit);  // (warp-aggregating these with match.any measured slower)
             const uint32_t m = __ballot_sync(0xffffffffu, undecided);
             if (m) {
                 uint32_t base2 = 0;
@@ -569,7 +577,7 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, SC_STAGE0_MIN_CTAS) k_scan_st
             const int row = code >> 6, half = (code >> 5) & 1, ln = code & 31;
             const int j = tx * SC_TILE_X + half * 32 + ln;
             const int gx = 2 * j + phase, gy = ty * SC_TILE_Y + row;
-            const float score = stage_score<HP>(reinterpret_cast<const char*>(lo4 + (gy * ppitch + j)), sg, sw, swb, n_weak, HP);
+            const float score = stage_score<HP>(reinterpret_cast<const char*>(lo4 + (gy * ppitch + SC_COL(j))), sg, sw, swb, n_weak, HP);
             const bool rejected = score < theta0;
             if (rejected && rejected_skips(score, 0, n_stages)) atomicOr(&s_multi[row][2 * half + (ln >> 4)], 1u << (2 * (ln & 15) + phase));
             push = !rejected || force;
@@ -611,8 +619,11 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, SC_STAGE0_MIN_CTAS) k_scan_st
 // After phase 0: per lattice row, the first even column whose window does not certainly skip (multi bit clear: it
 // passed stage 0, or was rejected with (s + 1) / N >= 0.5).  The reference's chain x += multi * step stays on even
 // columns up to there; odd columns can only be visited from the next one on.
+// With chunk_list non-null it also emits the work list of k_scan_odd: one entry (row << 10 | k) per run of 32 reachable odd
+// columns start + 64 k + 2 lane of the row.
 __global__ void __launch_bounds__(128) k_row_events(const ScPlan* __restrict__ plan, int nframes, const uint32_t* __restrict__ multi_bits,
-                                                     int* __restrict__ start_odd, unsigned long long* __restrict__ counters) {
+                                                     int* __restrict__ start_odd, unsigned long long* __restrict__ counters,
+                                                     uint32_t* __restrict__ chunk_list, uint32_t* __restrict__ chunk_count) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int rows = plan->rows_per_frame;
     if (t >= nframes * rows) return;
@@ -629,7 +640,101 @@ __global__ void __launch_bounds__(128) k_row_events(const ScPlan* __restrict__ p
         if (z) { start = 32 * wi + __ffs(z); break; }  // (ffs - 1) is the even column, + 1 the first odd one
     }
     start_odd[t] = start;
-    if (start < nx) atomicAdd(&counters[(size_t)f * SC_CNT_STRIDE + SC_CNT_EVALODD], (unsigned long long)((nx - start + 1) / 2));
+    if (start < nx) {
+        const int n_odd = (nx - start + 1) / 2;
+        atomicAdd(&counters[(size_t)f * SC_CNT_STRIDE + SC_CNT_EVALODD], (unsigned long long)n_odd);
+        if (chunk_list) {
+            const int n = (n_odd + 31) / 32;
+            const uint32_t base = atomicAdd(chunk_count, (uint32_t)n);
+            for (int k = 0; k < n; k++) chunk_list[base + k] = ((uint32_t)t << 10) | (uint32_t)k;
+        }
+    }
+}
+
+// Stage 0 on the reachable odd columns (the reference's stride reaches them only behind a row's first non-skipping
+// window: ~16 % of the odd columns at 1080p, as ragged row suffixes).  Persistent warps pull 32-window runs from the
+// list k_row_events built, so the work is proportional to the windows, not to the tiles they are scattered over: the
+// tile kernel spent 0.074 ms/frame here on tiles holding two or three reachable rows.  Same arithmetic and decisions as
+// k_scan_stage0<FAST = true>: prefilter, certified fast filter, exact re-evaluation of what it leaves undecided.
+template <int HP>
+__global__ void __launch_bounds__(256, SC_STAGE0_MIN_CTAS) k_scan_odd(const __grid_constant__ ScFastParams fp, const ScPlan* __restrict__ plan, const float4* __restrict__ S,
+                                                                      const ScGeom* __restrict__ geom_all, const float* __restrict__ w_all,
+                                                                      const double* __restrict__ wb_all, uint32_t* __restrict__ multi_bits,
+                                                                      uint32_t* __restrict__ pass_bits, ScRecord* __restrict__ rec,
+                                                                      uint32_t* __restrict__ rec_count, uint32_t rec_cap, const int* __restrict__ start_odd,
+                                                                      const uint32_t* __restrict__ chunk_list, const uint32_t* __restrict__ chunk_count,
+                                                                      uint32_t* __restrict__ cursor) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_chunks = *chunk_count;
+    const int rows = plan->rows_per_frame, n_stages = plan->n_stages, total_weak = plan->total_weak;
+    const bool use_pf = plan->use_prefilter != 0;
+    const float theta0 = plan->theta[0];
+    constexpr int ppitch = 2 * HP;
+    for (;;) {
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(cursor, 1u);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= n_chunks) break;
+        const uint32_t e = chunk_list[c];
+        const int t = (int)(e >> 10), k = (int)(e & 1023u);
+        const int f = t / rows, r = t - f * rows;
+        int si = 0;
+        while (si + 1 < plan->n_scales && plan->sc[si + 1].row_base <= r) si++;
+        const ScScale* sc = &plan->sc[si];
+        const int gy = r - sc->row_base, nx = sc->nx;
+        const int gx = start_odd[t] + 2 * (32 * k + lane);
+        const bool valid = gx < nx;
+        const int j = gx >> 1;
+        const char* base = reinterpret_cast<const char*>(S + (size_t)f * plan->lay.frame4 + (gy * ppitch + SC_COL(j)));
+        uint32_t* mw = multi_bits + (size_t)f * plan->words_per_frame + sc->word_base + (size_t)gy * sc->wpr + (gx >> 5);
+        uint32_t* pw = pass_bits + (size_t)f * plan->words_per_frame + sc->word_base + (size_t)gy * sc->wpr + (gx >> 5);
+        const uint32_t bit = 1u << (gx & 31);
+        bool pass = false;
+        if (valid) {
+            pass = use_pf ? (window_sum(base, sc->pf[1]) > sc->thr) : true;
+            if (pass) atomicOr(pw, bit);
+            else atomicOr(mw, bit);  // prefilter failed -> multi = 2 (ObjDetector.cpp:216-217)
+        }
+        bool exact = false;
+        if (pass) {
+            float sum = 0.f;
+#pragma unroll 1
+            for (int q = 0; q < fp.n_weak; q++) {
+                ScGeom g;
+#pragma unroll
+                for (int i = 0; i < 10; i++) g.c[i] = fp.geom[si][q][i];
+                g.shape = (int)fp.geom[si][q][10]; g.pad = 0;
+                float v[32];
+                box_sums_p<HP>(base, g, HP, v);
+                sum = __fadd_rn(sum, fast_tail(v, fp.w[q], fp.wb[q]));
+            }
+            if (sum < fp.lim_reject && sum < fp.lim_skip) atomicOr(mw, bit);
+            else exact = !(sum < fp.lim_reject && sum >= fp.lim_noskip);
+        }
+        bool push = false;
+        ScRecord rc;
+        rc.fs = 0; rc.yx = 0; rc.rej = 0; rc.score = 0;
+        if (exact) {  // rare: the reference's arithmetic decides (weights from global memory)
+            const float score = stage_score<HP>(base, geom_all + ((size_t)plan->n_scales + si) * total_weak, w_all, wb_all, fp.n_weak, HP);
+            const bool rejected = score < theta0;
+            if (rejected && rejected_skips(score, 0, n_stages)) atomicOr(mw, bit);
+            push = !rejected;
+            rc.fs = ((uint32_t)f << 8) | (uint32_t)si;
+            rc.yx = ((uint32_t)gy << 16) | (uint32_t)gx;
+            rc.rej = rejected ? 0 : (n_stages == 1 ? 1 : -1);
+            rc.score = __float_as_uint(score);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, push);
+        if (m) {
+            uint32_t slot0 = 0;
+            if (lane == 0) slot0 = atomicAdd(rec_count, __popc(m));
+            slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+            if (push) {
+                const uint32_t slot = slot0 + __popc(m & ((1u << lane) - 1u));
+                if (slot < rec_cap) rec[slot] = rc;
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -666,7 +771,7 @@ __global__ void __launch_bounds__(128) k_scan_stage(const ScPlan* __restrict__ p
             const int f = r.fs >> 8, si = r.fs & 0xff;
             const int gy = r.yx >> 16, gx = r.yx & 0xffff;
             const float4* lo4 = S + (size_t)f * plan->lay.frame4;
-            const float score = stage_score<HP>(reinterpret_cast<const char*>(lo4 + (gy * ppitch + (gx >> 1))),
+            const float score = stage_score<HP>(reinterpret_cast<const char*>(lo4 + (gy * ppitch + SC_COL(gx >> 1))),
                                                 geom_all + ((size_t)(gx & 1) * plan->n_scales + si) * total_weak + wbase, sw, swb, n_weak, HP);
             if (r.rej < 0) {
                 const bool rejected = score < theta;
@@ -809,9 +914,9 @@ __global__ void k_features(const float4* __restrict__ S, const ScLayout L, const
     if (i >= n) return;
     const int4 r = rects[i];  // x, y, w, h
     const int pitch = L.ppitch;
-    const char* base = reinterpret_cast<const char*>(S + ((size_t)r.y * pitch + r.x));
+    const char* base = reinterpret_cast<const char*>(S + ((size_t)r.y * pitch + SC_COL(r.x)));
     if (sums) {
-        const uint32_t pf[4] = {0u, 16u * r.z, 16u * (uint32_t)(r.w * pitch), 16u * (uint32_t)(r.w * pitch + r.z)};
+        const uint32_t pf[4] = {0u, 16u * SC_COL(r.z), 16u * (uint32_t)(r.w * pitch), 16u * (uint32_t)(r.w * pitch + SC_COL(r.z))};
         sums[i] = window_sum(base, pf);
     }
     if (out) {
@@ -821,11 +926,11 @@ __global__ void k_features(const float4* __restrict__ S, const ScLayout L, const
             const int ce = r.z / 2;
             g.shape = 0;
             for (int b = 0; b < 3; b++)
-                for (int a = 0; a < 3; a++) g.c[3 * b + a] = 16u * (uint32_t)(b * ce * pitch + a * ce);
+                for (int a = 0; a < 3; a++) g.c[3 * b + a] = 16u * (uint32_t)(b * ce * pitch + SC_COL(a * ce));
             g.c[9] = 0;
         } else {
             const int ce = min(r.z, r.w);
-            const int along = r.z > r.w ? ce : ce * pitch, across = r.z > r.w ? ce * pitch : ce;
+            const int along = r.z > r.w ? SC_COL(ce) : ce * pitch, across = r.z > r.w ? ce * pitch : SC_COL(ce);
             g.shape = 1;
             for (int k = 0; k < 5; k++) { g.c[k] = 16u * (uint32_t)(k * along); g.c[5 + k] = 16u * (uint32_t)(k * along + across); }
         }
@@ -841,7 +946,7 @@ __global__ void k_stage_scores(const ScPlan* __restrict__ plan, const float4* __
     // geom_win: [n][total_weak] geometry projected for each explicit window's side (host-built, layout step 1)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const char* base = reinterpret_cast<const char*>(S + ((size_t)wins[3 * i + 1] * plan->lay.ppitch + wins[3 * i]));
+    const char* base = reinterpret_cast<const char*>(S + ((size_t)wins[3 * i + 1] * plan->lay.ppitch + SC_COL(wins[3 * i])));
     for (int s = 0; s < plan->n_stages; s++) {
         const int wb = plan->weak_base[s];
         out[(size_t)i * plan->n_stages + s] = stage_score<0>(base, geom_win + (size_t)i * plan->total_weak + wb, w_all + (size_t)wb * SC_W_PITCH,
@@ -856,7 +961,7 @@ __global__ void k_stage0_fast_check(const ScPlan* __restrict__ plan, const float
                                     float* __restrict__ fast_sum, float* __restrict__ exact_sum) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const char* base = reinterpret_cast<const char*>(S + ((size_t)wins[3 * i + 1] * plan->lay.ppitch + wins[3 * i]));
+    const char* base = reinterpret_cast<const char*>(S + ((size_t)wins[3 * i + 1] * plan->lay.ppitch + SC_COL(wins[3 * i])));
     float fs = 0.f, es = 0.f;
     for (int q = 0; q < plan->n_weak[0]; q++) {
         const ScGeom g = geom_win[(size_t)i * plan->total_weak + q];
@@ -915,19 +1020,20 @@ __global__ void __launch_bounds__(256) k_probe_gather(const float4* __restrict__
 // Measurement probe (no product role): coalesced 16-byte loads (512 contiguous bytes per warp, as one corner fetch of the
 // scan in the half-split layout) streaming over an L2-resident table; mode 0 = ld.global.cg (L2 only), 1 = ld.global.nc
 // (allocates in L1).  Establishes the L2 -> SM bandwidth ceiling the scan's sector traffic is set against.
+template <int U>
 __global__ void __launch_bounds__(256) k_probe_stream(const float4* __restrict__ table, uint32_t n4, int per_thread, int mode, float* __restrict__ sink) {
     float acc = 0.f;
     uint32_t pos = (uint32_t)(((unsigned long long)blockIdx.x * per_thread * 256u) % n4) + threadIdx.x;
-    for (int i = 0; i < per_thread; i += 4) {
-        float4 v[4];
+    for (int i = 0; i < per_thread; i += U) {
+        float4 v[U];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < U; k++) {
             uint32_t p = pos + (uint32_t)(i + k) * 256u;
             p = p >= n4 ? p % n4 : p;
             v[k] = mode ? __ldg(table + p) : __ldcg(table + p);
         }
 #pragma unroll
-        for (int k = 0; k < 4; k++) acc += v[k].x + v[k].w;
+        for (int k = 0; k < U; k++) acc += v[k].x + v[k].w;
     }
     if (acc == 123.456f) sink[0] = acc;
 }

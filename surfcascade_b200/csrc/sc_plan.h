@@ -40,6 +40,19 @@
 //   The two halves of a plane are interleaved row by row at a power-of-two distance hp: a plane row is
 //   [hp float4: channels 0-3][hp float4: channels 4-7], so the second 16-byte load of a corner is the first one's
 //   address plus a compile-time constant (the scan kernels are instantiated per hp) and costs no address arithmetic.
+//   SC_PAIRED=1 (option; measured equal to the default on C2, 0.355 vs 0.351 ms/frame in stage 0): the two halves of a pixel are adjacent instead (32 contiguous bytes per pixel inside the
+//   plane row), so one corner is ONE 256-bit load (LDG.E.256 on sm_100a): a warp's corner fetch is 1024 contiguous
+//   bytes = 8-9 L1 wavefronts instead of 2 x 5-6 for the two 512-byte half loads, and half the load instructions.
+#ifndef SC_PAIRED
+#define SC_PAIRED 0
+#endif
+#if SC_PAIRED
+#define SC_COL(x) (2 * (x))      // float4 index of plane column x inside a plane row
+#define SC_HI(hp) 1              // float4 distance from a pixel's channels 0-3 to its channels 4-7
+#else
+#define SC_COL(x) (x)
+#define SC_HI(hp) (hp)
+#endif
 struct ScLayout {
     int sx, sy;            // column / row deinterleave factors
     int hp;                // float4 elements per half-row: power of two >= ceil((W+1)/sx), one of 256..4096
@@ -132,7 +145,7 @@ enum { SC_CNT_VISITED = 0, SC_CNT_PREFILTER = 1, SC_CNT_RAW = 2, SC_CNT_EVALODD 
 // layout index (float4 units, low half) of integral pixel (X, Y)
 SC_HD long long sc_layout_index(const ScLayout& L, int X, int Y) {
     const int px = X / L.sx, rx = X - px * L.sx, py = Y / L.sy, ry = Y - py * L.sy;
-    return (long long)(ry * L.sx + rx) * L.plane4 + (long long)py * L.ppitch + px;
+    return (long long)(ry * L.sx + rx) * L.plane4 + (long long)py * L.ppitch + SC_COL(px);
 }
 
 #endif
