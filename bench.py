@@ -241,21 +241,42 @@ def run_ours(args):
     stats = h.kernel_stats(reset=True)
     h.set_profiling(False)
 
-    # e2e: host buffers through sc_detect (H2D and D2H inside the timed region), wall clock bracketed by syncs
+    # e2e: host buffers through the C-ABI (H2D and D2H of every step inside the timed region), wall clock bracketed by syncs.
+    # The steps go through sc_detect_submit / sc_detect_collect with two batches in flight, as a streaming caller would:
+    # every step still uploads its own frames from pinned host memory and downloads its own detections and counters.
+    def ptrs_of(s):
+        x = host_sets[s % n_sets]
+        return (ctypes.c_void_p * B)(*[x.data_ptr() + i * W * H for i in range(B)])
+
     for s in range(min(args.warmup, 2)):
         step_host(s)
     barrier()
     t0 = time.perf_counter()
     nd = 0
+    keep = [ptrs_of(0)]
+    pending = h.detect_submit(keep[0], B, W, H, W, prm, cap)
     for s in range(args.steps):
-        nd += len(step_host(s))
+        nxt = None
+        if s + 1 < args.steps:
+            keep.append(ptrs_of(s + 1))
+            nxt = h.detect_submit(keep[-1], B, W, H, W, prm, cap)
+        dets, _ = h.detect_collect(pending, B, cap)
+        nd += len(dets)
+        pending = nxt
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    # the plain synchronous call, one batch at a time, for comparison
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step_host(s)
+    torch.cuda.synchronize()
+    e2e_sync_s = time.perf_counter() - t0
     if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        t = torch.tensor([e2e_s, e2e_sync_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+        e2e_s, e2e_sync_s = float(t[0].item()), float(t[1].item())
     e2e_fps = world * B * args.steps / e2e_s
+    e2e_sync_fps = world * B * args.steps / e2e_sync_s
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -265,7 +286,9 @@ def run_ours(args):
         mean = lambda f: float(np.mean([f(x) for x in cnts]))
         # algorithmic gather bytes of the scan per frame: 32 B x (4 per prefilter + 9|10 corners per weak eval)
         # evaluated on the grid windows this implementation scores (prefilter on every grid window)
-        st0_ms, st0_n = stats.get("k_scan_stage0", (0.0, 0))
+        ev_ms, ev_n = stats.get("k_scan_stage0", (0.0, 0))       # even lattice columns, one launch per 8-frame scan group
+        odd_ms, _ = stats.get("k_scan_stage0_odd", (0.0, 0))      # reachable odd columns
+        st0_ms = ev_ms + odd_ms
         walk_ms, walk_n = stats.get("k_integral_walk", (0.0, 0))
         carry_ms, _ = stats.get("k_strip_carry", (0.0, 0))
         total_k_ms = sum(v[0] for v in stats.values()) or 1.0
@@ -277,17 +300,21 @@ def run_ours(args):
         scan_gbs = alg_scan_bytes * frames_timed / (st0_ms / 1e3) / 1e9 if st0_ms else None
         alg_int_bytes = W * H + 32.0 * (W + 1) * (H + 1)
         int_gbs = alg_int_bytes * frames_timed / ((walk_ms + carry_ms) / 1e3) / 1e9 if walk_ms else None
-        traffic_scan = traffic_int = None
-        try:  # DRAM bytes per launch from the committed ncu --set full capture (profiles/), 8 frames per launch
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["dram_bytes_per_launch"]
-            traffic_scan = tj["k_scan_stage0_phase0"] + tj["k_scan_stage0_phase1"]
-            traffic_int = tj["k_integral_walk"]
+        traffic_scan = traffic_int = l2_bytes_ev = None
+        group = 8  # frames per scan-group launch, the unit the ncu capture in profiles/ was taken on
+        try:  # per-launch DRAM and L2->L1 bytes from the committed ncu --set full capture (profiles/), 8 frames per launch
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            traffic_scan = tj["dram_bytes_per_launch"]["k_scan_stage0_even"]
+            traffic_int = tj["dram_bytes_per_launch"]["k_integral_walk"]
+            l2_bytes_ev = tj["l2_to_l1_bytes_per_launch"]["k_scan_stage0_even"]
         except Exception:
             pass
-        try:
-            l2_peak = h.probe_gather(64 << 20, 5)
+        try:  # L2 -> SM ceiling measured live: coalesced 16-byte loads streaming over an L2-resident 32 MB table
+            l2_peak = max(h.probe_stream(32 << 20, 5, m) for m in (1, 3))
         except Exception:
             l2_peak = None
+        ev_launch_ms = ev_ms / ev_n if ev_n else None
+        l2_meas_gbs = (l2_bytes_ev / (ev_launch_ms / 1e3) / 1e9) if (l2_bytes_ev and ev_launch_ms and B % group == 0) else None
         cpu = None
         if world == 1:
             try:
@@ -309,16 +336,22 @@ def run_ours(args):
             "windows_per_s": {"grid": fps * grid, "reference_visited": fps * mean(lambda x: x.visited)},
             "work_per_frame": {"grid_windows": grid, "visited": mean(lambda x: x.visited), "prefilter_pass": mean(lambda x: x.prefilter_pass),
                                "weak_evals_reference": weak_ref, "raw_detections": mean(lambda x: x.raw)},
-            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": B * W * H, "d2h_bytes_per_step": int(24 * nd / max(args.steps, 1)) + B * 19 * 8 + 4},
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": B * W * H,
+                    "d2h_bytes_per_step": 24 * min(cap, 16384) + B * 20 * 8 + 4,
+                    "api": "sc_detect_submit / sc_detect_collect, two batches in flight (pinned host frames in, sorted detections + counters out)",
+                    "synchronous_sc_detect": e2e_sync_fps},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"kernel": "k_scan_stage0", "bound": "hbm", "achieved": scan_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": (scan_gbs / peak) if scan_gbs else None, "traffic": traffic_scan,
-                         "traffic_note": "dram__bytes_read+write of the two k_scan_stage0 launches (even, odd columns) of one 8-frame scan group, ncu --set full, profiles/r1_traffic.json",
-                         "algorithmic_bytes_per_launch": alg_scan_bytes * 8,
-                         "note": "algorithmic gather bytes = 32 B x (4 x reference-visited windows + 10 x reference weak evaluations) over the kernel's CUDA-event time (both parity launches); the gather is served by L1/L2, not HBM, so this is a cache-resident rate set against the HBM copy peak (" + peak_src + "); the kernel is co-limited by issue slots and the L1 data pipe (ncu: 67 % / 66 %), see DESIGN.md",
-                         "share_of_step": st0_ms / total_k_ms,
-                         "l2_sector_gather_peak_gbs": l2_peak, "frac_of_l2_sector_gather_peak": (scan_gbs / l2_peak) if (scan_gbs and l2_peak) else None},
+            "roofline": {"kernel": "k_scan_stage0 (even columns) + k_scan_odd (reachable odd columns)", "bound": "l2",
+                         "achieved": scan_gbs, "peak": l2_peak, "unit": "GB/s", "frac": (scan_gbs / l2_peak) if (scan_gbs and l2_peak) else None,
+                         "traffic": traffic_scan,
+                         "traffic_note": "dram__bytes_read+write of one k_scan_stage0 launch (even columns of an 8-frame scan group), ncu --set full, profiles/r1_traffic.json: the integral images are read from HBM about once, everything else is cache traffic",
+                         "algorithmic_bytes_per_launch": alg_scan_bytes * group,
+                         "l2_to_l1_bytes_per_launch": l2_bytes_ev, "l2_to_l1_achieved_gbs": l2_meas_gbs,
+                         "l2_to_l1_frac_of_peak": (l2_meas_gbs / l2_peak) if (l2_meas_gbs and l2_peak) else None,
+                         "hbm_peak": peak, "achieved_over_hbm_peak": (scan_gbs / peak) if scan_gbs else None,
+                         "note": "gather-bound scan (SURVEY.md 8d): `achieved` = algorithmic corner bytes 32 B x (4 x reference-visited windows + 10 x reference weak evaluations) per frame / CUDA-event time of both stage-0 kernels; they are served by L1 (~18 % hits) and L2, not HBM (" + peak_src + " is given for scale only), so `peak` is the L2 -> SM bandwidth measured live in this run by sc_probe_stream (coalesced 16-byte loads over an L2-resident table). `l2_to_l1_*` = the sectors L2 actually delivered to the SMs in the even-column launch (ncu l1tex__m_xbar2l1tex_read_bytes, profiles/) / that launch's live duration: the kernel runs at the L2 -> SM ceiling (ncu: L1TEX data pipe 81 %, LTS 67 %, issue 51 %), see DESIGN.md section 6",
+                         "share_of_step": st0_ms / total_k_ms},
             "roofline_integral": {"kernel": "k_strip_carry+k_integral_walk", "bound": "hbm", "achieved": int_gbs, "peak": peak, "unit": "GB/s",
                                   "frac": (int_gbs / peak) if int_gbs else None, "traffic": traffic_int,
                                   "traffic_note": "dram bytes of one 8-frame k_integral_walk launch (ncu); bench launches cover 32 frames",

@@ -144,6 +144,13 @@ int sc_pool_auc_device(sc_handle* h, const uint32_t* d_hist, int P, int64_t n_po
  * counters may be null or point at nframes entries. */
 int sc_detect(sc_handle* h, const uint8_t* const* frames, int nframes, int W, int H, int stride,
               const sc_detect_params* params, sc_detection* out, size_t cap, size_t* n, sc_counters* counters);
+/* The same call split in two so that batches pipeline: submit enqueues upload + path + download of one batch and
+ * returns a ticket (0 or 1) without waiting; collect waits for that batch and hands out what sc_detect would have.
+ * Two batches may be in flight: the upload of batch k+1 and the download / sorting of batch k-1 then run under the
+ * compute of batch k.  Host frame buffers must stay valid (and should be pinned) until the batch is collected. */
+int sc_detect_submit(sc_handle* h, const uint8_t* const* frames, int nframes, int W, int H, int stride,
+                     const sc_detect_params* params, size_t cap, int* ticket);
+int sc_detect_collect(sc_handle* h, int ticket, sc_detection* out, size_t cap, size_t* n, sc_counters* counters);
 /* Same work on frames already resident in DEVICE memory (d_frames: nframes x H x W contiguous u8), detections
  * left on the device, unsorted, in d_out (cap entries) with the count in *d_n (uint32).  Asynchronous on the
  * handle's stream; sc_sync waits.  counters (host, nframes entries or null) are valid after sc_sync. */

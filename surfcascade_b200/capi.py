@@ -43,7 +43,7 @@ EXPORTS = ["sc_create", "sc_destroy", "sc_last_error", "sc_version", "sc_set_cas
            "sc_integral", "sc_features", "sc_window_sum", "sc_stage_scores", "sc_weak_predict", "sc_stage_predict", "sc_detect",
            "sc_detect_device", "sc_sync", "sc_last_counters", "sc_stream", "sc_launch_count", "sc_group_rectangles",
            "sc_set_profiling", "sc_kernel_stats", "sc_model_flatten", "sc_model_resave", "sc_pool_eval", "sc_pool_hist_device",
-           "sc_pool_auc_device", "sc_probe_gather", "sc_probe_stream", "sc_stage0_fast_check"]
+           "sc_pool_auc_device", "sc_probe_gather", "sc_probe_stream", "sc_stage0_fast_check", "sc_detect_submit", "sc_detect_collect"]
 
 _lib = None
 
@@ -300,6 +300,26 @@ class Handle:
         if rc == SC_ERR_CAPACITY:
             return self.detect_ptrs(ptrs, n, w, h, stride, prm, int(found.value) + 16)
         self._check(rc)
+        return out[:found.value].copy(), list(cnt)
+
+    def detect_submit(self, ptrs, n: int, w: int, h: int, stride: int, prm: DetectParams | None = None, cap: int = 1 << 20) -> int:
+        """Enqueue one batch (host frame pointers, kept valid until collected); returns a ticket.  Two may be in flight."""
+        prm = prm or params()
+        L = lib()
+        L.sc_detect_submit.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(DetectParams), C.c_size_t,
+                                       C.POINTER(C.c_int)]
+        t = C.c_int(-1)
+        self._check(L.sc_detect_submit(self._h, ptrs, n, w, h, stride, C.byref(prm), cap, C.byref(t)))
+        return t.value
+
+    def detect_collect(self, ticket: int, n: int, cap: int = 1 << 20):
+        """Wait for a submitted batch of n frames: (detections, [Counters])."""
+        L = lib()
+        L.sc_detect_collect.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p]
+        out = np.empty(cap, DETECTION_DTYPE)
+        cnt = (Counters * n)()
+        found = C.c_size_t(0)
+        self._check(L.sc_detect_collect(self._h, ticket, out.ctypes.data, cap, C.byref(found), C.byref(cnt)))
         return out[:found.value].copy(), list(cnt)
 
     def detect_device(self, d_frames_ptr: int, n: int, w: int, h: int, d_out_ptr: int, cap: int, d_count_ptr: int, prm: DetectParams | None = None):

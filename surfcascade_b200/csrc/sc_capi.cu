@@ -103,6 +103,17 @@ struct sc_handle {
     HostBuf h_stage;
     std::vector<sc_counters> last_counters;
     int last_nframes = 0;
+    // sc_detect_submit / sc_detect_collect: two batches in flight, so the upload of batch k+1 and the download / host work
+    // of batch k-1 hide under the compute of batch k (the compute itself is serialised by the shared integral buffers)
+    struct Ticket {
+        bool busy = false;
+        int nframes = 0;
+        uint32_t det_cap = 0, eager = 0;
+        DevBuf d_img, d_det, d_cnt, d_counters;
+        HostBuf h_out;  // [counters | count | first `eager` detections]
+        cudaEvent_t done = nullptr;
+    };
+    Ticket tickets[2];
 
     // single-frame state for the parity hooks
     bool have_integral = false;
@@ -476,7 +487,7 @@ int run_group(sc_handle* h, sc_handle::Lane& L, int s0, int g, int frame0, sc_de
 // so the upload and the integral of chunk c+1 run under the scan of chunk c.
 #define SC_ICHUNK 16   // measured: 8-frame chunks lose more in the integral kernel than the upload overlap gains
 int run_supergroup(sc_handle* h, const uint8_t* const* frames, int stride, const uint8_t* d_frames, int ni, int frame0, sc_detection* d_det,
-                   uint32_t det_cap, uint32_t* d_det_count, unsigned long long* d_counters) {
+                   uint32_t det_cap, uint32_t* d_det_count, unsigned long long* d_counters, uint8_t* img_buf = nullptr, bool img_buf_busy = true) {
     const ScPlan& p = h->plan;
     const int lanes = h->profiling ? 1 : h->n_lanes;  // per-kernel event timing wants the kernels back to back
     // device-resident frames: one integral launch over the whole super-group is fastest (nothing to overlap it with
@@ -489,17 +500,18 @@ int run_supergroup(sc_handle* h, const uint8_t* const* frames, int stride, const
         h->ev_chunk.push_back(e);
     }
     if (frames && !h->copy_st) SC_CUDA(h, cudaStreamCreateWithFlags(&h->copy_st, cudaStreamNonBlocking));
-    if (frames) {
+    if (frames && img_buf_busy) {
         // the image buffer may still be read by the previous super-group's integral: order the copies after it
         SC_CUDA(h, cudaEventRecord(h->ev_integral, h->stream));
         SC_CUDA(h, cudaStreamWaitEvent(h->copy_st, h->ev_integral, 0));
     }
+    uint8_t* const up = img_buf ? img_buf : h->d_img.as<uint8_t>();
     for (int c = 0; c < nch; c++) {
         const int c0 = c * ich, n = std::min(ich, ni - c0);
-        const uint8_t* img = d_frames ? d_frames + (size_t)c0 * p.W * p.H : h->d_img.as<uint8_t>() + (size_t)c0 * p.W * p.H;
+        const uint8_t* img = d_frames ? d_frames + (size_t)c0 * p.W * p.H : up + (size_t)c0 * p.W * p.H;
         if (frames) {
             for (int k = 0; k < n; k++)
-                SC_CUDA(h, cudaMemcpy2DAsync(h->d_img.as<uint8_t>() + (size_t)(c0 + k) * p.W * p.H, p.W, frames[c0 + k], stride, p.W, p.H,
+                SC_CUDA(h, cudaMemcpy2DAsync(up + (size_t)(c0 + k) * p.W * p.H, p.W, frames[c0 + k], stride, p.W, p.H,
                                              cudaMemcpyHostToDevice, h->copy_st));
             SC_CUDA(h, cudaEventRecord(h->ev_chunk[2 * c], h->copy_st));
             SC_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[2 * c], 0));
@@ -611,6 +623,10 @@ void sc_destroy(sc_handle* h) {
         for (DevBuf* b : lb) b->release();
     }
     if (h->ev_integral) cudaEventDestroy(h->ev_integral);
+    for (auto& t : h->tickets) {
+        if (t.done) cudaEventDestroy(t.done);
+        t.d_img.release(); t.d_det.release(); t.d_cnt.release(); t.d_counters.release(); t.h_out.release();
+    }
     for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
     if (h->copy_st) { cudaStreamSynchronize(h->copy_st); cudaStreamDestroy(h->copy_st); }
     DevBuf* bufs[] = {&h->d_w, &h->d_wb, &h->d_plan, &h->d_geom, &h->d_img, &h->d_carry, &h->d_S, &h->d_counters, &h->d_det, &h->d_detcount, &h->d_pool_w, &h->d_pool_wb, &h->d_pool_auc, &h->d_pool_x, &h->d_pool_aux, &h->d_hook_img, &h->d_hook_carry, &h->d_hook_S};
@@ -1022,14 +1038,15 @@ int sc_probe_stream(sc_handle* h, size_t table_bytes, int iters, int mode, doubl
     SC_CUDA(h, tab.ensure(table_bytes));
     SC_CUDA(h, sink.ensure(256));
     SC_CUDA(h, cudaMemsetAsync(tab.p, 0, table_bytes, h->stream));
-    const uint32_t n4 = (uint32_t)std::min<size_t>(table_bytes / 16, 0x3fffffffu);
+    uint32_t n4 = 1u << 16;
+    while ((size_t)n4 * 2 * 16 <= table_bytes && n4 < (1u << 29)) n4 *= 2;  // largest power of two that fits
     // mode bit 0: 0 = ld.global.cg, 1 = ld.global.nc; bits 1..: independent loads in flight per thread (0 -> 4, 1 -> 8, 2 -> 16)
-    const int per_thread = 64, grid = h->n_sms * 32, unroll = mode >> 1;
+    const int per_thread = 256, grid = h->n_sms * 16, unroll = mode >> 1;
     mode &= 1;
     auto launch = [&]() {
-        if (unroll == 2) sck::k_probe_stream<16><<<grid, 256, 0, h->stream>>>(tab.as<float4>(), n4, per_thread, mode, sink.as<float>());
-        else if (unroll == 1) sck::k_probe_stream<8><<<grid, 256, 0, h->stream>>>(tab.as<float4>(), n4, per_thread, mode, sink.as<float>());
-        else sck::k_probe_stream<4><<<grid, 256, 0, h->stream>>>(tab.as<float4>(), n4, per_thread, mode, sink.as<float>());
+        if (unroll == 2) sck::k_probe_stream<16><<<grid, 256, 0, h->stream>>>(tab.as<float4>(), n4 - 1, per_thread, mode, sink.as<float>());
+        else if (unroll == 1) sck::k_probe_stream<8><<<grid, 256, 0, h->stream>>>(tab.as<float4>(), n4 - 1, per_thread, mode, sink.as<float>());
+        else sck::k_probe_stream<4><<<grid, 256, 0, h->stream>>>(tab.as<float4>(), n4 - 1, per_thread, mode, sink.as<float>());
     };
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
@@ -1069,46 +1086,92 @@ int sc_last_counters(sc_handle* h, sc_counters* counters, int nframes) {
     return SC_OK;
 }
 
-int sc_detect(sc_handle* h, const uint8_t* const* frames, int nframes, int W, int H, int stride, const sc_detect_params* params,
-              sc_detection* out, size_t cap, size_t* n, sc_counters* counters) {
-    if (!h || !frames || nframes < 1 || !n || (cap && !out) || stride < W) return fail(h, SC_ERR_INVALID, "bad arguments");
+#define SC_EAGER_DETS 16384u   // detections downloaded with the counters; more than that costs collect one extra copy
+
+int sc_detect_submit(sc_handle* h, const uint8_t* const* frames, int nframes, int W, int H, int stride, const sc_detect_params* params, size_t cap,
+                     int* ticket) {
+    if (!h || !frames || nframes < 1 || !ticket || stride < W) return fail(h, SC_ERR_INVALID, "bad arguments");
     SC_CUDA(h, cudaSetDevice(h->device));
+    int ti = -1;
+    for (int i = 0; i < 2 && ti < 0; i++)
+        if (!h->tickets[i].busy) ti = i;
+    if (ti < 0) return fail(h, SC_ERR_STATE, "two batches are already in flight: collect one first");
+    const bool other_busy = h->tickets[ti ^ 1].busy;
     const sc_detect_params prm = params ? *params : default_params();
+    const bool same_plan = h->have_plan && h->plan.W == W && h->plan.H == H && same_params(prm, h->pparams);
+    if (other_busy && (!same_plan || nframes > h->int_frames))
+        return fail(h, SC_ERR_STATE, "a batch in flight uses another plan or smaller buffers: collect it first");
     int rc = ensure_plan(h, W, H, prm);
     if (rc != SC_OK) return rc;
-    rc = ensure_group_buffers(h, nframes, true);
+    rc = ensure_group_buffers(h, nframes, false);
     if (rc != SC_OK) return rc;
-    if (h->d_img.cap < (size_t)h->int_frames * W * H) SC_CUDA(h, h->d_img.ensure(align256((size_t)h->int_frames * W * H)));
-    const uint32_t det_cap = (uint32_t)std::min<size_t>(std::max<size_t>(cap, 1), 0xffffffffu);
-    SC_CUDA(h, h->d_det.ensure((size_t)det_cap * sizeof(sc_detection)));
-    SC_CUDA(h, h->d_counters.ensure((size_t)nframes * SC_CNT_STRIDE * 8));
-    SC_CUDA(h, cudaMemsetAsync(h->d_counters.p, 0, (size_t)nframes * SC_CNT_STRIDE * 8, h->stream));
-    SC_CUDA(h, h->d_detcount.ensure(256));
-    uint32_t* d_cnt = h->d_detcount.as<uint32_t>();
-    SC_CUDA(h, cudaMemsetAsync(d_cnt, 0, 4, h->stream));
+    sc_handle::Ticket& t = h->tickets[ti];
+    if (!t.done) SC_CUDA(h, cudaEventCreateWithFlags(&t.done, cudaEventDisableTiming));
+    t.det_cap = (uint32_t)std::min<size_t>(std::max<size_t>(cap, 1), 0xffffffffu);
+    t.eager = std::min(t.det_cap, SC_EAGER_DETS);
+    t.nframes = nframes;
+    const size_t cbytes = (size_t)nframes * SC_CNT_STRIDE * 8;
+    SC_CUDA(h, t.d_img.ensure(align256((size_t)h->int_frames * W * H)));
+    SC_CUDA(h, t.d_det.ensure((size_t)t.det_cap * sizeof(sc_detection)));
+    SC_CUDA(h, t.d_cnt.ensure(256));
+    SC_CUDA(h, t.d_counters.ensure(cbytes));
+    SC_CUDA(h, t.h_out.ensure(cbytes + 16 + (size_t)t.eager * sizeof(sc_detection)));
+    SC_CUDA(h, cudaMemsetAsync(t.d_counters.p, 0, cbytes, h->stream));
+    SC_CUDA(h, cudaMemsetAsync(t.d_cnt.p, 0, 4, h->stream));
     for (int i0 = 0; i0 < nframes; i0 += h->int_frames) {
         const int ni = std::min(h->int_frames, nframes - i0);
-        rc = run_supergroup(h, frames + i0, stride, nullptr, ni, i0, h->d_det.as<sc_detection>(), det_cap, d_cnt,
-                            h->d_counters.as<unsigned long long>() + (size_t)i0 * SC_CNT_STRIDE);
+        // the ticket's image buffer is free when the call starts (its previous batch was collected); later super-groups of
+        // the same call reuse it and must wait for the integral that still reads it
+        rc = run_supergroup(h, frames + i0, stride, nullptr, ni, i0, t.d_det.as<sc_detection>(), t.det_cap, t.d_cnt.as<uint32_t>(),
+                            t.d_counters.as<unsigned long long>() + (size_t)i0 * SC_CNT_STRIDE, t.d_img.as<uint8_t>(), i0 > 0);
         if (rc != SC_OK) return rc;
     }
-    const size_t cbytes = (size_t)nframes * SC_CNT_STRIDE * 8;
-    SC_CUDA(h, h->h_stage.ensure(cbytes + 16));
-    SC_CUDA(h, cudaMemcpyAsync(h->h_stage.p, h->d_counters.p, cbytes, cudaMemcpyDeviceToHost, h->stream));
-    SC_CUDA(h, cudaMemcpyAsync(h->h_stage.as<unsigned char>() + cbytes, d_cnt, 4, cudaMemcpyDeviceToHost, h->stream));
-    SC_CUDA(h, cudaStreamSynchronize(h->stream));
-    drain_spans(h);
-    h->last_nframes = nframes;
+    unsigned char* ho = t.h_out.as<unsigned char>();
+    SC_CUDA(h, cudaMemcpyAsync(ho, t.d_counters.p, cbytes, cudaMemcpyDeviceToHost, h->stream));
+    SC_CUDA(h, cudaMemcpyAsync(ho + cbytes, t.d_cnt.p, 4, cudaMemcpyDeviceToHost, h->stream));
+    SC_CUDA(h, cudaMemcpyAsync(ho + cbytes + 16, t.d_det.p, (size_t)t.eager * sizeof(sc_detection), cudaMemcpyDeviceToHost, h->stream));
+    SC_CUDA(h, cudaEventRecord(t.done, h->stream));
+    t.busy = true;
+    *ticket = ti;
+    return SC_OK;
+}
+
+int sc_detect_collect(sc_handle* h, int ticket, sc_detection* out, size_t cap, size_t* n, sc_counters* counters) {
+    if (!h || ticket < 0 || ticket > 1 || !n || (cap && !out)) return fail(h, SC_ERR_INVALID, "bad arguments");
+    sc_handle::Ticket& t = h->tickets[ticket];
+    if (!t.busy) return fail(h, SC_ERR_STATE, "ticket is not in flight");
+    SC_CUDA(h, cudaSetDevice(h->device));
+    cudaError_t e = cudaEventSynchronize(t.done);
+    t.busy = false;
+    if (e != cudaSuccess) return cuda_fail(h, e, "sc_detect_collect");
+    if (!h->tickets[ticket ^ 1].busy) drain_spans(h);
+    const size_t cbytes = (size_t)t.nframes * SC_CNT_STRIDE * 8;
+    const unsigned char* ho = t.h_out.as<unsigned char>();
     uint32_t found = 0;
-    memcpy(&found, h->h_stage.as<unsigned char>() + cbytes, 4);
-    if (counters) fill_counters(h, h->h_stage.as<unsigned long long>(), nframes, counters);
+    memcpy(&found, ho + cbytes, 4);
+    if (counters) fill_counters(h, reinterpret_cast<const unsigned long long*>(ho), t.nframes, counters);
+    // keep sc_last_counters working for the host path as well
+    SC_CUDA(h, h->h_stage.ensure(cbytes + 16));
+    memcpy(h->h_stage.p, ho, cbytes);
+    h->last_nframes = t.nframes;
     *n = found;
-    if (found > cap) return fail(h, SC_ERR_CAPACITY, "detection buffer too small");
+    if (found > cap || found > t.det_cap) return fail(h, SC_ERR_CAPACITY, "detection buffer too small");
     if (found) {
-        SC_CUDA(h, cudaMemcpy(out, h->d_det.p, (size_t)found * sizeof(sc_detection), cudaMemcpyDeviceToHost));
+        const uint32_t k = std::min(found, t.eager);
+        memcpy(out, ho + cbytes + 16, (size_t)k * sizeof(sc_detection));
+        if (found > k) SC_CUDA(h, cudaMemcpy(out + k, t.d_det.as<sc_detection>() + k, (size_t)(found - k) * sizeof(sc_detection), cudaMemcpyDeviceToHost));
         sort_detections(out, found);
     }
     return SC_OK;
+}
+
+int sc_detect(sc_handle* h, const uint8_t* const* frames, int nframes, int W, int H, int stride, const sc_detect_params* params,
+              sc_detection* out, size_t cap, size_t* n, sc_counters* counters) {
+    if (!h || !frames || nframes < 1 || !n || (cap && !out) || stride < W) return fail(h, SC_ERR_INVALID, "bad arguments");
+    int ticket = -1;
+    int rc = sc_detect_submit(h, frames, nframes, W, H, stride, params, cap, &ticket);
+    if (rc != SC_OK) return rc;
+    return sc_detect_collect(h, ticket, out, cap, n, counters);
 }
 
 int sc_group_rectangles(const sc_rect* rects, const double* scores, int n, int group_threshold, double eps, sc_rect* out_rects,

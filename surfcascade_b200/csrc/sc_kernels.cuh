@@ -1021,15 +1021,15 @@ __global__ void __launch_bounds__(256) k_probe_gather(const float4* __restrict__
 // scan in the half-split layout) streaming over an L2-resident table; mode 0 = ld.global.cg (L2 only), 1 = ld.global.nc
 // (allocates in L1).  Establishes the L2 -> SM bandwidth ceiling the scan's sector traffic is set against.
 template <int U>
-__global__ void __launch_bounds__(256) k_probe_stream(const float4* __restrict__ table, uint32_t n4, int per_thread, int mode, float* __restrict__ sink) {
+__global__ void __launch_bounds__(256) k_probe_stream(const float4* __restrict__ table, uint32_t n4_mask, int per_thread, int mode, float* __restrict__ sink) {
+    // table length is a power of two (n4_mask = length - 1): every CTA streams its own contiguous window, wrapping
     float acc = 0.f;
-    uint32_t pos = (uint32_t)(((unsigned long long)blockIdx.x * per_thread * 256u) % n4) + threadIdx.x;
+    const uint32_t pos = blockIdx.x * (uint32_t)per_thread * 256u + threadIdx.x;
     for (int i = 0; i < per_thread; i += U) {
         float4 v[U];
 #pragma unroll
         for (int k = 0; k < U; k++) {
-            uint32_t p = pos + (uint32_t)(i + k) * 256u;
-            p = p >= n4 ? p % n4 : p;
+            const uint32_t p = (pos + (uint32_t)(i + k) * 256u) & n4_mask;
             v[k] = mode ? __ldg(table + p) : __ldcg(table + p);
         }
 #pragma unroll

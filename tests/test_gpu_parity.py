@@ -167,3 +167,26 @@ def test_group_rectangles_host(gpu_handle, oracle_cascade):
     gr, gs = capi.group_rectangles(rects, dets["score"])
     wr, ws = O.group_rectangles(rects, dets["score"])
     assert np.array_equal(gr, wr) and np.array_equal(gs, ws) and len(gr) > 0
+
+
+def test_submit_collect_pipeline_equals_sync(gpu_handle):
+    """sc_detect_submit / sc_detect_collect with two batches in flight returns what sc_detect returns, batch by batch."""
+    import ctypes
+    batches = [np.ascontiguousarray(np.stack([synth.frame(240, 320, 50 + 3 * b + i) for i in range(3)])) for b in range(5)]
+    want = [gpu_handle.detect(b) for b in batches]
+    ptrs = [(ctypes.c_void_p * 3)(*[b.ctypes.data + i * 240 * 320 for i in range(3)]) for b in batches]
+    got = []
+    pending = gpu_handle.detect_submit(ptrs[0], 3, 320, 240, 320)
+    for k in range(len(batches)):
+        nxt = gpu_handle.detect_submit(ptrs[k + 1], 3, 320, 240, 320) if k + 1 < len(batches) else None
+        got.append(gpu_handle.detect_collect(pending, 3))
+        pending = nxt
+    for (d1, c1), (d2, c2) in zip(want, got):
+        assert d1.tobytes() == d2.tobytes() and len(d1) > 0
+        assert all(bytes(a) == bytes(b) for a, b in zip(c1, c2))
+    # a third submit while two are in flight is refused, not queued
+    a = gpu_handle.detect_submit(ptrs[0], 3, 320, 240, 320)
+    b = gpu_handle.detect_submit(ptrs[1], 3, 320, 240, 320)
+    with pytest.raises(capi.SurfCascadeError):
+        gpu_handle.detect_submit(ptrs[2], 3, 320, 240, 320)
+    gpu_handle.detect_collect(a, 3); gpu_handle.detect_collect(b, 3)
