@@ -59,6 +59,10 @@ typedef struct {
     int32_t prefilter;         /* 6 (ObjDetector.cpp:188); negative disables the prefilter */
     int32_t skip_rule;         /* 1 -> reproduce the adaptive x stride `multi` (ObjDetector.cpp:186,214-217) */
     int32_t force_all_stages;  /* 1 -> no early reject: every stage of every window (stress mode, not in the reference) */
+    /* Single large frames over several GPUs: band_count > 1 restricts the scan to band band_index of
+     * every scale's lattice rows [ny * i / count, ny * (i + 1) / count).  The reference's stride chain never crosses a
+     * row, so the union of the bands' detections and the sum of their counters are the full scan's.  0 / 0 = whole frame. */
+    int32_t band_index, band_count;
 } sc_detect_params;
 
 /* One raw (ungrouped) detection: wins.push_back(win) / scores.push_back(score), ObjDetector.cpp:207-208. */

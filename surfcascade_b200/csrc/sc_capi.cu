@@ -51,7 +51,7 @@ struct HostBuf {
 
 bool same_params(const sc_detect_params& a, const sc_detect_params& b) {
     return a.base == b.base && a.step == b.step && a.scale == b.scale && a.prefilter == b.prefilter && a.skip_rule == b.skip_rule &&
-           a.force_all_stages == b.force_all_stages;
+           a.force_all_stages == b.force_all_stages && a.band_index == b.band_index && a.band_count == b.band_count;
 }
 
 }  // namespace
@@ -193,7 +193,7 @@ void drain_spans(sc_handle* h) {
 
 sc_detect_params default_params() {
     sc_detect_params p;
-    p.base = 40; p.step = 0; p.scale = 1.1; p.prefilter = 6; p.skip_rule = 1; p.force_all_stages = 0;
+    p.base = 40; p.step = 0; p.scale = 1.1; p.prefilter = 6; p.skip_rule = 1; p.force_all_stages = 0; p.band_index = 0; p.band_count = 0;
     return p;
 }
 
@@ -216,6 +216,8 @@ double fast_margin(const sc_handle* h) {
 int build_plan(sc_handle* h, int W, int H, const sc_detect_params& prm, std::vector<ScGeom>* geom_out) {
     if (!h->have_cascade) return fail(h, SC_ERR_STATE, "no cascade loaded (sc_set_cascade / sc_load_model)");
     if (W < 2 || H < 2 || prm.base < 1 || !(prm.scale > 1.0)) return fail(h, SC_ERR_INVALID, "bad frame size or scan parameters");
+    const int bands = prm.band_count > 1 ? prm.band_count : 1, band = bands > 1 ? prm.band_index : 0;
+    if (band < 0 || band >= bands) return fail(h, SC_ERR_INVALID, "band_index outside 0..band_count-1");
     ScPlan& p = h->plan;
     memset(&p, 0, sizeof(p));
     p.W = W; p.H = H;
@@ -239,6 +241,9 @@ int build_plan(sc_handle* h, int W, int H, const sc_detect_params& prm, std::vec
         s.l = l;
         s.nx = (W - l) / p.step + 1; s.ny = (H - l) / p.step + 1;
         if (s.nx > 65535 || s.ny > 65535) return fail(h, SC_ERR_INVALID, "lattice exceeds 65535 positions per axis");
+        // row band of a multi-GPU split: rows [ny * band / bands, ny * (band + 1) / bands) of every scale
+        s.gy0 = (int)((long long)s.ny * band / bands);
+        s.ny = (int)((long long)s.ny * (band + 1) / bands) - s.gy0;
         s.wpr = (s.nx + 31) / 32;
         s.thr = (float)(l * l * (prm.prefilter >= 0 ? prm.prefilter : 0));
         s.tiles_x = ((s.nx + 1) / 2 + SC_TILE_X - 1) / SC_TILE_X;  // tiles of 64 same-parity columns

@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, SC_STAGE0_MIN_CTAS) k_scan_st
     }
     const int n_weak = plan->n_weak[0], total_weak = plan->total_weak;
     constexpr int ppitch = 2 * HP;
-    const float4* lo4 = S + (size_t)f * plan->lay.frame4;
+    const float4* lo4 = S + (size_t)f * plan->lay.frame4 + (size_t)s_sc.gy0 * ppitch;  // lattice row gy0 is row 0 of this plan
     ScGeom* sg = reinterpret_cast<ScGeom*>(s_dyn);                                                          // [n_weak] 48 B each
     float* sw = reinterpret_cast<float*>(s_dyn + (size_t)n_weak * sizeof(ScGeom));                          // [n_weak][36]
     double* swb = reinterpret_cast<double*>(s_dyn + (size_t)n_weak * (sizeof(ScGeom) + SC_W_PITCH * 4));    // [n_weak]
@@ -685,7 +685,7 @@ __global__ void __launch_bounds__(256, SC_STAGE0_MIN_CTAS) k_scan_odd(const __gr
         const int gx = start_odd[t] + 2 * (32 * k + lane);
         const bool valid = gx < nx;
         const int j = gx >> 1;
-        const char* base = reinterpret_cast<const char*>(S + (size_t)f * plan->lay.frame4 + (gy * ppitch + SC_COL(j)));
+        const char* base = reinterpret_cast<const char*>(S + (size_t)f * plan->lay.frame4 + ((gy + sc->gy0) * ppitch + SC_COL(j)));
         uint32_t* mw = multi_bits + (size_t)f * plan->words_per_frame + sc->word_base + (size_t)gy * sc->wpr + (gx >> 5);
         uint32_t* pw = pass_bits + (size_t)f * plan->words_per_frame + sc->word_base + (size_t)gy * sc->wpr + (gx >> 5);
         const uint32_t bit = 1u << (gx & 31);
@@ -771,7 +771,7 @@ __global__ void __launch_bounds__(128) k_scan_stage(const ScPlan* __restrict__ p
             const int f = r.fs >> 8, si = r.fs & 0xff;
             const int gy = r.yx >> 16, gx = r.yx & 0xffff;
             const float4* lo4 = S + (size_t)f * plan->lay.frame4;
-            const float score = stage_score<HP>(reinterpret_cast<const char*>(lo4 + (gy * ppitch + SC_COL(gx >> 1))),
+            const float score = stage_score<HP>(reinterpret_cast<const char*>(lo4 + ((gy + plan->sc[si].gy0) * ppitch + SC_COL(gx >> 1))),
                                                 geom_all + ((size_t)(gx & 1) * plan->n_scales + si) * total_weak + wbase, sw, swb, n_weak, HP);
             if (r.rej < 0) {
                 const bool rejected = score < theta;
@@ -872,13 +872,14 @@ __global__ void __launch_bounds__(128) k_finalize(const ScPlan* __restrict__ pla
     for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < count; i0 += stride) {  // warp-uniform trip count
         const uint32_t i = i0 + threadIdx.x;
         bool vis = false;
-        int f = 0, gx = 0, gy = 0, l = 0, reached = 0;
+        int f = 0, gx = 0, gy = 0, ya = 0, l = 0, reached = 0;
         float score = 0.f;
         if (i < count) {
             const ScRecord r = rec[i];
             f = r.fs >> 8;
             const int si = r.fs & 0xff;
             gy = r.yx >> 16; gx = r.yx & 0xffff; l = plan->sc[si].l;
+            ya = gy + plan->sc[si].gy0;  // absolute lattice row (plans of a row band count rows from gy0)
             const uint32_t v = visited_bits[(size_t)f * plan->words_per_frame + plan->sc[si].word_base + (size_t)gy * plan->sc[si].wpr + (gx >> 5)];
             vis = (v >> (gx & 31)) & 1u;
             reached = r.rej < 0 ? n_stages : r.rej;  // stages 0..min(reached, n_stages-1) were entered
@@ -897,7 +898,7 @@ __global__ void __launch_bounds__(128) k_finalize(const ScPlan* __restrict__ pla
             const uint32_t slot = atomicAdd(det_count, 1u);
             if (slot < det_cap) {
                 ScDetOut d;
-                d.frame = frame0 + f; d.x = gx * plan->step; d.y = gy * plan->step; d.l = l;
+                d.frame = frame0 + f; d.x = gx * plan->step; d.y = ya * plan->step; d.l = l;
                 d.score = ((double)score + (double)n_stages + 1.0) / (double)n_stages;  // ObjDetector.cpp:201
                 det[slot] = d;
             }

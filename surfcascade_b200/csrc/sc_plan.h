@@ -74,7 +74,9 @@ struct ScScale {
     int row_base;     // first lattice row of this scale inside a frame (replay threads)
     uint32_t pf[2][4];  // per column parity: byte offsets of the prefilter corners (0,0) (l,0) (0,l) (l,l) relative to
                         // the window's layout element gy * ppitch + (gx >> 1)
-    int pad[3];
+    int gy0;          // first lattice row of this scale that the plan scans (row band of a multi-GPU split; else 0);
+                      // ny, the bitmasks and the records count rows from gy0
+    int pad[2];
 };
 
 struct ScPlan {

@@ -24,6 +24,18 @@ def to_global_frames(dets: np.ndarray, rank: int, world: int) -> np.ndarray:
     return out
 
 
+def band_rows(ny: int, rank: int, world: int) -> tuple[int, int]:
+    """Lattice rows [y0, y1) of a scale with ny rows that rank `rank` scans when ONE frame is split over `world` GPUs
+    (sc_detect_params.band_index / band_count; the reference's stride chain never crosses a row, ObjDetector.cpp:182-186)."""
+    return ny * rank // world, ny * (rank + 1) // world
+
+
+def band_params(rank: int, world: int, **kw):
+    """Scan parameters of rank `rank` for a single frame split by lattice rows over `world` GPUs."""
+    from . import capi
+    return capi.params(band_index=rank, band_count=world, **kw)
+
+
 def gather_records(buf: torch.Tensor, count: torch.Tensor, group=None) -> tuple[torch.Tensor, torch.Tensor]:
     """All-gather fixed-capacity record buffers and their fill counts.
 
@@ -37,11 +49,13 @@ def gather_records(buf: torch.Tensor, count: torch.Tensor, group=None) -> tuple[
     return torch.stack(bufs), torch.cat(counts)
 
 
-def gather_detections(local: np.ndarray, rank: int, world: int, device: torch.device | None = None, group=None) -> np.ndarray:
+def gather_detections(local: np.ndarray, rank: int, world: int, device: torch.device | None = None, group=None,
+                      renumber: bool = True) -> np.ndarray:
     """Host-level helper: every rank passes its detections (local frame indices); every rank gets all of them with
-    global frame indices, sorted by (frame, l, y, x)."""
+    global frame indices, sorted by (frame, l, y, x).  renumber=False keeps the frame indices (ranks that scanned row
+    bands of the same frames)."""
     device = device or torch.device("cpu")
-    g = to_global_frames(local, rank, world)
+    g = to_global_frames(local, rank, world) if renumber else local
     n = torch.tensor([len(g)], dtype=torch.int32, device=device)
     ns = [torch.empty_like(n) for _ in range(world)]
     dist.all_gather(ns, n, group=group)

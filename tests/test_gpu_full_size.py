@@ -60,3 +60,24 @@ def test_c5_pool_eval_at_scale(gpu_handle):
     auc = gpu_handle.pool_eval(X, labels, W, np.ones(P))
     # all-zero weights give p = 0.5 for every sample: one ROC step from (0,0) to (1,1), area exactly 0.5
     assert (auc[0::3] > 0.9).all() and (auc[1::3] < 0.1).all() and (auc[2::3] == 0.5).all()
+
+
+@pytest.mark.parametrize("bands", [2, 3, 8])
+def test_row_bands_partition_the_scan(gpu_handle, bands):
+    """Multi-GPU split of a single frame: every rank scans one band of each scale's lattice rows.  The union
+    of the bands' detections and the sum of their counters must be the whole-frame scan's, bit for bit."""
+    img = synth.frame(1080, 1920, 77)
+    full, cf = gpu_handle.detect([img])
+    parts, tot = [], dict(grid=0, visited=0, prefilter_pass=0, weak_evals=0, raw=0)
+    for k in range(bands):
+        d, c = gpu_handle.detect([img], capi.params(band_index=k, band_count=bands))
+        parts.append(d)
+        for key in tot:
+            tot[key] += getattr(c[0], key)
+    got = np.sort(np.concatenate(parts), order=["frame", "l", "y", "x"])
+    assert got.tobytes() == full.tobytes() and len(full) > 0
+    assert tot == {key: getattr(cf[0], key) for key in tot}
+    # the bands are disjoint in y per scale
+    for l in np.unique(full["l"]):
+        ys = [set(p[p["l"] == l]["y"].tolist()) for p in parts]
+        assert all(not (ys[a] & ys[b]) for a in range(bands) for b in range(a + 1, bands))

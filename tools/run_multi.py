@@ -1,0 +1,103 @@
+"""BASELINE configs C3 and C4 on N GPUs of one box (one process per GPU, NCCL over NVLink):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/run_multi.py
+
+C3: 1024 1080p frames sharded frame f -> rank f mod N (128-frame device-resident batches), detections gathered to every
+    rank and grouped per frame on rank 0 (host groupRectangles).
+C4: ONE 3840x2160 frame, step 1, all stages forced: every rank computes the integral image itself and scans its band of
+    every scale's lattice rows (sc_detect_params.band_index / band_count); same gather.
+Times are CUDA-event times on the handle's stream, max over ranks.  One JSON line on rank 0."""
+import json, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+from surfcascade_b200 import capi, synth
+from surfcascade_b200 import dist as scdist
+
+world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+json_fd = os.dup(1); os.dup2(2, 1)
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+MODEL = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "model_c1.cfg")
+h = capi.Handle(local); h.load_model(MODEL, 40)
+stream = torch.cuda.ExternalStream(h.stream, device=dev)
+
+
+def max_over_ranks(x):
+    if world == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier():
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+out = {"n_gpus": world}
+# ---- C3 ------------------------------------------------------------------------------------------------------
+n_total = int(os.environ.get("C3_FRAMES", "1024"))
+mine = scdist.shard_frames(n_total, rank, world)
+base = [synth.frame(1080, 1920, 100 + i) for i in range(8)]
+B = 128
+cap = 1 << 18
+d_out = torch.zeros(cap * 24, dtype=torch.uint8, device=dev); d_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+batches = [mine[i:i + B] for i in range(0, len(mine), B)]
+dev_batch = torch.from_numpy(np.stack([base[f % 8] for f in (batches[0] if batches else [0])])).to(dev)   # frame f is synthetic frame f mod 8
+h.detect_device(dev_batch.data_ptr(), dev_batch.shape[0], 1920, 1080, d_out.data_ptr(), cap, d_cnt.data_ptr(), capi.params()); h.sync()  # warm-up
+barrier()
+e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+e0.record(stream)
+gathered = []
+for b in batches:
+    # every batch of this rank holds the same synthetic content pattern (f mod 8 repeats with period 8 | world)
+    h.detect_device(dev_batch.data_ptr(), len(b), 1920, 1080, d_out.data_ptr(), cap, d_cnt.data_ptr(), capi.params())
+    if world > 1:
+        with torch.cuda.stream(stream):
+            gathered.append(scdist.gather_records(d_out[: (1 << 16) * 24], d_cnt))
+e1.record(stream); h.sync(); barrier()
+ms = max_over_ranks(e0.elapsed_time(e1))
+t0 = time.perf_counter()
+n_groups = 0
+if rank == 0:   # host grouping of rank 0's own share (every rank's records are there after the gather; one share timed)
+    n = int(d_cnt.item())
+    rec = np.frombuffer(d_out[: n * 24].cpu().numpy().tobytes(), capi.DETECTION_DTYPE)
+    for f in np.unique(rec["frame"]):
+        r = rec[rec["frame"] == f]
+        gr, _ = capi.group_rectangles(np.stack([r["x"], r["y"], r["l"], r["l"]], 1), r["score"])
+        n_groups += len(gr)
+group_s = time.perf_counter() - t0
+out["C3"] = {"frames": n_total, "ms": round(ms, 2), "frames_per_s": round(n_total / ms * 1e3, 1), "frames_per_rank": len(mine),
+             "host_grouping_ms_last_batch_rank0": round(group_s * 1e3, 2), "objects_last_batch_rank0": n_groups}
+# ---- C4 ------------------------------------------------------------------------------------------------------
+img = torch.from_numpy(synth.frame(2160, 3840, 300, n_objects=12)[None]).to(dev)
+cap4 = 1 << 20
+d_out4 = torch.zeros(cap4 * 24, dtype=torch.uint8, device=dev)
+prm = capi.params(step=1, prefilter=-1, skip_rule=False, force_all_stages=True, band_index=rank, band_count=world)
+h.detect_device(img.data_ptr(), 1, 3840, 2160, d_out4.data_ptr(), cap4, d_cnt.data_ptr(), prm); h.sync()
+barrier()
+e0.record(stream)
+reps = 3
+for _ in range(reps):
+    h.detect_device(img.data_ptr(), 1, 3840, 2160, d_out4.data_ptr(), cap4, d_cnt.data_ptr(), prm)
+    if world > 1:
+        with torch.cuda.stream(stream):
+            scdist.gather_records(d_out4[: (1 << 16) * 24], d_cnt)
+e1.record(stream); h.sync(); barrier()
+ms4 = max_over_ranks(e0.elapsed_time(e1)) / reps
+c = h.last_counters(1)[0]
+tot = torch.tensor([c.grid, int(d_cnt.item())], dtype=torch.int64, device=dev)
+if world > 1:
+    dist.all_reduce(tot)
+out["C4"] = {"ms_per_frame": round(ms4, 2), "windows": int(tot[0].item()), "windows_per_s": round(int(tot[0].item()) / ms4 * 1e3 / 1e9, 3), "unit": "G windows/s",
+             "raw_detections": int(tot[1].item()), "split": f"{world} row bands per scale, integral replicated"}
+if rank == 0:
+    os.write(json_fd, (json.dumps(out) + "\n").encode())
+if world > 1:
+    dist.destroy_process_group()
