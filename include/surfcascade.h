@@ -63,6 +63,13 @@ typedef struct {
      * every scale's lattice rows [ny * i / count, ny * (i + 1) / count).  The reference's stride chain never crosses a
      * row, so the union of the bands' detections and the sum of their counters are the full scan's.  0 / 0 = whole frame. */
     int32_t band_index, band_count;
+    /* group_threshold > 0: sc_detect / sc_detect_collect return GROUPED objects instead of raw windows --
+     * cv::groupRectangles(wins, weights, scores, group_threshold, group_eps) of every frame's raw windows
+     * (ObjDetector.cpp:224-225 uses 2, 0.2), computed on the device: {frame, x, y, l = mean side, score = best raw score},
+     * per frame in the order groupRectangles emits them for the (l, y, x)-sorted window list.  0 = raw windows. */
+    int32_t group_threshold;
+    int32_t reserved;
+    double group_eps;
 } sc_detect_params;
 
 /* One raw (ungrouped) detection: wins.push_back(win) / scores.push_back(score), ObjDetector.cpp:207-208. */

@@ -28,7 +28,8 @@ class CascadeDesc(C.Structure):
 
 class DetectParams(C.Structure):
     _fields_ = [("base", C.c_int32), ("step", C.c_int32), ("scale", C.c_double), ("prefilter", C.c_int32), ("skip_rule", C.c_int32),
-                ("force_all_stages", C.c_int32), ("band_index", C.c_int32), ("band_count", C.c_int32)]
+                ("force_all_stages", C.c_int32), ("band_index", C.c_int32), ("band_count", C.c_int32),
+                ("group_threshold", C.c_int32), ("reserved", C.c_int32), ("group_eps", C.c_double)]
 
 
 class Counters(C.Structure):
@@ -92,9 +93,10 @@ def lib():
     return _lib
 
 
-def params(base=40, step=0, scale=1.1, prefilter=6, skip_rule=True, force_all_stages=False, band_index=0, band_count=0) -> DetectParams:
+def params(base=40, step=0, scale=1.1, prefilter=6, skip_rule=True, force_all_stages=False, band_index=0, band_count=0, group_threshold=0,
+           group_eps=0.2) -> DetectParams:
     """Defaults are BASELINE config 1/2: base 40 -> step 2, scale 1.1, prefilter 6, adaptive stride on."""
-    return DetectParams(base, step, scale, prefilter, int(skip_rule), int(force_all_stages), band_index, band_count)
+    return DetectParams(base, step, scale, prefilter, int(skip_rule), int(force_all_stages), band_index, band_count, group_threshold, 0, group_eps)
 
 
 def counters_to_dict(c: Counters, n_stages: int) -> dict:

@@ -51,7 +51,7 @@ struct HostBuf {
 
 bool same_params(const sc_detect_params& a, const sc_detect_params& b) {
     return a.base == b.base && a.step == b.step && a.scale == b.scale && a.prefilter == b.prefilter && a.skip_rule == b.skip_rule &&
-           a.force_all_stages == b.force_all_stages && a.band_index == b.band_index && a.band_count == b.band_count;
+           a.force_all_stages == b.force_all_stages && a.band_index == b.band_index && a.band_count == b.band_count;  // grouping is not part of the plan
 }
 
 }  // namespace
@@ -109,8 +109,10 @@ struct sc_handle {
         bool busy = false;
         int nframes = 0;
         uint32_t det_cap = 0, eager = 0;
-        DevBuf d_img, d_det, d_cnt, d_counters;
-        HostBuf h_out;  // [counters | count | first `eager` detections]
+        DevBuf d_img, d_det, d_cnt, d_counters, d_grp;  // d_grp: segments, per-frame tables and output of the device grouping
+        HostBuf h_out;  // [counters | count | first `eager` detections]  (grouped: [counters | count, overflow | first `eager` objects])
+        int group_thr = 0;
+        double group_eps = 0.2;
         cudaEvent_t done = nullptr;
     };
     Ticket tickets[2];
@@ -151,9 +153,9 @@ int cuda_fail(sc_handle* h, cudaError_t e, const char* what) {
         if (e_ != cudaSuccess) return cuda_fail((h), e_, #call); \
     } while (0)
 
-enum { K_CARRY = 0, K_WALK, K_STAGE0, K_STAGE, K_REPLAY, K_FINALIZE, K_EVENTS, K_POOL, K_STAGE0_ODD, K_COUNT };
+enum { K_CARRY = 0, K_WALK, K_STAGE0, K_STAGE, K_REPLAY, K_FINALIZE, K_EVENTS, K_POOL, K_STAGE0_ODD, K_GROUP, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"k_strip_carry", "k_integral_walk", "k_scan_stage0", "k_scan_stage", "k_replay_rows", "k_finalize",
-                                            "k_row_events", "k_pool_hist", "k_scan_stage0_odd"};
+                                            "k_row_events", "k_pool_hist", "k_scan_stage0_odd", "k_group_frames"};
 
 cudaEvent_t take_event(sc_handle* h) {
     cudaEvent_t e = nullptr;
@@ -193,7 +195,7 @@ void drain_spans(sc_handle* h) {
 
 sc_detect_params default_params() {
     sc_detect_params p;
-    p.base = 40; p.step = 0; p.scale = 1.1; p.prefilter = 6; p.skip_rule = 1; p.force_all_stages = 0; p.band_index = 0; p.band_count = 0;
+    p.base = 40; p.step = 0; p.scale = 1.1; p.prefilter = 6; p.skip_rule = 1; p.force_all_stages = 0; p.band_index = 0; p.band_count = 0; p.group_threshold = 0; p.reserved = 0; p.group_eps = 0.2;
     return p;
 }
 
@@ -630,7 +632,7 @@ void sc_destroy(sc_handle* h) {
     if (h->ev_integral) cudaEventDestroy(h->ev_integral);
     for (auto& t : h->tickets) {
         if (t.done) cudaEventDestroy(t.done);
-        t.d_img.release(); t.d_det.release(); t.d_cnt.release(); t.d_counters.release(); t.h_out.release();
+        t.d_img.release(); t.d_det.release(); t.d_cnt.release(); t.d_counters.release(); t.d_grp.release(); t.h_out.release();
     }
     for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
     if (h->copy_st) { cudaStreamSynchronize(h->copy_st); cudaStreamDestroy(h->copy_st); }
@@ -1113,6 +1115,7 @@ int sc_detect_submit(sc_handle* h, const uint8_t* const* frames, int nframes, in
     sc_handle::Ticket& t = h->tickets[ti];
     if (!t.done) SC_CUDA(h, cudaEventCreateWithFlags(&t.done, cudaEventDisableTiming));
     t.det_cap = (uint32_t)std::min<size_t>(std::max<size_t>(cap, 1), 0xffffffffu);
+    if (prm.group_threshold > 0) t.det_cap = std::max(t.det_cap, 1u << 16);  // raw windows feed the grouping; `cap` counts objects
     t.eager = std::min(t.det_cap, SC_EAGER_DETS);
     t.nframes = nframes;
     const size_t cbytes = (size_t)nframes * SC_CNT_STRIDE * 8;
@@ -1120,7 +1123,7 @@ int sc_detect_submit(sc_handle* h, const uint8_t* const* frames, int nframes, in
     SC_CUDA(h, t.d_det.ensure((size_t)t.det_cap * sizeof(sc_detection)));
     SC_CUDA(h, t.d_cnt.ensure(256));
     SC_CUDA(h, t.d_counters.ensure(cbytes));
-    SC_CUDA(h, t.h_out.ensure(cbytes + 16 + (size_t)t.eager * sizeof(sc_detection)));
+    SC_CUDA(h, t.h_out.ensure(cbytes + 16 + (size_t)t.eager * sizeof(sck::ScGroupOut)));
     SC_CUDA(h, cudaMemsetAsync(t.d_counters.p, 0, cbytes, h->stream));
     SC_CUDA(h, cudaMemsetAsync(t.d_cnt.p, 0, 4, h->stream));
     for (int i0 = 0; i0 < nframes; i0 += h->int_frames) {
@@ -1133,8 +1136,42 @@ int sc_detect_submit(sc_handle* h, const uint8_t* const* frames, int nframes, in
     }
     unsigned char* ho = t.h_out.as<unsigned char>();
     SC_CUDA(h, cudaMemcpyAsync(ho, t.d_counters.p, cbytes, cudaMemcpyDeviceToHost, h->stream));
-    SC_CUDA(h, cudaMemcpyAsync(ho + cbytes, t.d_cnt.p, 4, cudaMemcpyDeviceToHost, h->stream));
-    SC_CUDA(h, cudaMemcpyAsync(ho + cbytes + 16, t.d_det.p, (size_t)t.eager * sizeof(sc_detection), cudaMemcpyDeviceToHost, h->stream));
+    t.group_thr = prm.group_threshold > 0 ? prm.group_threshold : 0;
+    t.group_eps = prm.group_eps;
+    if (t.group_thr > 0) {
+        // groupRectangles on the device: per-frame segments of the raw windows, one CTA per frame (sc_kernels.cuh)
+        const size_t seg_bytes = align256((size_t)t.det_cap * sizeof(sc_detection));
+        const size_t tab_bytes = align256(((size_t)3 * nframes + 8) * 4);
+        const size_t out_bytes = align256((size_t)t.det_cap * sizeof(sck::ScGroupOut));
+        SC_CUDA(h, t.d_grp.ensure(seg_bytes + tab_bytes + out_bytes));
+        unsigned char* gb = t.d_grp.as<unsigned char>();
+        sck::ScDetOut* seg = reinterpret_cast<sck::ScDetOut*>(gb);
+        uint32_t* per_frame = reinterpret_cast<uint32_t*>(gb + seg_bytes);   // [nframes] counts | [nframes + 1] offsets | [nframes] fill | out_count, overflow
+        uint32_t* offsets = per_frame + nframes;
+        uint32_t* fill = offsets + nframes + 1;
+        uint32_t* flags = fill + nframes;                                    // [0] overflow, [1] out_count
+        sck::ScGroupOut* gout = reinterpret_cast<sck::ScGroupOut*>(gb + seg_bytes + tab_bytes);
+        SC_CUDA(h, cudaMemsetAsync(per_frame, 0, tab_bytes, h->stream));
+        const sck::ScDetOut* det = reinterpret_cast<const sck::ScDetOut*>(t.d_det.p);
+        const size_t gsmem = (size_t)SC_GROUP_MAX * (8 + 8 + 6 * 4);
+        static bool attr_set = false;
+        if (!attr_set) { cudaFuncSetAttribute(sck::k_group_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem); attr_set = true; }
+        {
+            KernelSpan ks(h, K_GROUP);  // the three small table kernels ride in the same span
+            sck::k_group_count<<<h->n_sms * 2, 256, 0, h->stream>>>(det, t.d_cnt.as<uint32_t>(), t.det_cap, 0, nframes, per_frame);
+            sck::k_group_offsets<<<1, 32, 0, h->stream>>>(per_frame, nframes, offsets, fill, flags);
+            sck::k_group_scatter<<<h->n_sms * 2, 256, 0, h->stream>>>(det, t.d_cnt.as<uint32_t>(), t.det_cap, 0, nframes, offsets, fill, seg);
+            sck::k_group_frames<<<nframes, 256, gsmem, h->stream>>>(seg, offsets, 0, t.group_thr, t.group_eps, gout, flags + 1, t.det_cap);
+        }
+        h->launches += 3;
+        SC_CUDA(h, cudaGetLastError());
+        SC_CUDA(h, cudaMemcpyAsync(ho + cbytes, flags, 8, cudaMemcpyDeviceToHost, h->stream));  // overflow, object count
+        SC_CUDA(h, cudaMemcpyAsync(ho + cbytes + 8, t.d_cnt.p, 4, cudaMemcpyDeviceToHost, h->stream));
+        SC_CUDA(h, cudaMemcpyAsync(ho + cbytes + 16, gout, (size_t)t.eager * sizeof(sck::ScGroupOut), cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        SC_CUDA(h, cudaMemcpyAsync(ho + cbytes, t.d_cnt.p, 4, cudaMemcpyDeviceToHost, h->stream));
+        SC_CUDA(h, cudaMemcpyAsync(ho + cbytes + 16, t.d_det.p, (size_t)t.eager * sizeof(sc_detection), cudaMemcpyDeviceToHost, h->stream));
+    }
     SC_CUDA(h, cudaEventRecord(t.done, h->stream));
     t.busy = true;
     *ticket = ti;
@@ -1152,13 +1189,52 @@ int sc_detect_collect(sc_handle* h, int ticket, sc_detection* out, size_t cap, s
     if (!h->tickets[ticket ^ 1].busy) drain_spans(h);
     const size_t cbytes = (size_t)t.nframes * SC_CNT_STRIDE * 8;
     const unsigned char* ho = t.h_out.as<unsigned char>();
-    uint32_t found = 0;
-    memcpy(&found, ho + cbytes, 4);
     if (counters) fill_counters(h, reinterpret_cast<const unsigned long long*>(ho), t.nframes, counters);
     // keep sc_last_counters working for the host path as well
     SC_CUDA(h, h->h_stage.ensure(cbytes + 16));
     memcpy(h->h_stage.p, ho, cbytes);
     h->last_nframes = t.nframes;
+    if (t.group_thr > 0) {
+        uint32_t fl[3];
+        memcpy(fl, ho + cbytes, 12);  // overflow, objects, raw windows
+        const uint32_t raw = fl[2];
+        if (raw > t.det_cap) { *n = raw; return fail(h, SC_ERR_CAPACITY, "raw detection buffer too small for grouping"); }
+        if (fl[0]) {
+            // a frame holds more raw windows than one CTA groups (SC_GROUP_MAX): this batch is grouped on the host
+            std::vector<sc_detection> rawd(raw);
+            if (raw) SC_CUDA(h, cudaMemcpy(rawd.data(), t.d_det.p, (size_t)raw * sizeof(sc_detection), cudaMemcpyDeviceToHost));
+            sort_detections(rawd.data(), raw);
+            size_t k = 0, m = 0;
+            while (k < raw) {
+                size_t e2 = k;
+                std::vector<sc_rect> r;
+                std::vector<double> sc;
+                while (e2 < raw && rawd[e2].frame == rawd[k].frame) { r.push_back(sc_rect{rawd[e2].x, rawd[e2].y, rawd[e2].l, rawd[e2].l}); sc.push_back(rawd[e2].score); e2++; }
+                sc_host::group_rectangles(&r, &sc, t.group_thr, t.group_eps);
+                for (size_t i = 0; i < r.size(); i++, m++)
+                    if (m < cap) out[m] = sc_detection{rawd[k].frame, r[i].x, r[i].y, r[i].w, sc[i]};
+                k = e2;
+            }
+            *n = m;
+            return m > cap ? fail(h, SC_ERR_CAPACITY, "detection buffer too small") : SC_OK;
+        }
+        const uint32_t objs = fl[1];
+        *n = objs;
+        if (objs > cap || objs > t.det_cap) return fail(h, SC_ERR_CAPACITY, "detection buffer too small");
+        std::vector<sck::ScGroupOut> g(objs);
+        const uint32_t k = std::min(objs, t.eager);
+        if (k) memcpy(g.data(), ho + cbytes + 16, (size_t)k * sizeof(sck::ScGroupOut));
+        if (objs > k) {
+            const size_t seg_bytes = align256((size_t)t.det_cap * sizeof(sc_detection)), tab_bytes = align256(((size_t)3 * t.nframes + 8) * 4);
+            SC_CUDA(h, cudaMemcpy(g.data() + k, reinterpret_cast<const sck::ScGroupOut*>(t.d_grp.as<unsigned char>() + seg_bytes + tab_bytes) + k,
+                                  (size_t)(objs - k) * sizeof(sck::ScGroupOut), cudaMemcpyDeviceToHost));
+        }
+        std::sort(g.begin(), g.end(), [](const sck::ScGroupOut& a, const sck::ScGroupOut& b) { return a.frame != b.frame ? a.frame < b.frame : a.idx < b.idx; });
+        for (uint32_t i = 0; i < objs; i++) out[i] = sc_detection{g[i].frame, g[i].x, g[i].y, g[i].w, g[i].score};
+        return SC_OK;
+    }
+    uint32_t found = 0;
+    memcpy(&found, ho + cbytes, 4);
     *n = found;
     if (found > cap || found > t.det_cap) return fail(h, SC_ERR_CAPACITY, "detection buffer too small");
     if (found) {

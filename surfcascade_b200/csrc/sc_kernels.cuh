@@ -907,6 +907,202 @@ __global__ void __launch_bounds__(128) k_finalize(const ScPlan* __restrict__ pla
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Grouping of the raw windows on the device: cv::groupRectangles(wins, weights = 0.., scores, thr, eps) as called at
+// ObjDetector.cpp:224-225 (OpenCV's portable implementation), one CTA per frame.
+//   classes  = connected components of `similar` (partition): min-label propagation + pointer jumping; a class is named
+//              by its smallest member index, so ascending names = the first-seen order of cv::partition on the
+//              (l, y, x)-sorted window list the host path uses
+//   per class: integer sums of x, y, w, h, member count, best score; mean = cvRound(float(sum) * (1.f / n))
+//   kept     : more than thr members and not inside a larger kept-eligible class's mean rect grown by eps
+// ---------------------------------------------------------------------------------------------------------
+#define SC_GROUP_MAX 2048   // raw windows of one frame a CTA groups (more: the host path takes the batch)
+struct ScGroupOut { int32_t frame, idx, x, y, w, h; double score; };
+
+__global__ void k_group_count(const ScDetOut* __restrict__ det, const uint32_t* __restrict__ n_det, uint32_t cap, int frame_lo, int nframes,
+                              uint32_t* __restrict__ per_frame) {
+    const uint32_t n = min(*n_det, cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int f = det[i].frame - frame_lo;
+        if (f >= 0 && f < nframes) atomicAdd(&per_frame[f], 1u);
+    }
+}
+
+// single block: exclusive offsets of the per-frame segments, fill cursors reset, overflow flag
+__global__ void k_group_offsets(const uint32_t* __restrict__ per_frame, int nframes, uint32_t* __restrict__ offsets, uint32_t* __restrict__ fill,
+                                uint32_t* __restrict__ flags) {
+    if (threadIdx.x == 0) {
+        uint32_t run = 0, over = 0;
+        for (int f = 0; f < nframes; f++) { offsets[f] = run; run += per_frame[f]; fill[f] = 0; over |= per_frame[f] > SC_GROUP_MAX; }
+        offsets[nframes] = run;
+        flags[0] = over;
+    }
+}
+
+__global__ void k_group_scatter(const ScDetOut* __restrict__ det, const uint32_t* __restrict__ n_det, uint32_t cap, int frame_lo, int nframes,
+                                const uint32_t* __restrict__ offsets, uint32_t* __restrict__ fill, ScDetOut* __restrict__ seg) {
+    const uint32_t n = min(*n_det, cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const ScDetOut d = det[i];
+        const int f = d.frame - frame_lo;
+        if (f >= 0 && f < nframes) seg[offsets[f] + atomicAdd(&fill[f], 1u)] = d;
+    }
+}
+
+__device__ __forceinline__ bool rects_similar(int ax, int ay, int al, int bx, int by, int bl, double eps) {
+    const int m = min(al, bl);
+    const double delta = eps * (double)(m + m) * 0.5;  // eps * (min(w) + min(h)) * 0.5, all windows square
+    return (double)abs(ax - bx) <= delta && (double)abs(ay - by) <= delta && (double)abs(ax + al - bx - bl) <= delta &&
+           (double)abs(ay + al - by - bl) <= delta;
+}
+
+__global__ void __launch_bounds__(256) k_group_frames(const ScDetOut* __restrict__ seg, const uint32_t* __restrict__ offsets, int frame_lo, int thr,
+                                                       double eps, ScGroupOut* __restrict__ out, uint32_t* __restrict__ out_count, uint32_t out_cap) {
+    extern __shared__ __align__(16) unsigned char g_dyn[];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const uint32_t o0 = offsets[f];
+    const int n = (int)(offsets[f + 1] - o0);
+    if (n == 0 || n > SC_GROUP_MAX) return;
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    unsigned long long* key = reinterpret_cast<unsigned long long*>(g_dyn);      // [np2]  l << 32 | y << 16 | x ; later: best-score bits
+    double* score = reinterpret_cast<double*>(key + SC_GROUP_MAX);               // [n]
+    int* pay = reinterpret_cast<int*>(score + SC_GROUP_MAX);                     // [np2]  index into seg; later: class member count
+    int* label = pay + SC_GROUP_MAX;                                             // [n]
+    int* sx = label + SC_GROUP_MAX;                                              // [n]  class sums, indexed by the class name (a member index)
+    int* sy = sx + SC_GROUP_MAX;
+    int* sl = sy + SC_GROUP_MAX;
+    int* roots = sl + SC_GROUP_MAX;                                              // [n]  class names in ascending order; then kept classes
+    __shared__ int s_nroots;
+    __shared__ uint32_t s_base;
+    // ---- sort by (l, y, x): the order the host path groups in
+    for (int i = tid; i < np2; i += 256) {
+        if (i < n) {
+            const ScDetOut d = seg[o0 + i];
+            key[i] = ((unsigned long long)(uint32_t)d.l << 32) | ((unsigned long long)(uint32_t)d.y << 16) | (unsigned long long)(uint32_t)d.x;
+            pay[i] = i;
+        } else {
+            key[i] = ~0ull; pay[i] = -1;
+        }
+    }
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < np2; i += 256) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const bool up = (i & k) == 0;
+                    const unsigned long long a = key[i], b = key[p];
+                    if ((a > b) == up) { key[i] = b; key[p] = a; const int t = pay[i]; pay[i] = pay[p]; pay[p] = t; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = tid; i < n; i += 256) { score[i] = seg[o0 + pay[i]].score; label[i] = i; }
+    __syncthreads();
+    // ---- connected components of `similar`: every window takes the smallest label among its similar windows, then jumps
+    for (;;) {
+        int changed = 0;
+        for (int i = tid; i < n; i += 256) {
+            const unsigned long long ki = key[i];
+            const int xi = (int)(ki & 0xffffu), yi = (int)((ki >> 16) & 0xffffu), li = (int)(ki >> 32);
+            int m = label[i];
+            for (int j = 0; j < n; j++) {
+                const int lj = label[j];
+                if (lj < m) {
+                    const unsigned long long kj = key[j];
+                    if (rects_similar(xi, yi, li, (int)(kj & 0xffffu), (int)((kj >> 16) & 0xffffu), (int)(kj >> 32), eps)) m = lj;
+                }
+            }
+            if (m < label[i]) { label[i] = m; changed = 1; }
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += 256) {
+            int r = label[i];
+            while (label[r] != r) r = label[r];
+            label[i] = r;   // racing writers only ever lower a label towards its root
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    // ---- per class: sums, member count, best score
+    for (int i = tid; i < n; i += 256) { sx[i] = 0; sy[i] = 0; sl[i] = 0; pay[i] = 0; }
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        const unsigned long long ki = key[i];
+        const int r = label[i];
+        atomicAdd(&sx[r], (int)(ki & 0xffffu)); atomicAdd(&sy[r], (int)((ki >> 16) & 0xffffu)); atomicAdd(&sl[r], (int)(ki >> 32));
+        atomicAdd(&pay[r], 1);
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) key[i] = (unsigned long long)__double_as_longlong(DBL_MIN);  // keys are consumed: reuse as best-score bits
+    __syncthreads();
+    for (int i = tid; i < n; i += 256)
+        if (score[i] > DBL_MIN) atomicMax(&key[label[i]], (unsigned long long)__double_as_longlong(score[i]));  // positive doubles order like their bits
+    __syncthreads();
+    // ---- class list in ascending name order (= first-seen order), mean rects (into sx / sy / sl)
+    if (tid < 32) {
+        int run = 0;
+        for (int b0 = 0; b0 < n; b0 += 32) {
+            const int i = b0 + tid;
+            const bool is_root = i < n && label[i] == i;
+            const uint32_t m = __ballot_sync(0xffffffffu, is_root);
+            if (is_root) roots[run + __popc(m & ((1u << tid) - 1u))] = i;
+            run += __popc(m);
+        }
+        if (tid == 0) s_nroots = run;
+    }
+    __syncthreads();
+    const int k_cls = s_nroots;
+    for (int c = tid; c < k_cls; c += 256) {
+        const int r = roots[c];
+        const float inv = __fdiv_rn(1.f, (float)pay[r]);
+        sx[r] = __float2int_rn(__fmul_rn((float)sx[r], inv));
+        sy[r] = __float2int_rn(__fmul_rn((float)sy[r], inv));
+        sl[r] = __float2int_rn(__fmul_rn((float)sl[r], inv));
+    }
+    __syncthreads();
+    // ---- keep: > thr members and not swallowed; label[] is free now: kept flag per class slot
+    for (int c = tid; c < k_cls; c += 256) {
+        const int r = roots[c], ni = pay[r];
+        bool keep = ni > thr;
+        if (keep) {
+            const int ax = sx[r], ay = sy[r], al = sl[r];
+            for (int d = 0; d < k_cls && keep; d++) {
+                const int q = roots[d], nj = pay[q];
+                if (d == c || nj <= thr) continue;
+                const int bx = sx[q], by = sy[q], bl = sl[q];
+                const int dd = __double2int_rn((double)bl * eps);
+                if (ax >= bx - dd && ay >= by - dd && ax + al <= bx + bl + dd && ay + al <= by + bl + dd && (nj > max(3, ni) || ni < 3)) keep = false;
+            }
+        }
+        label[c] = keep ? 1 : 0;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        int run = 0;
+        for (int b0 = 0; b0 < k_cls; b0 += 32) {
+            const int c = b0 + tid;
+            const bool kp = c < k_cls && label[c] != 0;
+            const uint32_t m = __ballot_sync(0xffffffffu, kp);
+            if (kp) label[c] = 1 + run + __popc(m & ((1u << tid) - 1u));   // 1-based output rank
+            run += __popc(m);
+        }
+        if (tid == 0) s_base = run ? atomicAdd(out_count, (uint32_t)run) : 0u;
+    }
+    __syncthreads();
+    for (int c = tid; c < k_cls; c += 256) {
+        if (label[c] == 0) continue;
+        const int r = roots[c];
+        const uint32_t slot = s_base + (uint32_t)(label[c] - 1);
+        if (slot < out_cap) {
+            ScGroupOut g;
+            g.frame = frame_lo + f; g.idx = label[c] - 1; g.x = sx[r]; g.y = sy[r]; g.w = sl[r]; g.h = sl[r];
+            g.score = __longlong_as_double((long long)key[r]);
+            out[slot] = g;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Parity hooks on explicit rect / window lists (layout step 1)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void k_features(const float4* __restrict__ S, const ScLayout L, const int4* __restrict__ rects, int n, float* __restrict__ out,

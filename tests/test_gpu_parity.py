@@ -190,3 +190,44 @@ def test_submit_collect_pipeline_equals_sync(gpu_handle):
     with pytest.raises(capi.SurfCascadeError):
         gpu_handle.detect_submit(ptrs[2], 3, 320, 240, 320)
     gpu_handle.detect_collect(a, 3); gpu_handle.detect_collect(b, 3)
+
+
+def _host_groups(dets, n_frames, thr=2, eps=0.2):
+    out = []
+    for f in range(n_frames):
+        d = dets[dets["frame"] == f]
+        gr, gs = O.group_rectangles(np.stack([d["x"], d["y"], d["l"], d["l"]], 1), d["score"], thr, eps) if len(d) else (np.zeros((0, 4), np.int32), np.zeros(0))
+        out += [(f, int(r[0]), int(r[1]), int(r[2]), float(s)) for r, s in zip(gr, gs)]
+    return out
+
+
+def test_device_grouping_equals_group_rectangles(gpu_handle, oracle_cascade):
+    """Next row N1 on the device: sc_detect with group_threshold returns cv::groupRectangles(raw, 2, 0.2) of every frame
+    (oracle restatement pinned to cv2), in the same order, with the same rounded mean rects and best scores."""
+    frames = [synth.frame(480, 640, 1), synth.frame(240, 320, 3), synth.noise_frame(120, 160, 4), synth.frame(480, 640, 8)]
+    frames = [np.pad(f, ((0, 480 - f.shape[0]), (0, 640 - f.shape[1]))) for f in frames]
+    raw, _ = gpu_handle.detect(frames)
+    for thr, eps in ((2, 0.2), (1, 0.2), (3, 0.35)):
+        got, cnts = gpu_handle.detect(frames, capi.params(group_threshold=thr, group_eps=eps))
+        want = _host_groups(raw, len(frames), thr, eps)
+        assert [(int(g["frame"]), int(g["x"]), int(g["y"]), int(g["l"]), float(g["score"])) for g in got] == want
+        assert sum(c.raw for c in cnts) == len(raw)
+    assert len(want) > 0
+
+
+def test_device_grouping_falls_back_to_host_when_a_frame_is_crowded(oracle_cascade):
+    """More raw windows in a frame than one CTA groups (2048): the batch is grouped on the host, same result."""
+    c = oracle_cascade.c
+    k = int(c.n_weak[0])
+    h = capi.Handle(0)
+    try:
+        pool = O.pool_patches(40)
+        h.set_cascade(40, np.array([0.20], np.float32), c.n_weak[:1], pool[c.patch_index[:k]], c.w[:k], c.bias[:k])
+        img = synth.frame(240, 320, 41)
+        raw, _ = h.detect([img], capi.params(), cap=1 << 20)
+        assert len(raw) > 2048
+        got, _ = h.detect([img], capi.params(group_threshold=2), cap=1 << 20)
+        want = _host_groups(raw, 1)
+        assert [(int(g["frame"]), int(g["x"]), int(g["y"]), int(g["l"]), float(g["score"])) for g in got] == want and len(want) > 0
+    finally:
+        h.close()
