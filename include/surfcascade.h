@@ -149,6 +149,13 @@ int sc_pool_hist_device(sc_handle* h, const float* d_X, int N, int P, const uint
 /* The epilogue: AUC of every candidate from (all-reduced) histograms in device memory; auc [P] in host memory. */
 int sc_pool_auc_device(sc_handle* h, const uint32_t* d_hist, int P, int64_t n_pos, int64_t n_neg, float* auc);
 
+/* ---- training-side descriptor extraction (next row N3) --------------------------------------------------------- */
+/* ExtractNextImageFeatures (DenseSURFFeatureExtractor.cpp:104-120): IntegralImage + CalcFeature of every template-pool
+ * patch (sc_pool_patches order) for N template-sized gray samples imgs [N][tmpl][tmpl]: X [N][P][32], the training
+ * matrix sc_pool_eval consumes.  The _device variant keeps samples and X in device memory and is asynchronous. */
+int sc_extract_pool_features(sc_handle* h, const uint8_t* imgs, int N, int tmpl, float* X);
+int sc_extract_pool_features_device(sc_handle* h, const uint8_t* d_imgs, int N, int tmpl, float* d_X);
+
 /* ---- detection -------------------------------------------------------------------------------------- */
 /* The detect path of ObjDetector.cpp:165,174-219 on a batch of equally sized gray frames held in HOST memory:
  * upload, integral, scan, adaptive-stride replay, download.  Detections are sorted by (frame, l, y, x).

@@ -44,7 +44,7 @@ EXPORTS = ["sc_create", "sc_destroy", "sc_last_error", "sc_version", "sc_set_cas
            "sc_integral", "sc_features", "sc_window_sum", "sc_stage_scores", "sc_weak_predict", "sc_stage_predict", "sc_detect",
            "sc_detect_device", "sc_sync", "sc_last_counters", "sc_stream", "sc_launch_count", "sc_group_rectangles",
            "sc_set_profiling", "sc_kernel_stats", "sc_model_flatten", "sc_model_resave", "sc_pool_eval", "sc_pool_hist_device",
-           "sc_pool_auc_device", "sc_probe_gather", "sc_probe_stream", "sc_stage0_fast_check", "sc_detect_submit", "sc_detect_collect"]
+           "sc_pool_auc_device", "sc_probe_gather", "sc_probe_stream", "sc_stage0_fast_check", "sc_detect_submit", "sc_detect_collect", "sc_extract_pool_features", "sc_extract_pool_features_device"]
 
 _lib = None
 
@@ -281,6 +281,22 @@ class Handle:
         L.sc_pool_auc_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p]
         self._check(L.sc_pool_auc_device(self._h, d_hist, P, n_pos, n_neg, auc.ctypes.data))
         return auc
+
+    def extract_pool_features(self, imgs: np.ndarray, tmpl: int = 40) -> np.ndarray:
+        """imgs [N][tmpl][tmpl] u8 -> X [N][P][32] f32 (descriptors of every pool patch of every sample)."""
+        imgs = np.ascontiguousarray(imgs, np.uint8)
+        n = imgs.shape[0]
+        P = len(pool_patches(tmpl))
+        X = np.empty((n, P, 32), np.float32)
+        L = lib()
+        L.sc_extract_pool_features.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        self._check(L.sc_extract_pool_features(self._h, imgs.ctypes.data, n, tmpl, X.ctypes.data))
+        return X
+
+    def extract_pool_features_device(self, d_imgs: int, n: int, tmpl: int, d_X: int):
+        L = lib()
+        L.sc_extract_pool_features_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        self._check(L.sc_extract_pool_features_device(self._h, d_imgs, n, tmpl, d_X))
 
     # ---- detection ----
     def detect(self, frames, prm: DetectParams | None = None, cap: int = 1 << 20):

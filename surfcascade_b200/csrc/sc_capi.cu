@@ -123,6 +123,7 @@ struct sc_handle {
     ScLayout hook_lay{};
     DevBuf d_hook_img, d_hook_carry, d_hook_S;
     DevBuf d_pool_w, d_pool_wb, d_pool_auc, d_pool_x, d_pool_aux;  // training-side pool evaluation
+    DevBuf d_ext_img, d_ext_carry, d_ext_S, d_ext_geom, d_ext_X;   // training-side descriptor extraction
 
     // optional per-kernel timing with CUDA events on the handle's stream (bench.py's roofline leg)
     bool profiling = false;
@@ -153,9 +154,9 @@ int cuda_fail(sc_handle* h, cudaError_t e, const char* what) {
         if (e_ != cudaSuccess) return cuda_fail((h), e_, #call); \
     } while (0)
 
-enum { K_CARRY = 0, K_WALK, K_STAGE0, K_STAGE, K_REPLAY, K_FINALIZE, K_EVENTS, K_POOL, K_STAGE0_ODD, K_GROUP, K_COUNT };
+enum { K_CARRY = 0, K_WALK, K_STAGE0, K_STAGE, K_REPLAY, K_FINALIZE, K_EVENTS, K_POOL, K_STAGE0_ODD, K_GROUP, K_POOLFEAT, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"k_strip_carry", "k_integral_walk", "k_scan_stage0", "k_scan_stage", "k_replay_rows", "k_finalize",
-                                            "k_row_events", "k_pool_hist", "k_scan_stage0_odd", "k_group_frames"};
+                                            "k_row_events", "k_pool_hist", "k_scan_stage0_odd", "k_group_frames", "k_pool_features"};
 
 cudaEvent_t take_event(sc_handle* h) {
     cudaEvent_t e = nullptr;
@@ -636,7 +637,7 @@ void sc_destroy(sc_handle* h) {
     }
     for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
     if (h->copy_st) { cudaStreamSynchronize(h->copy_st); cudaStreamDestroy(h->copy_st); }
-    DevBuf* bufs[] = {&h->d_w, &h->d_wb, &h->d_plan, &h->d_geom, &h->d_img, &h->d_carry, &h->d_S, &h->d_counters, &h->d_det, &h->d_detcount, &h->d_pool_w, &h->d_pool_wb, &h->d_pool_auc, &h->d_pool_x, &h->d_pool_aux, &h->d_hook_img, &h->d_hook_carry, &h->d_hook_S};
+    DevBuf* bufs[] = {&h->d_w, &h->d_wb, &h->d_plan, &h->d_geom, &h->d_img, &h->d_carry, &h->d_S, &h->d_counters, &h->d_det, &h->d_detcount, &h->d_pool_w, &h->d_pool_wb, &h->d_pool_auc, &h->d_pool_x, &h->d_pool_aux, &h->d_hook_img, &h->d_hook_carry, &h->d_hook_S, &h->d_ext_img, &h->d_ext_carry, &h->d_ext_S, &h->d_ext_geom, &h->d_ext_X};
     for (DevBuf* b : bufs) b->release();
     h->h_stage.release();
     for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -978,6 +979,63 @@ int sc_pool_eval(sc_handle* h, const float* X, int N, int P, const uint8_t* labe
         if (rc != SC_OK) return rc;
     }
     return sc_pool_auc_device(h, d_hist, P, n_pos, N - n_pos, auc);
+}
+
+// Training-side descriptor extraction (next row N3).  d_imgs: N x tmpl x tmpl u8 samples in device memory;
+// d_X: [N][P][32] floats in device memory, P = size of the template pool.  Asynchronous on the handle's stream.
+int sc_extract_pool_features_device(sc_handle* h, const uint8_t* d_imgs, int N, int tmpl, float* d_X) {
+    if (!h || !d_imgs || !d_X || N < 1 || tmpl < 12) return fail(h, SC_ERR_INVALID, "bad arguments");
+    SC_CUDA(h, cudaSetDevice(h->device));
+    std::vector<sc_rect> pool;
+    sc_host::pool_patches(tmpl, tmpl, &pool);
+    const int P = (int)pool.size();
+    const ScLayout L = sc_host::make_layout(tmpl, tmpl, 1, 1, 16);
+    std::vector<ScGeom> geom(P);
+    for (int p = 0; p < P; p++)
+        if (!sc_host::project_geom(tmpl, tmpl, pool[p], L, 0, &geom[p])) return fail(h, SC_ERR_INVALID, "degenerate pool patch");
+    SC_CUDA(h, h->d_ext_geom.ensure((size_t)P * sizeof(ScGeom)));
+    SC_CUDA(h, cudaStreamSynchronize(h->stream));  // the previous call may still read the geometry
+    SC_CUDA(h, cudaMemcpy(h->d_ext_geom.p, geom.data(), (size_t)P * sizeof(ScGeom), cudaMemcpyHostToDevice));
+    const int n_strips = (tmpl + SC_STRIP - 1) / SC_STRIP;
+    const size_t per = (size_t)L.frame4 * 16 + (size_t)tmpl * n_strips * 32;
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)N, ((size_t)1 << 30) / per));
+    SC_CUDA(h, h->d_ext_carry.ensure(align256((size_t)chunk * tmpl * n_strips * 32)));
+    SC_CUDA(h, h->d_ext_S.ensure((size_t)chunk * L.frame4 * 16));
+    for (int n0 = 0; n0 < N; n0 += chunk) {
+        const int m = std::min(chunk, N - n0);
+        const uint8_t* img = d_imgs + (size_t)n0 * tmpl * tmpl;
+        { KernelSpan ks(h, K_CARRY); sck::k_strip_carry<<<(m * tmpl + 3) / 4, 128, 0, h->stream>>>(img, tmpl, tmpl, n_strips, m, h->d_ext_carry.as<int>()); }
+        { KernelSpan ks(h, K_WALK); sck::k_integral_walk<<<(m * n_strips + 3) / 4, 128, 0, h->stream>>>(img, tmpl, tmpl, n_strips, m, h->d_ext_carry.as<int>(),
+                                                                                                      h->d_ext_S.as<float4>(), L); }
+        const long long threads = (long long)m * P;
+        { KernelSpan ks(h, K_POOLFEAT);
+          sck::k_pool_features<<<(unsigned)((threads + 127) / 128), 128, 0, h->stream>>>(h->d_ext_S.as<float4>(), L, m, h->d_ext_geom.as<ScGeom>(), P,
+                                                                                          d_X + (size_t)n0 * P * 32); }
+    }
+    SC_CUDA(h, cudaGetLastError());
+    return SC_OK;
+}
+
+// Host-memory variant: imgs N x tmpl x tmpl u8, X [N][P][32]; streamed through bounded device buffers.
+int sc_extract_pool_features(sc_handle* h, const uint8_t* imgs, int N, int tmpl, float* X) {
+    if (!h || !imgs || !X || N < 1 || tmpl < 12) return fail(h, SC_ERR_INVALID, "bad arguments");
+    SC_CUDA(h, cudaSetDevice(h->device));
+    std::vector<sc_rect> pool;
+    sc_host::pool_patches(tmpl, tmpl, &pool);
+    const size_t row = pool.size() * 32 * sizeof(float);
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)N, ((size_t)1 << 29) / row));
+    SC_CUDA(h, h->d_ext_img.ensure(align256((size_t)chunk * tmpl * tmpl)));
+    SC_CUDA(h, h->d_ext_X.ensure((size_t)chunk * row));
+    for (int n0 = 0; n0 < N; n0 += chunk) {
+        const int m = std::min(chunk, N - n0);
+        SC_CUDA(h, cudaMemcpyAsync(h->d_ext_img.p, imgs + (size_t)n0 * tmpl * tmpl, (size_t)m * tmpl * tmpl, cudaMemcpyHostToDevice, h->stream));
+        int rc = sc_extract_pool_features_device(h, h->d_ext_img.as<uint8_t>(), m, tmpl, h->d_ext_X.as<float>());
+        if (rc != SC_OK) return rc;
+        SC_CUDA(h, cudaMemcpyAsync(X + (size_t)n0 * pool.size() * 32, h->d_ext_X.p, (size_t)m * row, cudaMemcpyDeviceToHost, h->stream));
+        SC_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    drain_spans(h);
+    return SC_OK;
 }
 
 int sc_detect_device(sc_handle* h, const uint8_t* d_frames, int nframes, int W, int H, const sc_detect_params* params, sc_detection* d_out,

@@ -1137,6 +1137,22 @@ __global__ void k_features(const float4* __restrict__ S, const ScLayout L, const
     }
 }
 
+// Training-side descriptor extraction (next row N3): ExtractNextImageFeatures -> IntegralImage + ExtractFeatures over the
+// template pool (DenseSURFFeatureExtractor.cpp:89-120) for a batch of template-sized samples.  One thread per
+// (sample, pool patch): X[n][p][0..31] = CalcFeature(pool[p]) on sample n's integral (layout step 1).
+__global__ void __launch_bounds__(128) k_pool_features(const float4* __restrict__ S, const ScLayout L, int nframes, const ScGeom* __restrict__ geom, int P,
+                                                        float* __restrict__ X) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)nframes * P) return;
+    const int n = (int)(i / P), p = (int)(i - (long long)n * P);
+    const ScGeom g = geom[p];  // offsets from the sample's origin
+    float v[32];
+    descriptor<0>(reinterpret_cast<const char*>(S + (size_t)n * L.frame4), g, L.hp, v);
+    float4* o = reinterpret_cast<float4*>(X + (size_t)i * 32);
+#pragma unroll
+    for (int k = 0; k < 8; k++) o[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+}
+
 __global__ void k_stage_scores(const ScPlan* __restrict__ plan, const float4* __restrict__ S, const ScGeom* __restrict__ geom_win,
                                const float* __restrict__ w_all, const double* __restrict__ wb_all, const int* __restrict__ wins, int n,
                                float* __restrict__ out) {

@@ -68,13 +68,13 @@ bool project_geom(int tmpl, int l, const sc_rect& patch, const ScLayout& L, int 
     return true;
 }
 
-ScLayout make_layout(int W, int H, int sx, int sy) {
+ScLayout make_layout(int W, int H, int sx, int sy, int min_hp) {
     ScLayout L;
     L.sx = sx < 1 ? 1 : sx;
     L.sy = sy < 1 ? 1 : sy;
     const int cols = (W + 1 + L.sx - 1) / L.sx;
-    L.hp = 256;
-    while (L.hp < cols) L.hp *= 2;  // callers reject hp > 4096 (no kernel instantiation)
+    L.hp = min_hp < 8 ? 8 : min_hp;  // the scan kernels are instantiated for 256..4096 (callers reject more); hooks take any power of two
+    while (L.hp < cols) L.hp *= 2;
     L.ppitch = 2 * L.hp;
     L.prows = (H + 1 + L.sy - 1) / L.sy;
     L.pad = 0;

@@ -25,7 +25,7 @@ sc_rect project_patch(int tmpl, int l, const sc_rect& patch);
 bool project_geom(int tmpl, int l, const sc_rect& patch, const ScLayout& L, int x0, ScGeom* g);
 
 // Integral-image layout deinterleaved by sx columns and sy rows (sc_plan.h)
-ScLayout make_layout(int W, int H, int sx, int sy);
+ScLayout make_layout(int W, int H, int sx, int sy, int min_hp = 256);
 
 // Window sides of the scale loop, ObjDetector.cpp:174,180
 void scale_ladder(int W, int H, int base, double scale, std::vector<int>* sides);

@@ -68,3 +68,18 @@ def test_pool_eval_sharded_histograms_add_up(gpu_handle):
     assert int(hist.sum().item()) == N * P
     got = gpu_handle.pool_auc_device(hist.data_ptr(), P, n_pos, N - n_pos)
     assert np.array_equal(got.view(np.uint32), whole.view(np.uint32))
+
+
+def test_extract_pool_features_bit_exact(gpu_handle):
+    """Next row N3: descriptors of all 608 pool patches of a batch of 40x40 samples (ExtractNextImageFeatures) == oracle."""
+    from oracle import oracle as O
+    from surfcascade_b200 import synth
+    rng = np.random.default_rng(5)
+    imgs = np.stack([synth.positive(s) for s in range(6)] + [rng.integers(0, 256, (40, 40), dtype=np.uint8) for _ in range(3)]
+                    + [np.zeros((40, 40), np.uint8), np.full((40, 40), 255, np.uint8)])
+    X = gpu_handle.extract_pool_features(imgs)
+    pool = O.pool_patches(40)
+    assert X.shape == (len(imgs), len(pool), 32)
+    for i, img in enumerate(imgs):
+        want, _ = O.features(O.integral(img), pool)
+        assert np.array_equal(X[i].view(np.uint32), want.view(np.uint32)), i
