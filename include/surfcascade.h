@@ -156,6 +156,15 @@ int sc_pool_auc_device(sc_handle* h, const uint32_t* d_hist, int P, int64_t n_po
 int sc_extract_pool_features(sc_handle* h, const uint8_t* imgs, int N, int tmpl, float* X);
 int sc_extract_pool_features_device(sc_handle* h, const uint8_t* d_imgs, int N, int tmpl, float* d_X);
 
+/* ---- hard-negative mining (next row N2) ------------------------------------------------------------------------ */
+/* DenseSURFFeatureExtractor::FillNegSamples (DenseSURFFeatureExtractor.cpp:124-195) in its single-thread order: per image
+ * every window of the scale ladder on a 10-pixel lattice; a window is a sample when `first` is set or the loaded cascade
+ * accepts it (CascadeClassifier::Predict, CascadeClassifier.cpp:58-67); a sample is the descriptors of all P pool patches
+ * projected into the window, X [need][P][32].  Stops when `need` samples are filled: *filled <= need, *frames_used =
+ * index after the image that completed the fill (the reference's `idx`), nframes when the images ran out. */
+int sc_mine_negatives(sc_handle* h, const uint8_t* const* frames, const int32_t* W, const int32_t* H, const int32_t* stride, int nframes,
+                      int first, int need, float* X, int* filled, int* frames_used);
+
 /* ---- detection -------------------------------------------------------------------------------------- */
 /* The detect path of ObjDetector.cpp:165,174-219 on a batch of equally sized gray frames held in HOST memory:
  * upload, integral, scan, adaptive-stride replay, download.  Detections are sorted by (frame, l, y, x).

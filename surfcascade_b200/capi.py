@@ -44,7 +44,7 @@ EXPORTS = ["sc_create", "sc_destroy", "sc_last_error", "sc_version", "sc_set_cas
            "sc_integral", "sc_features", "sc_window_sum", "sc_stage_scores", "sc_weak_predict", "sc_stage_predict", "sc_detect",
            "sc_detect_device", "sc_sync", "sc_last_counters", "sc_stream", "sc_launch_count", "sc_group_rectangles",
            "sc_set_profiling", "sc_kernel_stats", "sc_model_flatten", "sc_model_resave", "sc_pool_eval", "sc_pool_hist_device",
-           "sc_pool_auc_device", "sc_probe_gather", "sc_probe_stream", "sc_stage0_fast_check", "sc_detect_submit", "sc_detect_collect", "sc_extract_pool_features", "sc_extract_pool_features_device"]
+           "sc_pool_auc_device", "sc_probe_gather", "sc_probe_stream", "sc_stage0_fast_check", "sc_detect_submit", "sc_detect_collect", "sc_extract_pool_features", "sc_extract_pool_features_device", "sc_mine_negatives"]
 
 _lib = None
 
@@ -297,6 +297,21 @@ class Handle:
         L = lib()
         L.sc_extract_pool_features_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         self._check(L.sc_extract_pool_features_device(self._h, d_imgs, n, tmpl, d_X))
+
+    def mine_negatives(self, frames, need: int, first: bool = False, tmpl: int = 40):
+        """FillNegSamples over a list of u8 images: (X [filled][P][32], frames_used)."""
+        frames = [np.ascontiguousarray(f, np.uint8) for f in frames]
+        n = len(frames)
+        P = len(pool_patches(tmpl))
+        X = np.zeros((need, P, 32), np.float32)
+        ptrs = (C.c_void_p * n)(*[f.ctypes.data for f in frames])
+        Ws = (C.c_int32 * n)(*[f.shape[1] for f in frames]); Hs = (C.c_int32 * n)(*[f.shape[0] for f in frames])
+        filled = C.c_int(0); used = C.c_int(0)
+        L = lib()
+        L.sc_mine_negatives.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int,
+                                        C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        self._check(L.sc_mine_negatives(self._h, ptrs, Ws, Hs, Ws, n, int(first), need, X.ctypes.data, C.byref(filled), C.byref(used)))
+        return X[:filled.value], used.value
 
     # ---- detection ----
     def detect(self, frames, prm: DetectParams | None = None, cap: int = 1 << 20):

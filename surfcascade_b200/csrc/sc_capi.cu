@@ -1313,6 +1313,70 @@ int sc_detect(sc_handle* h, const uint8_t* const* frames, int nframes, int W, in
     return sc_detect_collect(h, ticket, out, cap, n, counters);
 }
 
+// Hard-negative mining (next row N2): DenseSURFFeatureExtractor::FillNegSamples (DenseSURFFeatureExtractor.cpp:124-195) in its
+// single-thread order.  Per image: every window of the scale ladder on a 10-pixel lattice; a window is taken when `first`
+// or when the loaded cascade accepts it (CascadeClassifier::Predict == every stage score >= theta: the scan with the
+// prefilter and the stride rule off); for a taken window the descriptors of ALL pool patches projected into it are
+// appended to X.  Stops when `need` samples are filled; *frames_used = index after the image that completed the fill
+// (the reference's static idx, :165), or nframes.
+int sc_mine_negatives(sc_handle* h, const uint8_t* const* frames, const int32_t* Ws, const int32_t* Hs, const int32_t* strides, int nframes, int first,
+                      int need, float* X, int* filled, int* frames_used) {
+    if (!h || !frames || !Ws || !Hs || !strides || nframes < 0 || need < 0 || !X || !filled || !frames_used)
+        return fail(h, SC_ERR_INVALID, "bad arguments");
+    if (!first && !h->have_cascade) return fail(h, SC_ERR_STATE, "no cascade loaded");
+    const int tmpl = h->have_cascade ? h->tmpl : 40;
+    std::vector<sc_rect> pool;
+    sc_host::pool_patches(tmpl, tmpl, &pool);
+    const int P = (int)pool.size();
+    sc_detect_params prm = default_params();
+    prm.base = tmpl; prm.step = 10; prm.scale = 1.1; prm.prefilter = -1; prm.skip_rule = 0;
+    int have = 0, used = nframes;
+    std::vector<sc_detection> wins;
+    std::vector<sc_rect> rects;
+    for (int i = 0; i < nframes && have < need; i++) {
+        const int W = Ws[i], H = Hs[i];
+        if (!frames[i] || W < tmpl || H < tmpl) continue;  // :137-138
+        wins.clear();
+        if (first) {
+            std::vector<int> sides;
+            sc_host::scale_ladder(W, H, tmpl, 1.1, &sides);
+            for (int l : sides)
+                for (int y = 0; y <= H - l; y += 10)
+                    for (int x = 0; x + l <= W; x += 10) wins.push_back(sc_detection{0, x, y, l, 0.0});
+        } else {
+            size_t cap = 1024, n = 0;
+            for (;;) {
+                wins.resize(cap);
+                const uint8_t* one[1] = {frames[i]};
+                const int rc = sc_detect(h, one, 1, W, H, strides[i], &prm, wins.data(), cap, &n, nullptr);
+                if (rc == SC_ERR_CAPACITY) { cap = n + 16; continue; }
+                if (rc != SC_OK) return rc;
+                break;
+            }
+            wins.resize(n);  // sorted by (l, y, x): the reference's loop order (:146-156)
+        }
+        const int take = (int)std::min<size_t>(wins.size(), (size_t)(need - have));
+        if (take > 0) {
+            int rc = sc_integral(h, frames[i], W, H, strides[i], nullptr);
+            if (rc != SC_OK) return rc;
+            rects.resize((size_t)take * P);
+            for (int k = 0; k < take; k++)
+                for (int p = 0; p < P; p++) {
+                    sc_rect r = sc_host::project_patch(tmpl, wins[k].l, pool[p]);  // ProjectPatches(win, patches, new_patches), :158
+                    r.x += wins[k].x; r.y += wins[k].y;
+                    rects[(size_t)k * P + p] = r;
+                }
+            rc = sc_features(h, rects.data(), take * P, X + (size_t)have * P * 32);
+            if (rc != SC_OK) return rc;
+            have += take;
+        }
+        if (have == need) used = i + 1;
+    }
+    *filled = have;
+    *frames_used = used;
+    return SC_OK;
+}
+
 int sc_group_rectangles(const sc_rect* rects, const double* scores, int n, int group_threshold, double eps, sc_rect* out_rects,
                         double* out_scores, int cap) {
     if (n < 0 || (n && (!rects || !scores))) return SC_ERR_INVALID;
