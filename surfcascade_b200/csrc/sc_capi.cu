@@ -360,7 +360,7 @@ int ensure_group_buffers(sc_handle* h, int want_frames, bool own_images) {
         SC_CUDA(h, L.d_idx[0].ensure(align256(std::max<size_t>(recs, 1) * 4)));
         SC_CUDA(h, L.d_idx[1].ensure(align256(std::max<size_t>(recs, 1) * 4)));
         SC_CUDA(h, L.d_small.ensure(SM_WORDS * 4));
-        SC_CUDA(h, L.d_chunks.ensure(align256(((size_t)g * (p.windows_per_frame / 64 + p.rows_per_frame) + 64) * 4)));
+        SC_CUDA(h, L.d_chunks.ensure(align256(((size_t)g * (p.windows_per_frame / 64 + 2 * (size_t)p.rows_per_frame) + 1024) * 4)));
     }
     if (!h->ev_integral) SC_CUDA(h, cudaEventCreateWithFlags(&h->ev_integral, cudaEventDisableTiming));
     h->rec_cap = (uint32_t)recs;
@@ -443,8 +443,16 @@ int run_group(sc_handle* h, sc_handle::Lane& L, int s0, int g, int frame0, sc_de
             if (p.skip_rule) {
                 if (odd_list) SC_CUDA(h, cudaMemsetAsync(small + SM_CHUNKS, 0, 8, st));
                 KernelSpan ks(h, K_EVENTS, st);
-                sck::k_row_events<<<(rows0 + 127) / 128, 128, 0, st>>>(dp, g, multi, start_odd, d_counters, odd_list ? L.d_chunks.as<uint32_t>() : nullptr,
-                                                                        small + SM_CHUNKS);
+                // d_chunks: [rows0] per-row run counts -> offsets | run list
+                uint32_t* row_chunks = L.d_chunks.as<uint32_t>();
+                sck::k_row_events<<<(rows0 + 127) / 128, 128, 0, st>>>(dp, g, multi, start_odd, d_counters, odd_list ? row_chunks : nullptr);
+                if (odd_list) {
+                    const int nb = (rows0 + 1023) / 1024;
+                    uint32_t* blk = row_chunks + rows0;           // [nb] block sums
+                    sck::k_chunk_blocksum<<<nb, 1024, 0, st>>>(row_chunks, rows0, blk);
+                    sck::k_chunk_fill<<<nb, 1024, 0, st>>>(row_chunks, rows0, blk, blk + nb, small + SM_CHUNKS);
+                    h->launches += 2;
+                }
             } else {
                 SC_CUDA(h, cudaMemsetAsync(start_odd, 0, (size_t)rows0 * 4, st));  // every odd column is visited
             }
@@ -453,7 +461,7 @@ int run_group(sc_handle* h, sc_handle::Lane& L, int s0, int g, int frame0, sc_de
                 const int grid = h->n_sms * SC_STAGE0_MIN_CTAS;
                 switch (p.lay.hp) {
 #define SC_ODD(HPV) sck::k_scan_odd<HPV><<<grid, 256, 0, st>>>(h->fast[1], dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, start_odd, \
-                                                            L.d_chunks.as<uint32_t>(), small + SM_CHUNKS, small + SM_CURSOR)
+                                                            L.d_chunks.as<uint32_t>() + rows0 + (rows0 + 1023) / 1024, small + SM_CHUNKS, small + SM_CURSOR)
                     case 256: SC_ODD(256); break;
                     case 512: SC_ODD(512); break;
                     case 1024: SC_ODD(1024); break;

@@ -619,11 +619,13 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, SC_STAGE0_MIN_CTAS) k_scan_st
 // After phase 0: per lattice row, the first even column whose window does not certainly skip (multi bit clear: it
 // passed stage 0, or was rejected with (s + 1) / N >= 0.5).  The reference's chain x += multi * step stays on even
 // columns up to there; odd columns can only be visited from the next one on.
-// With chunk_list non-null it also emits the work list of k_scan_odd: one entry (row << 10 | k) per run of 32 reachable odd
-// columns start + 64 k + 2 lane of the row.
+// With row_chunks non-null it also counts, per row, the 32-window runs of reachable odd columns (start + 64 k + 2 lane):
+// k_chunk_scan / k_chunk_fill turn the counts into the work list of k_scan_odd in (frame, scale, row) order, so that the
+// warps pulling consecutive runs stay inside one frame's integral image (L2-resident).  An atomically appended list
+// interleaved frames and scales and made k_scan_odd read 1.9 GB from HBM per 8 frames (ncu), 3.5 x their integral images.
 __global__ void __launch_bounds__(128) k_row_events(const ScPlan* __restrict__ plan, int nframes, const uint32_t* __restrict__ multi_bits,
                                                      int* __restrict__ start_odd, unsigned long long* __restrict__ counters,
-                                                     uint32_t* __restrict__ chunk_list, uint32_t* __restrict__ chunk_count) {
+                                                     uint32_t* __restrict__ row_chunks) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int rows = plan->rows_per_frame;
     if (t >= nframes * rows) return;
@@ -643,12 +645,62 @@ __global__ void __launch_bounds__(128) k_row_events(const ScPlan* __restrict__ p
     if (start < nx) {
         const int n_odd = (nx - start + 1) / 2;
         atomicAdd(&counters[(size_t)f * SC_CNT_STRIDE + SC_CNT_EVALODD], (unsigned long long)n_odd);
-        if (chunk_list) {
-            const int n = (n_odd + 31) / 32;
-            const uint32_t base = atomicAdd(chunk_count, (uint32_t)n);
-            for (int k = 0; k < n; k++) chunk_list[base + k] = ((uint32_t)t << 10) | (uint32_t)k;
-        }
+        if (row_chunks) row_chunks[t] = (uint32_t)((n_odd + 31) / 32);
+    } else if (row_chunks) {
+        row_chunks[t] = 0;
     }
+}
+
+// sum of every 1024-row block of row_chunks
+__global__ void __launch_bounds__(1024) k_chunk_blocksum(const uint32_t* __restrict__ row_chunks, int n, uint32_t* __restrict__ blk) {
+    __shared__ uint32_t wsum[32];
+    const int t = blockIdx.x * 1024 + threadIdx.x;
+    uint32_t v = t < n ? row_chunks[t] : 0u;
+    v = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const uint32_t s = __reduce_add_sync(0xffffffffu, wsum[threadIdx.x]);
+        if (threadIdx.x == 0) blk[blockIdx.x] = s;
+    }
+}
+
+// per 1024-row block: offset of the block (sum of the earlier blocks) + exclusive scan of its rows' counts, then every
+// row writes its entries (row << 10 | k); the last block publishes the total
+__global__ void __launch_bounds__(1024) k_chunk_fill(const uint32_t* __restrict__ row_chunks, int n, const uint32_t* __restrict__ blk,
+                                                      uint32_t* __restrict__ chunk_list, uint32_t* __restrict__ chunk_count) {
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (warp == 0) {
+        uint32_t acc = 0;
+        for (int b = lane; b < (int)blockIdx.x; b += 32) acc += blk[b];
+        acc = __reduce_add_sync(0xffffffffu, acc);
+        if (lane == 0) s_base = acc;
+    }
+    const int t = blockIdx.x * 1024 + tid;
+    const uint32_t c = t < n ? row_chunks[t] : 0u;
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = wsum[lane], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += v;
+        }
+        wsum[lane] = wi - w;  // exclusive prefix of the warp sums
+    }
+    __syncthreads();
+    const uint32_t off = s_base + wsum[warp] + incl - c;
+    for (uint32_t k = 0; k < c; k++) chunk_list[off + k] = ((uint32_t)t << 10) | k;
+    if (blockIdx.x == gridDim.x - 1 && tid == 1023) *chunk_count = off + c;
 }
 
 // Stage 0 on the reachable odd columns (the reference's stride reaches them only behind a row's first non-skipping
