@@ -89,9 +89,10 @@ int main(int argc, char* argv[]) {
     if (!out_path.empty()) of.open(out_path.c_str(), std::ios::binary);
     std::ostream& os = out_path.empty() ? std::cout : of;
 
-    sc_detect_params prm;
+    sc_detect_params prm = {};
     prm.base = base; prm.step = 0; prm.scale = 1.1; prm.prefilter = 6; prm.skip_rule = 1; prm.force_all_stages = 0;
-    std::vector<sc_detection> dets(1 << 20);
+    prm.group_threshold = 2; prm.group_eps = 0.2;   // groupRectangles(wins, weights, scores, 2, 0.2), ObjDetector.cpp:224-225, on the device
+    std::vector<sc_detection> dets(1 << 16);
     size_t i = 0;
     while (i < files.size()) {
         // batch consecutive images of equal size
@@ -115,17 +116,10 @@ int main(int argc, char* argv[]) {
         size_t k = 0;
         for (size_t f = 0; f < imgs.size(); f++) {
             std::cout << "Detecting image " << i + f + 1 << '/' << files.size() << std::endl;
-            std::vector<sc_rect> rects;
-            std::vector<double> scores;
-            for (; k < n && dets[k].frame == (int)f; k++) {
-                rects.push_back(sc_rect{dets[k].x, dets[k].y, dets[k].l, dets[k].l});
-                scores.push_back(dets[k].score);
-            }
-            std::vector<sc_rect> gr(rects.size() + 1);
-            std::vector<double> gs(rects.size() + 1);
-            const int m = sc_group_rectangles(rects.data(), scores.data(), (int)rects.size(), 2, 0.2, gr.data(), gs.data(), (int)gr.size());
-            os << files[i + f] << '\n' << m << '\n';
-            for (int q = 0; q < m; q++) os << gr[q].x << ' ' << gr[q].y << ' ' << gr[q].w << ' ' << gr[q].h << ' ' << gs[q] << '\n';
+            size_t k1 = k;
+            while (k1 < n && dets[k1].frame == (int)f) k1++;
+            os << files[i + f] << '\n' << (k1 - k) << '\n';   // path, count, then x y w h score (ObjDetector.cpp:228-231)
+            for (; k < k1; k++) os << dets[k].x << ' ' << dets[k].y << ' ' << dets[k].l << ' ' << dets[k].l << ' ' << dets[k].score << '\n';
         }
         i += imgs.size();
     }
