@@ -1058,7 +1058,15 @@ __global__ void __launch_bounds__(256) k_group_frames(const ScDetOut* __restrict
             const unsigned long long ki = key[i];
             const int xi = (int)(ki & 0xffffu), yi = (int)((ki >> 16) & 0xffffu), li = (int)(ki >> 32);
             int m = label[i];
-            for (int j = 0; j < n; j++) {
+            // similar windows differ in side by at most 2 delta = 2 eps min(l): in the (l, y, x)-sorted list the candidates
+            // are the contiguous run with l in [li / (1 + 2 eps), li (1 + 2 eps)] (found by bisection; a superset is fine)
+            const double span = 1.0 + 2.0 * eps;
+            const unsigned long long klo = (unsigned long long)(uint32_t)max((int)floor((double)li / span) - 1, 0) << 32;
+            const unsigned long long khi = ((unsigned long long)(uint32_t)((int)ceil((double)li * span) + 1) << 32) | 0xffffffffull;
+            int j0 = 0, j1 = n;
+            for (int a = 0, b = n; a < b;) { const int mid = (a + b) >> 1; if (key[mid] < klo) a = mid + 1; else b = mid; j0 = a; }
+            for (int a = j0, b = n; a < b;) { const int mid = (a + b) >> 1; if (key[mid] <= khi) a = mid + 1; else b = mid; j1 = a; }
+            for (int j = j0; j < j1; j++) {
                 const int lj = label[j];
                 if (lj < m) {
                     const unsigned long long kj = key[j];
