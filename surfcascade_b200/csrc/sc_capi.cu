@@ -123,7 +123,7 @@ struct sc_handle {
     ScLayout hook_lay{};
     DevBuf d_hook_img, d_hook_carry, d_hook_S;
     DevBuf d_pool_w, d_pool_wb, d_pool_auc, d_pool_x, d_pool_aux;  // training-side pool evaluation
-    DevBuf d_ext_img, d_ext_carry, d_ext_S, d_ext_geom, d_ext_X;   // training-side descriptor extraction
+    DevBuf d_ext_img, d_ext_geom, d_ext_X;   // training-side descriptor extraction
 
     // optional per-kernel timing with CUDA events on the handle's stream (bench.py's roofline leg)
     bool profiling = false;
@@ -645,7 +645,7 @@ void sc_destroy(sc_handle* h) {
     }
     for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
     if (h->copy_st) { cudaStreamSynchronize(h->copy_st); cudaStreamDestroy(h->copy_st); }
-    DevBuf* bufs[] = {&h->d_w, &h->d_wb, &h->d_plan, &h->d_geom, &h->d_img, &h->d_carry, &h->d_S, &h->d_counters, &h->d_det, &h->d_detcount, &h->d_pool_w, &h->d_pool_wb, &h->d_pool_auc, &h->d_pool_x, &h->d_pool_aux, &h->d_hook_img, &h->d_hook_carry, &h->d_hook_S, &h->d_ext_img, &h->d_ext_carry, &h->d_ext_S, &h->d_ext_geom, &h->d_ext_X};
+    DevBuf* bufs[] = {&h->d_w, &h->d_wb, &h->d_plan, &h->d_geom, &h->d_img, &h->d_carry, &h->d_S, &h->d_counters, &h->d_det, &h->d_detcount, &h->d_pool_w, &h->d_pool_wb, &h->d_pool_auc, &h->d_pool_x, &h->d_pool_aux, &h->d_hook_img, &h->d_hook_carry, &h->d_hook_S, &h->d_ext_img, &h->d_ext_geom, &h->d_ext_X};
     for (DevBuf* b : bufs) b->release();
     h->h_stage.release();
     for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -997,28 +997,15 @@ int sc_extract_pool_features_device(sc_handle* h, const uint8_t* d_imgs, int N, 
     std::vector<sc_rect> pool;
     sc_host::pool_patches(tmpl, tmpl, &pool);
     const int P = (int)pool.size();
-    const ScLayout L = sc_host::make_layout(tmpl, tmpl, 1, 1, 16);
-    std::vector<ScGeom> geom(P);
-    for (int p = 0; p < P; p++)
-        if (!sc_host::project_geom(tmpl, tmpl, pool[p], L, 0, &geom[p])) return fail(h, SC_ERR_INVALID, "degenerate pool patch");
-    SC_CUDA(h, h->d_ext_geom.ensure((size_t)P * sizeof(ScGeom)));
-    SC_CUDA(h, cudaStreamSynchronize(h->stream));  // the previous call may still read the geometry
-    SC_CUDA(h, cudaMemcpy(h->d_ext_geom.p, geom.data(), (size_t)P * sizeof(ScGeom), cudaMemcpyHostToDevice));
-    const int n_strips = (tmpl + SC_STRIP - 1) / SC_STRIP;
-    const size_t per = (size_t)L.frame4 * 16 + (size_t)tmpl * n_strips * 32;
-    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)N, ((size_t)1 << 30) / per));
-    SC_CUDA(h, h->d_ext_carry.ensure(align256((size_t)chunk * tmpl * n_strips * 32)));
-    SC_CUDA(h, h->d_ext_S.ensure((size_t)chunk * L.frame4 * 16));
-    for (int n0 = 0; n0 < N; n0 += chunk) {
-        const int m = std::min(chunk, N - n0);
-        const uint8_t* img = d_imgs + (size_t)n0 * tmpl * tmpl;
-        { KernelSpan ks(h, K_CARRY); sck::k_strip_carry<<<(m * tmpl + 3) / 4, 128, 0, h->stream>>>(img, tmpl, tmpl, n_strips, m, h->d_ext_carry.as<int>()); }
-        { KernelSpan ks(h, K_WALK); sck::k_integral_walk<<<(m * n_strips + 3) / 4, 128, 0, h->stream>>>(img, tmpl, tmpl, n_strips, m, h->d_ext_carry.as<int>(),
-                                                                                                      h->d_ext_S.as<float4>(), L); }
-        const long long threads = (long long)m * P;
-        { KernelSpan ks(h, K_POOLFEAT);
-          sck::k_pool_features<<<(unsigned)((threads + 127) / 128), 128, 0, h->stream>>>(h->d_ext_S.as<float4>(), L, m, h->d_ext_geom.as<ScGeom>(), P,
-                                                                                          d_X + (size_t)n0 * P * 32); }
+    const size_t smem = (size_t)(tmpl + 1) * (tmpl + 1) * 32 + (size_t)tmpl * tmpl;
+    if (smem > 220 * 1024) return fail(h, SC_ERR_INVALID, "template too large for the shared-memory sample integral (side <= 82)");
+    SC_CUDA(h, h->d_ext_geom.ensure((size_t)P * sizeof(sc_rect)));
+    SC_CUDA(h, cudaStreamSynchronize(h->stream));  // the previous call may still read the pool
+    SC_CUDA(h, cudaMemcpy(h->d_ext_geom.p, pool.data(), (size_t)P * sizeof(sc_rect), cudaMemcpyHostToDevice));
+    SC_CUDA(h, cudaFuncSetAttribute(sck::k_pool_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        KernelSpan ks(h, K_POOLFEAT);
+        sck::k_pool_features<<<N, 320, smem, h->stream>>>(d_imgs, tmpl, h->d_ext_geom.as<int4>(), P, d_X);
     }
     SC_CUDA(h, cudaGetLastError());
     return SC_OK;

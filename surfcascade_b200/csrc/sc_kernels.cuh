@@ -180,6 +180,12 @@ struct Px { float v[8]; };
 template <int HP>
 __device__ __forceinline__ Px load_px(const char* __restrict__ base, uint32_t off, int hp) {
     const float4* p = reinterpret_cast<const float4*>(base + off);
+    if (HP < 0) {  // integral image staged in shared memory, 32 contiguous bytes per pixel (k_pool_features)
+        const float4 lo = p[0], hi = p[1];
+        Px r;
+        r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w; r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+        return r;
+    }
 #if SC_PAIRED
     Px q;  // one 256-bit load: both halves of the pixel
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -1198,19 +1204,72 @@ __global__ void k_features(const float4* __restrict__ S, const ScLayout L, const
 }
 
 // Training-side descriptor extraction (next row N3): ExtractNextImageFeatures -> IntegralImage + ExtractFeatures over the
-// template pool (DenseSURFFeatureExtractor.cpp:89-120) for a batch of template-sized samples.  One thread per
-// (sample, pool patch): X[n][p][0..31] = CalcFeature(pool[p]) on sample n's integral (layout step 1).
-__global__ void __launch_bounds__(128) k_pool_features(const float4* __restrict__ S, const ScLayout L, int nframes, const ScGeom* __restrict__ geom, int P,
-                                                        float* __restrict__ X) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)nframes * P) return;
-    const int n = (int)(i / P), p = (int)(i - (long long)n * P);
-    const ScGeom g = geom[p];  // offsets from the sample's origin
-    float v[32];
-    descriptor<0>(reinterpret_cast<const char*>(S + (size_t)n * L.frame4), g, L.hp, v);
-    float4* o = reinterpret_cast<float4*>(X + (size_t)i * 32);
+// template pool (DenseSURFFeatureExtractor.cpp:65-120) for a batch of template-sized samples.  One CTA per sample, nothing
+// but the sample and its descriptors touches HBM: channels, exact integer row prefixes and the reference's sequential
+// float32 column recurrence are built in shared memory ((T+1)^2 pixels x 32 B; 54 KB for T = 40), then every thread takes
+// pool patches and runs the exact CalcFeature + Normalize on shared-memory corners.  X[n][p][0..31].
+__global__ void __launch_bounds__(320) k_pool_features(const uint8_t* __restrict__ imgs, int T, const int4* __restrict__ pool, int P, float* __restrict__ X) {
+    extern __shared__ __align__(16) unsigned char f_dyn[];
+    float* S = reinterpret_cast<float*>(f_dyn);                     // [(T+1)][(T+1)][8]
+    int* Si = reinterpret_cast<int*>(f_dyn);
+    uint8_t* im = f_dyn + (size_t)(T + 1) * (T + 1) * 32;           // [T][T]
+    const int n = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, T1 = T + 1;
+    const uint8_t* src = imgs + (size_t)n * T * T;
+    for (int i = tid; i < T * T; i += nt) im[i] = src[i];
+    for (int i = tid; i < T1 * 8; i += nt) { S[i] = 0.f; S[(size_t)(i >> 3) * T1 * 8 + (i & 7)] = 0.f; }  // row 0 and column 0
+    __syncthreads();
+    // exact row prefixes of the eight channels (T2bFilter :199-349): thread = (row, channel); the four differences are
+    // one formula with per-channel neighbour offsets (no divergence between the channels of a warp)
+    for (int t = tid; t < T * 8; t += nt) {
+        const int y = t >> 3, c = t & 7, k = c >> 1;
+        // d = I[y + ay][x + ax] - I[y + by][x + bx]:  dx (0,+1)-(0,-1)  dy (+1,0)-(-1,0)  du (+1,+1)-(-1,-1)  dv (-1,+1)-(+1,-1)
+        const int ay = k == 0 ? 0 : (k == 3 ? -1 : 1), ax = k == 1 ? 0 : 1;
+        const int ra = min(max(y + ay, 0), T - 1) * T, rb = min(max(y - ay, 0), T - 1) * T;
+        const int sgn = (c & 1) ? 1 : -1;
+        int run = 0;
+        int* out = Si + ((size_t)(y + 1) * T1 + 1) * 8 + c;
+        for (int x = 0; x < T; x++) {
+            const int xa = min(max(x + ax, 0), T - 1), xb = min(max(x - ax, 0), T - 1);
+            const int d = (int)im[ra + xa] - (int)im[rb + xb];
+            run += max(sgn * d, 0);
+            out[x * 8] = run;
+        }
+    }
+    __syncthreads();
+    // S[y+1][x+1][c] = fl32(S[y][x+1][c] + float(rowprefix)), sequential in y (cv::integral, Appendix A.2): thread = (column, channel)
+    for (int t = tid; t < T * 8; t += nt) {
+        const int x = (t >> 3) + 1, c = t & 7;
+        float acc = 0.f;
+        for (int y = 1; y <= T; y++) {
+            const size_t i = ((size_t)y * T1 + x) * 8 + c;
+            acc = __fadd_rn(acc, (float)Si[i]);
+            S[i] = acc;
+        }
+    }
+    __syncthreads();
+    const int pitch = T1 * 32;  // bytes per integral row
+    for (int p = tid; p < P; p += nt) {
+        const int4 r = pool[p];  // x, y, w, h on the template
+        ScGeom g;
+        g.pad = 0;
+        if (r.z == r.w) {
+            const int ce = r.z / 2;
+            g.shape = 0;
+            for (int b = 0; b < 3; b++)
+                for (int a = 0; a < 3; a++) g.c[3 * b + a] = (uint32_t)(b * ce * pitch + a * ce * 32);
+            g.c[9] = 0;
+        } else {
+            const int ce = min(r.z, r.w);
+            const int along = r.z > r.w ? ce * 32 : ce * pitch, across = r.z > r.w ? ce * pitch : ce * 32;
+            g.shape = 1;
+            for (int k = 0; k < 5; k++) { g.c[k] = (uint32_t)(k * along); g.c[5 + k] = (uint32_t)(k * along + across); }
+        }
+        float v[32];
+        descriptor<-1>(reinterpret_cast<const char*>(S) + (size_t)r.y * pitch + (size_t)r.x * 32, g, 1, v);
+        float4* o = reinterpret_cast<float4*>(X + ((size_t)n * P + p) * 32);
 #pragma unroll
-    for (int k = 0; k < 8; k++) o[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        for (int k = 0; k < 8; k++) o[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    }
 }
 
 __global__ void k_stage_scores(const ScPlan* __restrict__ plan, const float4* __restrict__ S, const ScGeom* __restrict__ geom_win,
