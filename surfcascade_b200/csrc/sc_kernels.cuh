@@ -286,37 +286,17 @@ __device__ __forceinline__ float stage_score(const char* __restrict__ base, cons
         g.c[0] = g0.x; g.c[1] = g0.y; g.c[2] = g0.z; g.c[3] = g0.w; g.c[4] = g1.x; g.c[5] = g1.y; g.c[6] = g1.z; g.c[7] = g1.w;
         g.c[8] = g2.x; g.c[9] = g2.y; g.shape = g2.z; g.pad = 0;
         float v[32];
-#ifdef SC_EXP_LOADS_ONLY   // tuning experiment: loads + box sums only (wrong results), to see what the memory system alone allows
-        box_sums<HP>(base, g, hp, v);
-        float t = 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; i++) t += v[i];
-        acc += (t == 12345.678f) ? 1.f : 0.f;
-#else
         descriptor<HP>(base, g, hp, v);
         acc = __fadd_rn(acc, weak_predict(v, w + q * SC_W_PITCH, wb[q]));
-#endif
     }
     return __fdiv_rn(acc, (float)n_weak);
 }
 
 // DenseSURFFeatureExtractor::sum (:351-358) and the compare at ObjDetector.cpp:188; pf = byte offsets of the corners
 // (0,0) (l,0) (0,l) (l,l) from the window's low-half element
-// 16-byte read-only load that does not allocate in L1: the prefilter's four corners are used once, the descriptor
-// corners that follow have short-distance reuse worth keeping
-__device__ __forceinline__ float4 ldg_stream(const float4* p) {
-#ifdef SC_PF_NOALLOC
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-#else
-    return __ldg(p);
-#endif
-}
-
 __device__ __forceinline__ float window_sum(const char* __restrict__ base, const uint32_t* pf) {
-    const float4 a = ldg_stream(reinterpret_cast<const float4*>(base + pf[0])), b = ldg_stream(reinterpret_cast<const float4*>(base + pf[1]));
-    const float4 c = ldg_stream(reinterpret_cast<const float4*>(base + pf[2])), d = ldg_stream(reinterpret_cast<const float4*>(base + pf[3]));
+    const float4 a = __ldg(reinterpret_cast<const float4*>(base + pf[0])), b = __ldg(reinterpret_cast<const float4*>(base + pf[1]));
+    const float4 c = __ldg(reinterpret_cast<const float4*>(base + pf[2])), d = __ldg(reinterpret_cast<const float4*>(base + pf[3]));
     const float s0 = __fsub_rn(__fadd_rn(a.x, d.x), __fadd_rn(b.x, c.x));
     const float s1 = __fsub_rn(__fadd_rn(a.y, d.y), __fadd_rn(b.y, c.y));
     const float s2 = __fsub_rn(__fadd_rn(a.z, d.z), __fadd_rn(b.z, c.z));

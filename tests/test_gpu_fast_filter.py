@@ -92,3 +92,45 @@ def test_recut_cascades_match_oracle(oracle_cascade, n_stages, theta0):
             np.testing.assert_allclose(dets["score"], want.score, rtol=1e-6, atol=0)
     finally:
         h.close()
+
+
+def _random_cascade(seed, n_weak, thetas, shapes="mixed"):
+    """Cascade with weak classifiers on randomly drawn pool patches (squares 0-343, tall 344-475, wide 476-607)."""
+    from oracle.modelcfg import Cascade
+    rng = np.random.default_rng(seed)
+    total = int(sum(n_weak))
+    if shapes == "mixed":
+        idx = np.concatenate([rng.integers(0, 344, total - 2 * (total // 3)), rng.integers(344, 476, total // 3), rng.integers(476, 608, total // 3)])
+        rng.shuffle(idx)
+    else:
+        idx = rng.integers(0, 344, total)
+    w = rng.normal(0, 1.0, (total, 33)).astype(np.float32)
+    w[:, 32] = rng.normal(0, 0.3, total).astype(np.float32)
+    return Cascade(np.array(thetas, np.float32), np.array(n_weak, np.int32), idx.astype(np.int32), w, np.ones(total))
+
+
+@pytest.mark.parametrize("seed,n_weak,thetas,shapes", [(1, [3, 5, 4], [0.50, 0.50, 0.50], "mixed"), (2, [2, 3], [0.45, 0.52], "squares"),
+                                                        (3, [6, 2], [0.48, 0.50], "mixed"), (4, [8, 3, 3], [0.49, 0.50, 0.50], "mixed"),
+                                                        (5, [1], [0.55], "squares")])
+def test_random_cascades_with_square_patches_match_oracle(seed, n_weak, thetas, shapes):
+    """Cascades the model file does not cover: 2x2-cell patches in stage 0 (fast filter and exact path), six weak classifiers
+    (the filter's limit), eight (exact-only kernel), a single weak classifier; full detect parity incl. counters."""
+    bc = O.BoundCascade(_random_cascade(seed, n_weak, thetas, shapes))
+    h = capi.Handle(0)
+    try:
+        h.set_cascade(40, bc.theta, bc.n_weak, bc.rects, bc.w, bc.bias)
+        for img, prm in ((synth.frame(200, 260, 60 + seed), {}), (synth.noise_frame(130, 170, seed), {"step": 1}), (synth.frame(200, 260, 70 + seed), {"skip_rule": False})):
+            dets, cnts = h.detect([img], capi.params(**prm), cap=1 << 21)
+            want = O.detect(O.integral(img), bc, O.params(base=40, step=prm.get("step", 0), skip_rule=prm.get("skip_rule", True), nthreads=8), cap=1 << 21)
+            assert cnts[0].visited == want.counters[O.C_VISITED] and cnts[0].prefilter_pass == want.counters[O.C_PREFILTER]
+            assert [cnts[0].reach[s] for s in range(len(n_weak))] == [int(want.counters[O.C_REACH0 + s]) for s in range(len(n_weak))]
+            assert np.array_equal(dets["x"], want.x) and np.array_equal(dets["y"], want.y) and np.array_equal(dets["l"], want.l)
+            np.testing.assert_allclose(dets["score"], want.score, rtol=1e-6, atol=0)
+        # the fast filter's distance budget holds for these weights and shapes too
+        if n_weak[0] <= 6:
+            img = synth.frame(240, 320, 80 + seed)
+            h.integral(img, want_output=False)
+            fs, es, margin = h.stage0_fast_check(_windows(240, 320, 60000, np.random.default_rng(seed)))
+            assert np.abs(fs.astype(np.float64) - es.astype(np.float64)).max() < margin / 4
+    finally:
+        h.close()

@@ -97,6 +97,34 @@ if world > 1:
     dist.all_reduce(tot)
 out["C4"] = {"ms_per_frame": round(ms4, 2), "windows": int(tot[0].item()), "windows_per_s": round(int(tot[0].item()) / ms4 * 1e3 / 1e9, 3), "unit": "G windows/s",
              "raw_detections": int(tot[1].item()), "split": f"{world} row bands per scale, integral replicated"}
+# ---- C5 ------------------------------------------------------------------------------------------------------
+# candidate scoring of one boosting round: X [100k][608][32] sharded by sample; every rank streams its shard into the
+# 608 x 2 x 21 level histograms, ONE all-reduce (NCCL) of 102 KB, AUC of every candidate on every rank
+del d_out4, img, dev_batch
+torch.cuda.empty_cache()
+N5, P5 = 100000, 608
+n_loc = len(range(rank, N5, world))
+X5 = torch.randn(n_loc, P5, 32, device=dev) * 0.2
+lab5 = (torch.arange(n_loc, device=dev) % 2).to(torch.uint8)
+hist = torch.zeros(P5 * 2 * 21, dtype=torch.int32, device=dev)
+W5 = np.random.default_rng(0).normal(0, 1, size=(P5, 33)).astype(np.float32); b5 = np.ones(P5)
+n_pos = torch.tensor([int(lab5.sum().item()), n_loc], dtype=torch.int64, device=dev)
+if world > 1:
+    dist.all_reduce(n_pos)
+for it in range(2):   # first pass warms up
+    hist.zero_()
+    barrier()
+    e0.record(stream)
+    h.pool_hist_device(X5.data_ptr(), n_loc, P5, lab5.data_ptr(), W5, b5, None, 0, hist.data_ptr())
+    if world > 1:
+        with torch.cuda.stream(stream):
+            dist.all_reduce(hist)
+    e1.record(stream); h.sync()
+    auc = h.pool_auc_device(hist.data_ptr(), P5, int(n_pos[0].item()), int((n_pos[1] - n_pos[0]).item()))
+    barrier()
+ms5 = max_over_ranks(e0.elapsed_time(e1))
+out["C5"] = {"ms": round(ms5, 3), "GB_streamed": round(N5 * P5 * 128 / 1e9, 2), "GBps_aggregate": round(N5 * P5 * 128 / ms5 / 1e6, 0), "samples_per_rank": n_loc,
+             "auc_mean": round(float(auc.mean()), 4), "exchange": "one all-reduce of 608 x 2 x 21 int32 level counts"}
 if rank == 0:
     os.write(json_fd, (json.dumps(out) + "\n").encode())
 if world > 1:
