@@ -474,8 +474,10 @@ int run_group(sc_handle* h, sc_handle::Lane& L, int s0, int g, int frame0, sc_de
             }
         }
         const int tail_grid = h->n_sms * 8;
-        for (int s = 1; s < p.n_stages; s++) {
-            const bool first = s == 1 || p.force_all;
+        // with the fast filter, stage 0's undecided windows are live records: k_scan_stage(0) gives them the exact arithmetic
+        const int s_begin = h->use_fast ? 0 : 1;
+        for (int s = s_begin; s < p.n_stages; s++) {
+            const bool first = s == s_begin || p.force_all;
             const uint32_t* in_idx = first ? nullptr : L.d_idx[(s - 1) & 1].as<uint32_t>();
             const uint32_t* in_cnt = first ? small + SM_REC : small + SM_STAGE0 + (s - 1);
             const size_t smem = (size_t)p.n_weak[s] * (SC_W_PITCH * 4 + 8);

@@ -23,6 +23,10 @@
 #define SC_STAGE0_MIN_CTAS 3   // 80 registers: 3 CTAs (24 warps) per SM; 4 forces 64 registers and spills (measured slower)
 #endif
 
+#ifndef SC_FAST_MIN_CTAS
+#define SC_FAST_MIN_CTAS 4     // the fast-filter kernel holds no exact arithmetic: 64 registers, 4 CTAs (32 warps) per SM
+#endif
+
 // Integral strips: one warp walks one 32-column strip down the frame, SC_WALK_RB rows per prefetch block.
 #define SC_STRIP 32
 #ifndef SC_WALK_RB

@@ -65,7 +65,13 @@ def test_filtered_scan_equals_exact_only_scan(gpu_handle, model_c1):
             b, cb = hx.detect(frames, prm)
             assert a.tobytes() == b.tobytes()
             for x, y in zip(ca, cb):
-                assert bytes(x) == bytes(y)
+                # every reference-defined counter is equal; `evaluated` is this implementation's own work count: the
+                # filtered scan leaves its undecided windows to a later exact pass and, until then, treats them as "may
+                # not skip" when it picks the odd columns to evaluate -- a superset of the exact-only scan's choice
+                for k in ("grid", "visited", "prefilter_pass", "weak_evals", "raw"):
+                    assert getattr(x, k) == getattr(y, k), k
+                assert list(x.reach) == list(y.reach)
+                assert x.visited <= y.evaluated <= x.evaluated <= x.grid
     finally:
         hx.close()
 
