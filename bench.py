@@ -374,7 +374,7 @@ def run_ours(args):
                          "l2_to_l1_bytes_per_launch": l2_bytes_ev, "l2_to_l1_achieved_gbs": l2_meas_gbs,
                          "l2_to_l1_frac_of_peak": (l2_meas_gbs / l2_peak) if (l2_meas_gbs and l2_peak) else None,
                          "hbm_peak": peak, "achieved_over_hbm_peak": (scan_gbs / peak) if scan_gbs else None,
-                         "note": "gather-bound scan (SURVEY.md 8d): `achieved` = algorithmic corner bytes 32 B x (4 x reference-visited windows + 10 x reference weak evaluations) per frame / CUDA-event time of both stage-0 kernels; they are served by L1 (~18 % hits) and L2, not HBM (" + peak_src + " is given for scale only), so `peak` is the L2 -> SM bandwidth measured live in this run by sc_probe_stream (coalesced 16-byte loads over an L2-resident table). `l2_to_l1_*` = the sectors L2 actually delivered to the SMs in the even-column launch (ncu l1tex__m_xbar2l1tex_read_bytes, profiles/) / that launch's live duration: the kernel runs at the L2 -> SM ceiling (ncu: L1TEX data pipe 81 %, LTS 67 %, issue 51 %), see DESIGN.md section 6",
+                         "note": "gather-bound scan (SURVEY.md 8d): `achieved` = algorithmic corner bytes 32 B x (4 x reference-visited windows + 10 x reference weak evaluations) per frame / CUDA-event time of both stage-0 kernels; they are served by L1 (~18 % hits) and L2, not HBM (" + peak_src + " is given for scale only), so `peak` is the L2 -> SM bandwidth measured live in this run by sc_probe_stream (coalesced 16-byte loads over an L2-resident table). `l2_to_l1_*` = the sectors L2 actually delivered to the SMs in the even-column launch (ncu l1tex__m_xbar2l1tex_read_bytes, profiles/) / that launch's live duration: the kernel is bound by the L1TEX data pipe it feeds (ncu: 88 % busy; LTS 75 %, issue 57 %) and moves more L2 -> SM bytes per second than the stream probe does, see DESIGN.md section 5",
                          "share_of_step": st0_ms / total_k_ms},
             "roofline_integral": {"kernel": "k_strip_carry+k_integral_walk", "bound": "hbm", "achieved": int_gbs, "peak": peak, "unit": "GB/s",
                                   "frac": (int_gbs / peak) if int_gbs else None, "traffic": traffic_int,
