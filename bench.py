@@ -334,6 +334,13 @@ def run_ours(args):
             l2_peak = max(h.probe_stream(32 << 20, 5, m) for m in (1, 3))
         except Exception:
             l2_peak = None
+        sm_mhz = (clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965.0) if isinstance(clk, dict) else 1965.0
+        l1_peak = 18944.0 * sm_mhz * 1e6 / 1e9  # GB/s: 128 B/clk/SM x 148 SMs
+        ncu_pct = None
+        try:
+            ncu_pct = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["ncu_pct_of_peak"]["k_scan_stage0_even"]
+        except Exception:
+            pass
         ev_launch_ms = ev_ms / ev_n if ev_n else None
         l2_meas_gbs = (l2_bytes_ev / (ev_launch_ms / 1e3) / 1e9) if (l2_bytes_ev and ev_launch_ms and B % group == 0) else None
         cpu = None
@@ -366,15 +373,17 @@ def run_ours(args):
                                              "note": "groupRectangles(raw, 2, 0.2) per frame on the device (next row N1); same pipelined calls, grouped objects out"}},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"kernel": "k_scan_stage0 (even columns) + k_scan_odd (reachable odd columns)", "bound": "l2",
-                         "achieved": scan_gbs, "peak": l2_peak, "unit": "GB/s", "frac": (scan_gbs / l2_peak) if (scan_gbs and l2_peak) else None,
+            "roofline": {"kernel": "k_scan_stage0 (even columns) + k_scan_odd (reachable odd columns)", "bound": "l1",
+                         "achieved": scan_gbs, "peak": l1_peak, "unit": "GB/s", "frac": (scan_gbs / l1_peak) if (scan_gbs and l1_peak) else None,
+                         "peak_note": "L1TEX data-pipe bandwidth, 128 B/clk/SM (ncu derived__l1tex__lsu_writeback_bytes_mem_lgds.sum.peak_sustained = 18944 B/clk on 148 SMs) x the SM clock sampled in this run",
                          "traffic": traffic_scan,
                          "traffic_note": "dram__bytes_read+write of one k_scan_stage0 launch (even columns of an 8-frame scan group), ncu --set full, profiles/r1_traffic.json: the integral images are read from HBM about once, everything else is cache traffic",
                          "algorithmic_bytes_per_launch": alg_scan_bytes * group,
+                         "ncu_pct_of_peak_even_launch": ncu_pct,
                          "l2_to_l1_bytes_per_launch": l2_bytes_ev, "l2_to_l1_achieved_gbs": l2_meas_gbs,
-                         "l2_to_l1_frac_of_peak": (l2_meas_gbs / l2_peak) if (l2_meas_gbs and l2_peak) else None,
+                         "stream_probe_gbs": l2_peak,
                          "hbm_peak": peak, "achieved_over_hbm_peak": (scan_gbs / peak) if scan_gbs else None,
-                         "note": "gather-bound scan (SURVEY.md 8d): `achieved` = algorithmic corner bytes 32 B x (4 x reference-visited windows + 10 x reference weak evaluations) per frame / CUDA-event time of both stage-0 kernels; they are served by L1 (~18 % hits) and L2, not HBM (" + peak_src + " is given for scale only), so `peak` is the L2 -> SM bandwidth measured live in this run by sc_probe_stream (coalesced 16-byte loads over an L2-resident table). `l2_to_l1_*` = the sectors L2 actually delivered to the SMs in the even-column launch (ncu l1tex__m_xbar2l1tex_read_bytes, profiles/) / that launch's live duration: the kernel is bound by the L1TEX data pipe it feeds (ncu: 88 % busy; LTS 75 %, issue 57 %) and moves more L2 -> SM bytes per second than the stream probe does, see DESIGN.md section 5",
+                         "note": "gather-bound scan (SURVEY.md 8d): `achieved` = algorithmic corner bytes 32 B x (4 x reference-visited windows + 10 x reference weak evaluations) per frame / CUDA-event time of both stage-0 kernels. They are served by L1 (~15 % hits) and L2, not HBM (" + peak_src + ", given for scale only: DRAM is ~5 % busy), so the roof is the L1TEX data pipe every 16-byte-per-lane load goes through. ncu on the even-column launch (profiles/r1_ncu_scan_final.txt): that pipe is 88 % busy -- a 512-byte warp load costs 5.6 wavefronts instead of the ideal 4 (misaligned start, fills of the 85 % that miss) -- LTS 75 %, issue 57 %. `l2_to_l1_achieved_gbs` = sectors L2 delivered in that launch (ncu l1tex__m_xbar2l1tex_read_bytes) / the launch's live duration; `stream_probe_gbs` = sc_probe_stream, coalesced 16-byte loads over a 32 MB table, measured live (an L1-resident table gives the same figure: the probe is LSU-bound, so it is a reference point, not a ceiling)",
                          "share_of_step": st0_ms / total_k_ms},
             "roofline_integral": {"kernel": "k_strip_carry+k_integral_walk", "bound": "hbm", "achieved": int_gbs, "peak": peak, "unit": "GB/s",
                                   "frac": (int_gbs / peak) if int_gbs else None, "traffic": traffic_int,

@@ -1094,14 +1094,14 @@ int sc_probe_gather(sc_handle* h, size_t table_bytes, int iters, double* gbps) {
 }
 
 int sc_probe_stream(sc_handle* h, size_t table_bytes, int iters, int mode, double* gbps) {
-    if (!h || !gbps || table_bytes < (1u << 20) || iters < 1) return fail(h, SC_ERR_INVALID, "bad arguments");
+    if (!h || !gbps || table_bytes < (1u << 14) || iters < 1) return fail(h, SC_ERR_INVALID, "bad arguments");
     SC_CUDA(h, cudaSetDevice(h->device));
     DevBuf tab, sink;
     SC_CUDA(h, tab.ensure(table_bytes));
     SC_CUDA(h, sink.ensure(256));
     SC_CUDA(h, cudaMemsetAsync(tab.p, 0, table_bytes, h->stream));
-    uint32_t n4 = 1u << 16;
-    while ((size_t)n4 * 2 * 16 <= table_bytes && n4 < (1u << 29)) n4 *= 2;  // largest power of two that fits
+    uint32_t n4 = 1u << 10;
+    while ((size_t)n4 * 2 * 16 <= table_bytes && n4 < (1u << 29)) n4 *= 2;  // largest power of two that fits (64 KB and less: L1-resident)
     // mode bit 0: 0 = ld.global.cg, 1 = ld.global.nc; bits 1..: independent loads in flight per thread (0 -> 4, 1 -> 8, 2 -> 16)
     const int per_thread = 256, grid = h->n_sms * 16, unroll = mode >> 1;
     mode &= 1;
