@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, FAST ? SC_FAST_MIN_CTAS : SC_
                 if (sum < fp.lim_reject && sum < fp.lim_skip) { word = (uint32_t)(row * 4 + 2 * half + (ln >> 4)); bit = 1u << (2 * (ln & 15) + phase); }
                 else undecided = !(sum < fp.lim_reject && sum >= fp.lim_noskip);
             }
-            if (bit) atomicOr(&s_multi[word >> 2][word & 3], bit);  // (warp-aggregating these with match.any measured slower)
+            if (bit) atomicOr(&s_multi[word >> 2][word & 3], bit);  // (warp-aggregating these -- match.any + REDUX, or run heads + REDUX -- measured slower: the kernel sits at 64 registers)
             const uint32_t m = __ballot_sync(0xffffffffu, undecided);
             if (m) {
                 uint32_t base2 = 0;
