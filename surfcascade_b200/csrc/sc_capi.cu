@@ -82,6 +82,7 @@ struct sc_handle {
     bool allow_fast = true;     // SC_DISABLE_FAST=1 in the environment forces the exact-only kernel (A/B tests)
     bool use_fast = false;
     ScFastParams fast[2];
+    int stage_lg = 0;  // log2 of the lanes per window in k_scan_stage (SC_STAGE_LG, experiments)
 
     // group buffers
     int group_frames = 0;       // frames one scan group holds (records, bitmasks)
@@ -294,6 +295,7 @@ int build_plan(sc_handle* h, int W, int H, const sc_detect_params& prm, std::vec
             }
             for (int i = 0; i < nsc; i++) {
                 fp.block_base[i] = p.sc[i].block_base;
+                fp.row_base[i] = p.sc[i].row_base;
                 for (int q = 0; q < n0; q++) {
                     const ScGeom& g = (*geom_out)[((size_t)ph * nsc + i) * h->total_weak + q];
                     for (int k = 0; k < 10; k++) fp.geom[i][q][k] = g.c[k];
@@ -481,9 +483,15 @@ int run_group(sc_handle* h, sc_handle::Lane& L, int s0, int g, int frame0, sc_de
             const uint32_t* in_idx = first ? nullptr : L.d_idx[(s - 1) & 1].as<uint32_t>();
             const uint32_t* in_cnt = first ? small + SM_REC : small + SM_STAGE0 + (s - 1);
             const size_t smem = (size_t)p.n_weak[s] * (SC_W_PITCH * 4 + 8);
+            // lanes per surviving window (k_scan_stage): 0 = one thread per window.  Spreading a window's weak classifiers
+            // over 2^lg lanes was measured slower on C2 (0.0247 -> 0.0269 ms/frame): the survivors' gathers are one L1
+            // wavefront per lane either way, and fewer windows per warp lose the lines x-adjacent survivors share.
+            // SC_STAGE_LG=n overrides for experiments.
+            int lg = 0;
+            if (h->stage_lg > 0 && !p.force_all) while ((1 << lg) < p.n_weak[s] && lg < h->stage_lg) lg++;
             KernelSpan ks(h, K_STAGE, st);
             launch_stage(p.lay.hp, tail_grid, smem, st, dp, s, S, geom, w, wb, multi, rec, in_idx, in_cnt, L.d_idx[s & 1].as<uint32_t>(),
-                         small + SM_STAGE0 + s, h->rec_cap);
+                         small + SM_STAGE0 + s, h->rec_cap, lg);
         }
         const int rows = g * p.rows_per_frame;
         { KernelSpan ks(h, K_REPLAY, st); sck::k_replay_rows<<<(rows + 127) / 128, 128, 0, st>>>(dp, g, multi, pass, visited, d_counters); }
@@ -626,6 +634,8 @@ int sc_create(int device, sc_handle** out) {
     cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device);
     const char* nofast = getenv("SC_DISABLE_FAST");
     h->allow_fast = !(nofast && nofast[0] == '1');
+    const char* slg = getenv("SC_STAGE_LG");
+    h->stage_lg = slg ? std::min(5, std::max(0, atoi(slg))) : 0;
     *out = h;
     return SC_OK;
 }

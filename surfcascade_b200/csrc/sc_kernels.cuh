@@ -273,22 +273,27 @@ __device__ __forceinline__ float weak_predict(const float* v, const float* __res
     return (float)(1.0 / (1.0 + exp(-z)));
 }
 
-// GentleAdaboost::Predict2 (GentleAdaboost.cpp:247-261) of one stage on one window; geometry is read as three 16-byte
-// vectors per weak classifier (shared or global memory).
+// One weak classifier of a stage on one window: CalcFeature + Normalize + LogisticRegression::Predict.  The projected
+// geometry is read as three 16-byte vectors (shared or global memory).
+template <int HP>
+__device__ __forceinline__ float weak_output(const char* __restrict__ base, const ScGeom* __restrict__ geom, const float* __restrict__ w,
+                                             const double* __restrict__ wb, int q, int hp) {
+    ScGeom g;
+    const uint4* gs = reinterpret_cast<const uint4*>(geom + q);
+    const uint4 g0 = gs[0], g1 = gs[1], g2 = gs[2];
+    g.c[0] = g0.x; g.c[1] = g0.y; g.c[2] = g0.z; g.c[3] = g0.w; g.c[4] = g1.x; g.c[5] = g1.y; g.c[6] = g1.z; g.c[7] = g1.w;
+    g.c[8] = g2.x; g.c[9] = g2.y; g.shape = g2.z; g.pad = 0;
+    float v[32];
+    descriptor<HP>(base, g, hp, v);
+    return weak_predict(v, w + q * SC_W_PITCH, wb[q]);
+}
+
+// GentleAdaboost::Predict2 (GentleAdaboost.cpp:247-261) of one stage on one window
 template <int HP>
 __device__ __forceinline__ float stage_score(const char* __restrict__ base, const ScGeom* __restrict__ geom, const float* __restrict__ w,
                                              const double* __restrict__ wb, int n_weak, int hp) {
     float acc = 0.f;
-    for (int q = 0; q < n_weak; q++) {
-        ScGeom g;
-        const uint4* gs = reinterpret_cast<const uint4*>(geom + q);
-        const uint4 g0 = gs[0], g1 = gs[1], g2 = gs[2];
-        g.c[0] = g0.x; g.c[1] = g0.y; g.c[2] = g0.z; g.c[3] = g0.w; g.c[4] = g1.x; g.c[5] = g1.y; g.c[6] = g1.z; g.c[7] = g1.w;
-        g.c[8] = g2.x; g.c[9] = g2.y; g.shape = g2.z; g.pad = 0;
-        float v[32];
-        descriptor<HP>(base, g, hp, v);
-        acc = __fadd_rn(acc, weak_predict(v, w + q * SC_W_PITCH, wb[q]));
-    }
+    for (int q = 0; q < n_weak; q++) acc = __fadd_rn(acc, weak_output<HP>(base, geom, w, wb, q, hp));
     return __fdiv_rn(acc, (float)n_weak);
 }
 
@@ -639,7 +644,7 @@ __global__ void __launch_bounds__(128) k_row_events(const ScPlan* __restrict__ p
     if (start < nx) {
         const int n_odd = (nx - start + 1) / 2;
         atomicAdd(&counters[(size_t)f * SC_CNT_STRIDE + SC_CNT_EVALODD], (unsigned long long)n_odd);
-        if (row_chunks) row_chunks[t] = (uint32_t)((n_odd + 31) / 32);
+        if (row_chunks) row_chunks[t] = (uint32_t)((n_odd + SC_ODD_UNIT - 1) / SC_ODD_UNIT);
     } else if (row_chunks) {
         row_chunks[t] = 0;
     }
@@ -698,10 +703,15 @@ __global__ void __launch_bounds__(1024) k_chunk_fill(const uint32_t* __restrict_
 }
 
 // Stage 0 on the reachable odd columns (the reference's stride reaches them only behind a row's first non-skipping
-// window: ~16 % of the odd columns at 1080p, as ragged row suffixes).  Persistent warps pull 32-window runs from the
-// list k_row_events built, so the work is proportional to the windows, not to the tiles they are scattered over: the
-// tile kernel spent 0.074 ms/frame here on tiles holding two or three reachable rows.  Same arithmetic and decisions as
-// k_scan_stage0<FAST = true>: prefilter, certified fast filter, live records for what it leaves undecided.
+// window: ~16 % of the odd columns at 1080p, as ragged row suffixes).  Persistent warps pull units of up to SC_ODD_UNIT
+// consecutive odd windows of one row from the list k_row_events built, so the work is proportional to the windows, not
+// to the tiles they are scattered over.  Same arithmetic and decisions as k_scan_stage0<FAST = true>: prefilter (four
+// 32-window passes, bits assembled from the ballots), survivors compacted into a per-warp list, certified fast filter on
+// dense 32-window batches of that list, live records for what it leaves undecided.  The unit's bitmask words are
+// collected in shared memory and ORed into the global masks once (<= 9 + 9 atomics per unit instead of one per window).
+// The claim of the next unit (cursor atomic -> list entry -> row start: three dependent round trips to L2) is issued by
+// lane 0 before the current unit is processed and only broadcast afterwards.
+// (32-window units without compaction: 0.0495 ms/frame on C2, lanes 70 % busy in the filter.)
 template <int HP>
 __global__ void __launch_bounds__(256, SC_STAGE0_MIN_CTAS) k_scan_odd(const __grid_constant__ ScFastParams fp, const ScPlan* __restrict__ plan, const float4* __restrict__ S,
                                                                       const ScGeom* __restrict__ geom_all, const float* __restrict__ w_all,
@@ -710,76 +720,126 @@ __global__ void __launch_bounds__(256, SC_STAGE0_MIN_CTAS) k_scan_odd(const __gr
                                                                       uint32_t* __restrict__ rec_count, uint32_t rec_cap, const int* __restrict__ start_odd,
                                                                       const uint32_t* __restrict__ chunk_list, const uint32_t* __restrict__ chunk_count,
                                                                       uint32_t* __restrict__ cursor) {
-    const int lane = threadIdx.x & 31;
+    constexpr int NWARP = 8, WORDS = 2 * SC_ODD_UNIT / 32 + 2;  // a unit spans 2 * SC_ODD_UNIT lattice columns at an odd offset
+    __shared__ uint8_t s_q[NWARP][SC_ODD_UNIT];
+    __shared__ uint32_t s_mb[NWARP][WORDS], s_pb[NWARP][WORDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n_chunks = *chunk_count;
     const int rows = plan->rows_per_frame;
     const bool use_pf = plan->use_prefilter != 0;
     constexpr int ppitch = 2 * HP;
-    for (;;) {
-        uint32_t c = 0;
-        if (lane == 0) c = atomicAdd(cursor, 1u);
-        c = __shfl_sync(0xffffffffu, c, 0);
-        if (c >= n_chunks) break;
-        const uint32_t e = chunk_list[c];
+    const uint32_t lt = (1u << lane) - 1u;
+    // claim of a unit, lane 0 only: index, list entry, first reachable odd column of its row
+    uint32_t c = 0, e = 0;
+    int st0 = 0;
+    if (lane == 0) {
+        c = atomicAdd(cursor, 1u);
+        if (c < n_chunks) { e = chunk_list[c]; st0 = start_odd[e >> 10]; }
+    }
+    c = __shfl_sync(0xffffffffu, c, 0); e = __shfl_sync(0xffffffffu, e, 0); st0 = __shfl_sync(0xffffffffu, st0, 0);
+    while (c < n_chunks) {
+        uint32_t c2 = 0, e2 = 0;
+        int st2 = 0;
+        if (lane == 0) {  // next unit: in flight while this one is processed
+            c2 = atomicAdd(cursor, 1u);
+            if (c2 < n_chunks) { e2 = chunk_list[c2]; st2 = start_odd[e2 >> 10]; }
+        }
         const int t = (int)(e >> 10), k = (int)(e & 1023u);
         const int f = t / rows, r = t - f * rows;
         int si = 0;
-        while (si + 1 < plan->n_scales && plan->sc[si + 1].row_base <= r) si++;
+        while (si + 1 < fp.n_scales && fp.row_base[si + 1] <= r) si++;
         const ScScale* sc = &plan->sc[si];
-        const int gy = r - sc->row_base, nx = sc->nx;
-        const int gx = start_odd[t] + 2 * (32 * k + lane);
-        const bool valid = gx < nx;
-        const int j = gx >> 1;
-        const char* base = reinterpret_cast<const char*>(S + (size_t)f * plan->lay.frame4 + ((gy + sc->gy0) * ppitch + SC_COL(j)));
-        uint32_t* mw = multi_bits + (size_t)f * plan->words_per_frame + sc->word_base + (size_t)gy * sc->wpr + (gx >> 5);
-        uint32_t* pw = pass_bits + (size_t)f * plan->words_per_frame + sc->word_base + (size_t)gy * sc->wpr + (gx >> 5);
-        const uint32_t bit = 1u << (gx & 31);
-        bool pass = false;
-        if (valid) {
-            pass = use_pf ? (window_sum(base, sc->pf[1]) > sc->thr) : true;
-            if (pass) atomicOr(pw, bit);
-            else atomicOr(mw, bit);  // prefilter failed -> multi = 2 (ObjDetector.cpp:216-217)
-        }
-        bool exact = false;
-        if (pass) {
-            float sum = 0.f;
-#pragma unroll 1
-            for (int q = 0; q < fp.n_weak; q++) {
-                ScGeom g;
+        const int gy = r - fp.row_base[si], nx = sc->nx;
+        const int g0 = st0 + 2 * SC_ODD_UNIT * k;  // lattice column (odd) of the unit's first window
+        const float4* row4 = S + (size_t)f * plan->lay.frame4 + (size_t)(gy + sc->gy0) * ppitch;
+        const size_t word0 = (size_t)f * plan->words_per_frame + sc->word_base + (size_t)gy * sc->wpr + (g0 >> 5);
+        if (lane < WORDS) { s_mb[warp][lane] = 0; s_pb[warp][lane] = 0; }
+        __syncwarp();
+        // prefilter; pass / prefilter-failed bits of lane i sit at bit (gc & 31) + 2 i of the 96-bit run starting at word wb
+        int n = 0;
+        {
+            const float thr = sc->thr;
+            uint32_t pf[4];
 #pragma unroll
-                for (int i = 0; i < 10; i++) g.c[i] = fp.geom[si][q][i];
-                g.shape = (int)fp.geom[si][q][10]; g.pad = 0;
-                float v[32];
-                box_sums_p<HP>(base, g, HP, v);
-                sum = __fadd_rn(sum, fast_tail(v, fp.w[q], fp.wb[q]));
-            }
-            if (sum < fp.lim_reject && sum < fp.lim_skip) atomicOr(mw, bit);
-            else exact = !(sum < fp.lim_reject && sum >= fp.lim_noskip);
-        }
-        bool push = false;
-        ScRecord rc;
-        rc.fs = 0; rc.yx = 0; rc.rej = 0; rc.score = 0;
-        if (exact) {  // rare: left to the exact arithmetic of k_scan_stage(stage 0) as a live record
-            push = true;
-            rc.fs = ((uint32_t)f << 8) | (uint32_t)si;
-            rc.yx = ((uint32_t)gy << 16) | (uint32_t)gx;
-            rc.rej = -1;
-        }
-        const uint32_t m = __ballot_sync(0xffffffffu, push);
-        if (m) {
-            uint32_t slot0 = 0;
-            if (lane == 0) slot0 = atomicAdd(rec_count, __popc(m));
-            slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-            if (push) {
-                const uint32_t slot = slot0 + __popc(m & ((1u << lane) - 1u));
-                if (slot < rec_cap) rec[slot] = rc;
+            for (int i = 0; i < 4; i++) pf[i] = sc->pf[1][i];
+#pragma unroll
+            for (int ch = 0; ch < SC_ODD_UNIT / 32; ch++) {
+                const int gc = g0 + 64 * ch, gx = gc + 2 * lane;
+                const bool valid = gx < nx;
+                bool pass = false;
+                if (valid) pass = use_pf ? (window_sum(reinterpret_cast<const char*>(row4 + SC_COL(gx >> 1)), pf) > thr) : true;
+                const uint32_t m = __ballot_sync(0xffffffffu, pass);
+                const uint32_t fail = __ballot_sync(0xffffffffu, valid && !pass);
+                if (pass) s_q[warp][n + __popc(m & lt)] = (uint8_t)(32 * ch + lane);
+                n += __popc(m);
+                if (lane < 2) {  // lane 0: pass bits, lane 1: prefilter failed -> multi = 2 (ObjDetector.cpp:216-217)
+                    const uint32_t b = lane ? fail : m;
+                    const unsigned long long v = ((unsigned long long)spread16(b) | ((unsigned long long)spread16(b >> 16) << 32));
+                    const int sh = gc & 31, wb = (gc >> 5) - (g0 >> 5);  // sh is odd: never 0
+                    uint32_t* dst = lane ? s_mb[warp] : s_pb[warp];
+                    dst[wb] |= (uint32_t)(v << sh);
+                    dst[wb + 1] |= (uint32_t)(v >> (32 - sh));
+                    dst[wb + 2] |= (uint32_t)(v >> (64 - sh));
+                }
             }
         }
+        __syncwarp();
+        // certified fast filter on dense batches of the survivors
+        for (int b0 = 0; b0 < n; b0 += 32) {
+            const int ei = b0 + lane;
+            bool exact = false;
+            int gx = 0;
+            if (ei < n) {
+                gx = g0 + 2 * (int)s_q[warp][ei];
+                const char* base = reinterpret_cast<const char*>(row4 + SC_COL(gx >> 1));
+                float sum = 0.f;
+#pragma unroll 1
+                for (int q = 0; q < fp.n_weak; q++) {
+                    ScGeom g;
+#pragma unroll
+                    for (int i = 0; i < 10; i++) g.c[i] = fp.geom[si][q][i];
+                    g.shape = (int)fp.geom[si][q][10]; g.pad = 0;
+                    float v[32];
+                    box_sums_p<HP>(base, g, HP, v);
+                    sum = __fadd_rn(sum, fast_tail(v, fp.w[q], fp.wb[q]));
+                }
+                if (sum < fp.lim_reject && sum < fp.lim_skip) atomicOr(&s_mb[warp][(gx >> 5) - (g0 >> 5)], 1u << (gx & 31));
+                else exact = !(sum < fp.lim_reject && sum >= fp.lim_noskip);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, exact);
+            if (m) {  // rare: left to the exact arithmetic of k_scan_stage(stage 0) as live records
+                uint32_t slot0 = 0;
+                if (lane == 0) slot0 = atomicAdd(rec_count, __popc(m));
+                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                if (exact) {
+                    const uint32_t slot = slot0 + __popc(m & lt);
+                    if (slot < rec_cap) {
+                        ScRecord rc;
+                        rc.fs = ((uint32_t)f << 8) | (uint32_t)si;
+                        rc.yx = ((uint32_t)gy << 16) | (uint32_t)gx;
+                        rc.rej = -1; rc.score = 0;
+                        rec[slot] = rc;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane < WORDS) {
+            const uint32_t mb = s_mb[warp][lane], pb = s_pb[warp][lane];
+            if (mb) atomicOr(&multi_bits[word0 + lane], mb);
+            if (pb) atomicOr(&pass_bits[word0 + lane], pb);
+        }
+        __syncwarp();
+        c = __shfl_sync(0xffffffffu, c2, 0); e = __shfl_sync(0xffffffffu, e2, 0); st0 = __shfl_sync(0xffffffffu, st2, 0);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Stages 1..N-1 on compacted index lists
+// Stages 1..N-1 (and, behind the fast filter, the exact stage 0) on compacted index lists.
+// One thread per surviving window by default (lg = 0).  With lg > 0 a window's stage is spread over 2^lg lanes: lane j of
+// the group evaluates weak classifiers j, j + 2^lg, ..., and the group then adds the outputs IN THE REFERENCE'S ORDER
+// (GentleAdaboost.cpp:253-256) through shuffles, so the stage score is bit-identical.  Measured on C2 it is slower (see
+// run_group in sc_capi.cu): the kernel is bound by L1 wavefronts of uncoalesced 16-byte gathers, not by the serial chain.
 // ---------------------------------------------------------------------------------------------------------
 template <int HP>
 __global__ void __launch_bounds__(128) k_scan_stage(const ScPlan* __restrict__ plan, int stage, const float4* __restrict__ S,
@@ -787,7 +847,7 @@ __global__ void __launch_bounds__(128) k_scan_stage(const ScPlan* __restrict__ p
                                                      const double* __restrict__ wb_all, uint32_t* __restrict__ multi_bits,
                                                      ScRecord* __restrict__ rec, const uint32_t* __restrict__ in_idx,
                                                      const uint32_t* __restrict__ in_count, uint32_t* __restrict__ out_idx,
-                                                     uint32_t* __restrict__ out_count, uint32_t cap) {
+                                                     uint32_t* __restrict__ out_count, uint32_t cap, int lg) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     const int n_weak = plan->n_weak[stage], wbase = plan->weak_base[stage], total_weak = plan->total_weak;
     float* sw = reinterpret_cast<float*>(s_dyn);
@@ -801,19 +861,37 @@ __global__ void __launch_bounds__(128) k_scan_stage(const ScPlan* __restrict__ p
     const bool force = plan->force_all != 0, last = stage == n_stages - 1;
     const float theta = plan->theta[stage];
     const int lane = threadIdx.x & 31;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < count; i0 += stride) {
-        const uint32_t i = i0 + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long n_items = (unsigned long long)count << lg;
+    const int nwp = 1 << lg, sub = lane & (nwp - 1), lead = lane & ~(nwp - 1);
+    for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x; i0 < n_items; i0 += stride) {  // warp-uniform trip count
+        const uint32_t i = (uint32_t)((i0 + threadIdx.x) >> lg);
         bool push = false;
         uint32_t idx = 0;
+        ScRecord r;
+        r.fs = 0; r.yx = 0; r.rej = 0; r.score = 0;
+        const char* base = nullptr;
+        const ScGeom* geom = geom_all;
         if (i < count) {
             idx = in_idx ? in_idx[i] : i;
-            ScRecord r = rec[idx];
+            r = rec[idx];
             const int f = r.fs >> 8, si = r.fs & 0xff;
             const int gy = r.yx >> 16, gx = r.yx & 0xffff;
-            const float4* lo4 = S + (size_t)f * plan->lay.frame4;
-            const float score = stage_score<HP>(reinterpret_cast<const char*>(lo4 + ((gy + plan->sc[si].gy0) * ppitch + SC_COL(gx >> 1))),
-                                                geom_all + ((size_t)(gx & 1) * plan->n_scales + si) * total_weak + wbase, sw, swb, n_weak, HP);
+            base = reinterpret_cast<const char*>(S + (size_t)f * plan->lay.frame4 + ((gy + plan->sc[si].gy0) * ppitch + SC_COL(gx >> 1)));
+            geom = geom_all + ((size_t)(gx & 1) * plan->n_scales + si) * total_weak + wbase;
+        }
+        float acc = 0.f;
+        for (int q0 = 0; q0 < n_weak; q0 += nwp) {
+            const int q = q0 + sub;
+            float p = 0.f;
+            if (i < count && q < n_weak) p = weak_output<HP>(base, geom, sw, swb, q, HP);
+            const int nj = min(nwp, n_weak - q0);
+            for (int j = 0; j < nj; j++) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, p, lead + j));
+        }
+        if (i < count && sub == 0) {
+            const float score = __fdiv_rn(acc, (float)n_weak);
+            const int f = r.fs >> 8, si = r.fs & 0xff;
+            const int gy = r.yx >> 16, gx = r.yx & 0xffff;
             if (r.rej < 0) {
                 const bool rejected = score < theta;
                 if (rejected) {
@@ -833,11 +911,11 @@ __global__ void __launch_bounds__(128) k_scan_stage(const ScPlan* __restrict__ p
         }
         const uint32_t m = __ballot_sync(0xffffffffu, push);
         if (m) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(out_count, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
+            uint32_t slot0 = 0;
+            if (lane == 0) slot0 = atomicAdd(out_count, __popc(m));
+            slot0 = __shfl_sync(0xffffffffu, slot0, 0);
             if (push) {
-                const uint32_t slot = base + __popc(m & ((1u << lane) - 1u));
+                const uint32_t slot = slot0 + __popc(m & ((1u << lane) - 1u));
                 if (slot < cap) out_idx[slot] = idx;
             }
         }

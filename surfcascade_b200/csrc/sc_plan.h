@@ -14,7 +14,7 @@
 // (phase 0) and the odd columns only from that window on (phase 1), about 56-58 % of the lattice at 1080p.
 #define SC_TILE_X 64
 #ifndef SC_TILE_Y
-#define SC_TILE_Y 16
+#define SC_TILE_Y 32          // measured on C2: 8 -> 0.270, 16 -> 0.2525, 32 -> 0.2477, 64 -> 0.325 ms/frame (even columns)
 #endif
 #ifndef SC_TILE_THREADS
 #define SC_TILE_THREADS 256   // SC_TILE_Y must be a multiple of the warp count; 4 * SC_TILE_Y <= SC_TILE_THREADS
@@ -26,6 +26,10 @@
 #ifndef SC_FAST_MIN_CTAS
 #define SC_FAST_MIN_CTAS 4     // the fast-filter kernel holds no exact arithmetic: 64 registers, 4 CTAs (32 warps) per SM
 #endif
+
+// k_scan_odd work unit: a run of up to SC_ODD_UNIT reachable odd-column windows of one lattice row (one warp per unit:
+// prefilter in four 32-window passes, the survivors compacted into a dense list for the fast filter).
+#define SC_ODD_UNIT 128
 
 // Integral strips: one warp walks one 32-column strip down the frame, SC_WALK_RB rows per prefetch block.
 #define SC_STRIP 32
@@ -127,6 +131,7 @@ struct ScFastParams {
     float lim_reject, lim_skip, lim_noskip, pad1;
     float wb[8];                                         // float(w[32] * bias)
     int block_base[SC_PLAN_MAX_SCALES];                  // first stage-0 CTA of every scale inside a frame
+    int row_base[SC_PLAN_MAX_SCALES];                    // first lattice row of every scale inside a frame (k_scan_odd)
     float w[SC_F_MAXW][32];
     uint32_t geom[SC_PLAN_MAX_SCALES][SC_F_MAXW][12];    // ScGeom of (this launch's column parity, scale, weak)
 };
