@@ -507,8 +507,12 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, FAST ? SC_FAST_MIN_CTAS : SC_
             if (lane == 0) {
                 s_pass[row][2 * half] = spread16(m) << phase;
                 s_pass[row][2 * half + 1] = spread16(m >> 16) << phase;
-                s_multi[row][2 * half] = spread16(fail) << phase;  // prefilter failed -> multi = 2 (ObjDetector.cpp:216-217)
-                s_multi[row][2 * half + 1] = spread16(fail >> 16) << phase;
+                // prefilter failed -> multi = 2 (ObjDetector.cpp:216-217).  FAST: the windows that pass start with their bit
+                // set too -- 99.7 % of them are rejected with multi = 2 -- and the filter CLEARS the bit of the few it
+                // cannot decide or that do not skip: one shared-memory atomic per ~300 windows instead of one per window
+                const uint32_t mb = FAST ? (fail | m) : fail;
+                s_multi[row][2 * half] = spread16(mb) << phase;
+                s_multi[row][2 * half + 1] = spread16(mb >> 16) << phase;
                 base = atomicAdd(&s_count, __popc(m));
             }
             base = __shfl_sync(0xffffffffu, base, 0);
@@ -523,7 +527,7 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, FAST ? SC_FAST_MIN_CTAS : SC_
         for (uint32_t i0 = 0; i0 < n_pass; i0 += SC_TILE_THREADS) {
             const uint32_t i = i0 + tid;
             bool undecided = false;
-            uint32_t code = 0, word = 0xffffffffu, bit = 0;
+            uint32_t code = 0;
             if (i < n_pass) {
                 code = s_list[i];
                 const int row = code >> 6, half = (code >> 5) & 1, ln = code & 31;
@@ -541,10 +545,11 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, FAST ? SC_FAST_MIN_CTAS : SC_
                     box_sums_p<HP>(base, g, HP, v);
                     sum = __fadd_rn(sum, fast_tail(v, fp.w[q], fp.wb[q]));
                 }
-                if (sum < fp.lim_reject && sum < fp.lim_skip) { word = (uint32_t)(row * 4 + 2 * half + (ln >> 4)); bit = 1u << (2 * (ln & 15) + phase); }
-                else undecided = !(sum < fp.lim_reject && sum >= fp.lim_noskip);
+                if (!(sum < fp.lim_reject && sum < fp.lim_skip)) {  // not "rejected and skips for certain": rare
+                    atomicAnd(&s_multi[row][2 * half + (ln >> 4)], ~(1u << (2 * (ln & 15) + phase)));
+                    undecided = !(sum < fp.lim_reject && sum >= fp.lim_noskip);
+                }
             }
-            if (bit) atomicOr(&s_multi[word >> 2][word & 3], bit);  // (warp-aggregating these -- match.any + REDUX, or run heads + REDUX -- measured slower: the kernel sits at 64 registers)
             const uint32_t m = __ballot_sync(0xffffffffu, undecided);
             if (m) {
                 uint32_t base2 = 0;
@@ -772,8 +777,9 @@ __global__ void __launch_bounds__(256, SC_STAGE0_MIN_CTAS) k_scan_odd(const __gr
                 const uint32_t fail = __ballot_sync(0xffffffffu, valid && !pass);
                 if (pass) s_q[warp][n + __popc(m & lt)] = (uint8_t)(32 * ch + lane);
                 n += __popc(m);
-                if (lane < 2) {  // lane 0: pass bits, lane 1: prefilter failed -> multi = 2 (ObjDetector.cpp:216-217)
-                    const uint32_t b = lane ? fail : m;
+                if (lane < 2) {  // lane 0: pass bits; lane 1: multi bits = prefilter failed (ObjDetector.cpp:216-217) or passed --
+                                 // the filter below clears the bit of the few survivors that are not "rejected and skip"
+                    const uint32_t b = lane ? (fail | m) : m;
                     const unsigned long long v = ((unsigned long long)spread16(b) | ((unsigned long long)spread16(b >> 16) << 32));
                     const int sh = gc & 31, wb = (gc >> 5) - (g0 >> 5);  // sh is odd: never 0
                     uint32_t* dst = lane ? s_mb[warp] : s_pb[warp];
@@ -803,8 +809,10 @@ __global__ void __launch_bounds__(256, SC_STAGE0_MIN_CTAS) k_scan_odd(const __gr
                     box_sums_p<HP>(base, g, HP, v);
                     sum = __fadd_rn(sum, fast_tail(v, fp.w[q], fp.wb[q]));
                 }
-                if (sum < fp.lim_reject && sum < fp.lim_skip) atomicOr(&s_mb[warp][(gx >> 5) - (g0 >> 5)], 1u << (gx & 31));
-                else exact = !(sum < fp.lim_reject && sum >= fp.lim_noskip);
+                if (!(sum < fp.lim_reject && sum < fp.lim_skip)) {
+                    atomicAnd(&s_mb[warp][(gx >> 5) - (g0 >> 5)], ~(1u << (gx & 31)));
+                    exact = !(sum < fp.lim_reject && sum >= fp.lim_noskip);
+                }
             }
             const uint32_t m = __ballot_sync(0xffffffffu, exact);
             if (m) {  // rare: left to the exact arithmetic of k_scan_stage(stage 0) as live records
