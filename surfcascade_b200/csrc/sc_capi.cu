@@ -82,6 +82,7 @@ struct sc_handle {
     bool allow_fast = true;     // SC_DISABLE_FAST=1 in the environment forces the exact-only kernel (A/B tests)
     bool use_fast = false;
     ScFastParams fast[2];
+    int group_max = 8;  // frames per scan group (SC_GROUP_FRAMES overrides, 1..32)
     int stage_lg = 0;  // log2 of the lanes per window in k_scan_stage (SC_STAGE_LG, experiments)
 
     // group buffers
@@ -96,7 +97,8 @@ struct sc_handle {
         cudaEvent_t done = nullptr;
         DevBuf d_multi, d_pass, d_visited, d_start, d_rec, d_idx[2], d_small, d_chunks;  // d_chunks: work list of k_scan_odd (32-window runs of reachable odd columns)
     };
-    Lane lanes[2];
+    Lane lanes[4];
+    int lanes_max = 4;  // scan groups in flight, one stream each (SC_LANES overrides, 1..4; C2: 2 -> 3068, 4 -> 3095 frames/s)
     int n_lanes = 0;
     cudaEvent_t ev_integral = nullptr;
     std::vector<cudaEvent_t> ev_chunk;   // per pipeline chunk: [2c] upload done, [2c+1] integral done
@@ -333,7 +335,7 @@ int ensure_group_buffers(sc_handle* h, int want_frames, bool own_images) {
     const size_t per_rec = sizeof(ScRecord) + 2 * sizeof(uint32_t);
     const size_t per_frame = (size_t)p.lay.frame4 * 16 + (size_t)p.windows_per_frame * per_rec + (size_t)p.words_per_frame * 12 +
                              (size_t)p.H * p.n_strips * 32 + (size_t)p.W * p.H;
-    int g = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)6 << 30) / std::max<size_t>(per_frame, 1)));
+    int g = (int)std::max<size_t>(1, std::min<size_t>((size_t)h->group_max, ((size_t)6 << 30) / std::max<size_t>(per_frame, 1)));
     g = std::min(g, std::max(want_frames, 1));
     // the integral stage runs on a larger super-group (its warps walk rows sequentially and need many frames in flight)
     const size_t int_frame = (size_t)p.lay.frame4 * 16 + (size_t)p.H * p.n_strips * 32 + (size_t)p.W * p.H;
@@ -343,7 +345,7 @@ int ensure_group_buffers(sc_handle* h, int want_frames, bool own_images) {
     gi = std::max(gi, h->int_frames);
     const unsigned long long recs = (unsigned long long)p.windows_per_frame * g;
     if (recs > 0xfffffff0ull) return fail(h, SC_ERR_INVALID, "too many windows per group");
-    const int want_lanes = std::max(h->n_lanes, (want_frames > g && recs * per_rec < ((size_t)3 << 30)) ? 2 : 1);
+    const int want_lanes = std::max(h->n_lanes, (want_frames > g && recs * per_rec < ((size_t)3 << 30)) ? std::min(h->lanes_max, (want_frames + g - 1) / g) : 1);
     if (g <= h->group_frames && gi <= h->int_frames && want_lanes <= h->n_lanes) return SC_OK;
     if (own_images) SC_CUDA(h, h->d_img.ensure(align256((size_t)gi * p.W * p.H)));
     SC_CUDA(h, h->d_carry.ensure(align256((size_t)gi * p.H * p.n_strips * 32)));
@@ -634,6 +636,10 @@ int sc_create(int device, sc_handle** out) {
     cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device);
     const char* nofast = getenv("SC_DISABLE_FAST");
     h->allow_fast = !(nofast && nofast[0] == '1');
+    const char* sgf = getenv("SC_GROUP_FRAMES");
+    if (sgf) h->group_max = std::min(32, std::max(1, atoi(sgf)));
+    const char* sln = getenv("SC_LANES");
+    if (sln) h->lanes_max = std::min(4, std::max(1, atoi(sln)));
     const char* slg = getenv("SC_STAGE_LG");
     h->stage_lg = slg ? std::min(5, std::max(0, atoi(slg))) : 0;
     *out = h;
