@@ -83,7 +83,6 @@ struct sc_handle {
     bool use_fast = false;
     ScFastParams fast[2];
     int group_max = 8;  // frames per scan group (SC_GROUP_FRAMES overrides, 1..32)
-    int stage_lg = 0;  // log2 of the lanes per window in k_scan_stage (SC_STAGE_LG, experiments)
 
     // group buffers
     int group_frames = 0;       // frames one scan group holds (records, bitmasks)
@@ -240,6 +239,9 @@ int build_plan(sc_handle* h, int W, int H, const sc_detect_params& prm, std::vec
     if ((int)sides.size() > SC_PLAN_MAX_SCALES) return fail(h, SC_ERR_INVALID, "too many scales (max 64)");
     int nsc = 0, blocks = 0, words = 0, rows = 0;
     long long windows = 0;
+    // the fast-filter variant of the stage-0 kernel is used whenever it applies (below); its tiles are taller (sc_plan.h)
+    const bool fast_plan = h->allow_fast && !p.force_all && h->n_stages > 0 && h->n_weak[0] <= SC_F_MAXW;
+    const int tile_y = fast_plan ? SC_TILE_Y_FAST : SC_TILE_Y_EXACT;
     for (size_t i = 0; i < sides.size(); i++) {
         const int l = sides[i];
         if (l > W || l > H) continue;
@@ -253,7 +255,7 @@ int build_plan(sc_handle* h, int W, int H, const sc_detect_params& prm, std::vec
         s.wpr = (s.nx + 31) / 32;
         s.thr = (float)(l * l * (prm.prefilter >= 0 ? prm.prefilter : 0));
         s.tiles_x = ((s.nx + 1) / 2 + SC_TILE_X - 1) / SC_TILE_X;  // tiles of 64 same-parity columns
-        const int tiles_y = (s.ny + SC_TILE_Y - 1) / SC_TILE_Y;
+        const int tiles_y = (s.ny + tile_y - 1) / tile_y;
         s.block_base = blocks; s.word_base = words; s.row_base = rows;
         for (int ph = 0; ph < 2; ph++) {
             const int x0 = ph * p.step;
@@ -280,7 +282,7 @@ int build_plan(sc_handle* h, int W, int H, const sc_detect_params& prm, std::vec
 
     // Certified fast filter for stage 0 (sc_kernels.cuh, "Error budget").  Limits are on the float sum of the fast weak outputs.
     const int n0 = h->n_weak[0];
-    h->use_fast = h->allow_fast && !p.force_all && n0 <= SC_F_MAXW && nsc >= 1;
+    h->use_fast = fast_plan && nsc >= 1;
     if (h->use_fast) {
         const double margin = fast_margin(h);
         const double tau = 0.5 * h->n_stages - 1.0;           // rejected at stage 0: multi == 2  <=>  score < tau (ObjDetector.cpp:201,214)
@@ -485,15 +487,9 @@ int run_group(sc_handle* h, sc_handle::Lane& L, int s0, int g, int frame0, sc_de
             const uint32_t* in_idx = first ? nullptr : L.d_idx[(s - 1) & 1].as<uint32_t>();
             const uint32_t* in_cnt = first ? small + SM_REC : small + SM_STAGE0 + (s - 1);
             const size_t smem = (size_t)p.n_weak[s] * (SC_W_PITCH * 4 + 8);
-            // lanes per surviving window (k_scan_stage): 0 = one thread per window.  Spreading a window's weak classifiers
-            // over 2^lg lanes was measured slower on C2 (0.0247 -> 0.0269 ms/frame): the survivors' gathers are one L1
-            // wavefront per lane either way, and fewer windows per warp lose the lines x-adjacent survivors share.
-            // SC_STAGE_LG=n overrides for experiments.
-            int lg = 0;
-            if (h->stage_lg > 0 && !p.force_all) while ((1 << lg) < p.n_weak[s] && lg < h->stage_lg) lg++;
             KernelSpan ks(h, K_STAGE, st);
             launch_stage(p.lay.hp, tail_grid, smem, st, dp, s, S, geom, w, wb, multi, rec, in_idx, in_cnt, L.d_idx[s & 1].as<uint32_t>(),
-                         small + SM_STAGE0 + s, h->rec_cap, lg);
+                         small + SM_STAGE0 + s, h->rec_cap);
         }
         const int rows = g * p.rows_per_frame;
         { KernelSpan ks(h, K_REPLAY, st); sck::k_replay_rows<<<(rows + 127) / 128, 128, 0, st>>>(dp, g, multi, pass, visited, d_counters); }
@@ -515,12 +511,14 @@ int run_group(sc_handle* h, sc_handle::Lane& L, int s0, int g, int frame0, sc_de
 // so the upload and the integral of chunk c+1 run under the scan of chunk c.
 #define SC_ICHUNK 16   // measured: 8-frame chunks lose more in the integral kernel than the upload overlap gains
 int run_supergroup(sc_handle* h, const uint8_t* const* frames, int stride, const uint8_t* d_frames, int ni, int frame0, sc_detection* d_det,
-                   uint32_t det_cap, uint32_t* d_det_count, unsigned long long* d_counters, uint8_t* img_buf = nullptr, bool img_buf_busy = true) {
+                   uint32_t det_cap, uint32_t* d_det_count, unsigned long long* d_counters, uint8_t* img_buf = nullptr, bool img_buf_busy = true,
+                   bool uploads_hidden = false) {
     const ScPlan& p = h->plan;
     const int lanes = h->profiling ? 1 : h->n_lanes;  // per-kernel event timing wants the kernels back to back
     // device-resident frames: one integral launch over the whole super-group is fastest (nothing to overlap it with
     // but the scan, which it only slows down); host frames: chunks, so that uploads hide under the scan
-    const int ich = (h->profiling || !frames) ? ni : SC_ICHUNK;
+    // (uploads_hidden: another batch is computing, so this batch's uploads already run under it -- sc_detect_submit)
+    const int ich = (h->profiling || !frames || uploads_hidden) ? ni : SC_ICHUNK;
     const int nch = (ni + ich - 1) / ich;
     while ((int)h->ev_chunk.size() < 2 * nch) {
         cudaEvent_t e = nullptr;
@@ -640,8 +638,6 @@ int sc_create(int device, sc_handle** out) {
     if (sgf) h->group_max = std::min(32, std::max(1, atoi(sgf)));
     const char* sln = getenv("SC_LANES");
     if (sln) h->lanes_max = std::min(4, std::max(1, atoi(sln)));
-    const char* slg = getenv("SC_STAGE_LG");
-    h->stage_lg = slg ? std::min(5, std::max(0, atoi(slg))) : 0;
     *out = h;
     return SC_OK;
 }
@@ -1202,7 +1198,7 @@ int sc_detect_submit(sc_handle* h, const uint8_t* const* frames, int nframes, in
         // the ticket's image buffer is free when the call starts (its previous batch was collected); later super-groups of
         // the same call reuse it and must wait for the integral that still reads it
         rc = run_supergroup(h, frames + i0, stride, nullptr, ni, i0, t.d_det.as<sc_detection>(), t.det_cap, t.d_cnt.as<uint32_t>(),
-                            t.d_counters.as<unsigned long long>() + (size_t)i0 * SC_CNT_STRIDE, t.d_img.as<uint8_t>(), i0 > 0);
+                            t.d_counters.as<unsigned long long>() + (size_t)i0 * SC_CNT_STRIDE, t.d_img.as<uint8_t>(), i0 > 0, other_busy);
         if (rc != SC_OK) return rc;
     }
     unsigned char* ho = t.h_out.as<unsigned char>();

@@ -435,6 +435,7 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, FAST ? SC_FAST_MIN_CTAS : SC_
                                                                   uint32_t* __restrict__ pass_bits, ScRecord* __restrict__ rec,
                                                                   uint32_t* __restrict__ rec_count, uint32_t rec_cap, int phase,
                                                                   const int* __restrict__ start_odd) {
+    constexpr int SC_TILE_Y = FAST ? SC_TILE_Y_FAST : SC_TILE_Y_EXACT;  // tile rows of this variant (sc_plan.h)
     const uint32_t block = blockIdx.x;
     __shared__ uint32_t s_multi[SC_TILE_Y][4];
     __shared__ uint32_t s_pass[SC_TILE_Y][4];
@@ -843,11 +844,11 @@ __global__ void __launch_bounds__(256, SC_STAGE0_MIN_CTAS) k_scan_odd(const __gr
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Stages 1..N-1 (and, behind the fast filter, the exact stage 0) on compacted index lists.
-// One thread per surviving window by default (lg = 0).  With lg > 0 a window's stage is spread over 2^lg lanes: lane j of
-// the group evaluates weak classifiers j, j + 2^lg, ..., and the group then adds the outputs IN THE REFERENCE'S ORDER
-// (GentleAdaboost.cpp:253-256) through shuffles, so the stage score is bit-identical.  Measured on C2 it is slower (see
-// run_group in sc_capi.cu): the kernel is bound by L1 wavefronts of uncoalesced 16-byte gathers, not by the serial chain.
+// Stages 1..N-1 (and, behind the fast filter, the exact stage 0) on compacted index lists, one thread per window.
+// (Spreading a window's weak classifiers over 2..8 lanes and adding their outputs in the reference's order through
+// shuffles was measured slower, 0.0247 -> 0.0269 ms/frame on C2 and +9 % on C4: ncu shows the kernel waiting on scattered
+// 32-byte sector reads -- DRAM 50 % busy at 0.35 GB per launch, L2 hit rate 35 % because the 8 integral images of a scan
+// group have left L2 by then -- not on the serial chain, and fewer windows per warp lose the lines x-adjacent survivors share.)
 // ---------------------------------------------------------------------------------------------------------
 template <int HP>
 __global__ void __launch_bounds__(128) k_scan_stage(const ScPlan* __restrict__ plan, int stage, const float4* __restrict__ S,
@@ -855,7 +856,7 @@ __global__ void __launch_bounds__(128) k_scan_stage(const ScPlan* __restrict__ p
                                                      const double* __restrict__ wb_all, uint32_t* __restrict__ multi_bits,
                                                      ScRecord* __restrict__ rec, const uint32_t* __restrict__ in_idx,
                                                      const uint32_t* __restrict__ in_count, uint32_t* __restrict__ out_idx,
-                                                     uint32_t* __restrict__ out_count, uint32_t cap, int lg) {
+                                                     uint32_t* __restrict__ out_count, uint32_t cap) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     const int n_weak = plan->n_weak[stage], wbase = plan->weak_base[stage], total_weak = plan->total_weak;
     float* sw = reinterpret_cast<float*>(s_dyn);
@@ -869,37 +870,19 @@ __global__ void __launch_bounds__(128) k_scan_stage(const ScPlan* __restrict__ p
     const bool force = plan->force_all != 0, last = stage == n_stages - 1;
     const float theta = plan->theta[stage];
     const int lane = threadIdx.x & 31;
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    const unsigned long long n_items = (unsigned long long)count << lg;
-    const int nwp = 1 << lg, sub = lane & (nwp - 1), lead = lane & ~(nwp - 1);
-    for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x; i0 < n_items; i0 += stride) {  // warp-uniform trip count
-        const uint32_t i = (uint32_t)((i0 + threadIdx.x) >> lg);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < count; i0 += stride) {
+        const uint32_t i = i0 + threadIdx.x;
         bool push = false;
         uint32_t idx = 0;
-        ScRecord r;
-        r.fs = 0; r.yx = 0; r.rej = 0; r.score = 0;
-        const char* base = nullptr;
-        const ScGeom* geom = geom_all;
         if (i < count) {
             idx = in_idx ? in_idx[i] : i;
-            r = rec[idx];
+            ScRecord r = rec[idx];
             const int f = r.fs >> 8, si = r.fs & 0xff;
             const int gy = r.yx >> 16, gx = r.yx & 0xffff;
-            base = reinterpret_cast<const char*>(S + (size_t)f * plan->lay.frame4 + ((gy + plan->sc[si].gy0) * ppitch + SC_COL(gx >> 1)));
-            geom = geom_all + ((size_t)(gx & 1) * plan->n_scales + si) * total_weak + wbase;
-        }
-        float acc = 0.f;
-        for (int q0 = 0; q0 < n_weak; q0 += nwp) {
-            const int q = q0 + sub;
-            float p = 0.f;
-            if (i < count && q < n_weak) p = weak_output<HP>(base, geom, sw, swb, q, HP);
-            const int nj = min(nwp, n_weak - q0);
-            for (int j = 0; j < nj; j++) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, p, lead + j));
-        }
-        if (i < count && sub == 0) {
-            const float score = __fdiv_rn(acc, (float)n_weak);
-            const int f = r.fs >> 8, si = r.fs & 0xff;
-            const int gy = r.yx >> 16, gx = r.yx & 0xffff;
+            const float4* lo4 = S + (size_t)f * plan->lay.frame4;
+            const float score = stage_score<HP>(reinterpret_cast<const char*>(lo4 + ((gy + plan->sc[si].gy0) * ppitch + SC_COL(gx >> 1))),
+                                                geom_all + ((size_t)(gx & 1) * plan->n_scales + si) * total_weak + wbase, sw, swb, n_weak, HP);
             if (r.rej < 0) {
                 const bool rejected = score < theta;
                 if (rejected) {

@@ -13,11 +13,17 @@
 // the even columns until the first window that does not skip; the scan therefore evaluates the even columns first
 // (phase 0) and the odd columns only from that window on (phase 1), about 56-58 % of the lattice at 1080p.
 #define SC_TILE_X 64
-#ifndef SC_TILE_Y
-#define SC_TILE_Y 32          // measured on C2: 8 -> 0.270, 16 -> 0.2525, 32 -> 0.2477, 64 -> 0.325 ms/frame (even columns)
+// Tile rows: 32 for the fast-filter variant (measured on C2: 8 -> 0.270, 16 -> 0.2525, 32 -> 0.2477, 64 -> 0.325 ms/frame for
+// the even columns), 16 for the exact variant (force_all / more than SC_F_MAXW weak classifiers in stage 0; on C4 the
+// record order of 32-row tiles costs the later stages 7 %).
+#ifndef SC_TILE_Y_FAST
+#define SC_TILE_Y_FAST 32
+#endif
+#ifndef SC_TILE_Y_EXACT
+#define SC_TILE_Y_EXACT 16
 #endif
 #ifndef SC_TILE_THREADS
-#define SC_TILE_THREADS 256   // SC_TILE_Y must be a multiple of the warp count; 4 * SC_TILE_Y <= SC_TILE_THREADS
+#define SC_TILE_THREADS 256   // tile rows must be a multiple of the warp count; 4 * rows <= SC_TILE_THREADS
 #endif
 #ifndef SC_STAGE0_MIN_CTAS
 #define SC_STAGE0_MIN_CTAS 3   // 80 registers: 3 CTAs (24 warps) per SM; 4 forces 64 registers and spills (measured slower)
