@@ -374,7 +374,7 @@ def run_ours(args):
                          "l2_to_l1_bytes_per_launch": l2_bytes_ev, "l2_to_l1_achieved_gbs": l2_meas_gbs,
                          "stream_probe_gbs": l2_peak,
                          "hbm_peak": peak, "achieved_over_hbm_peak": (scan_gbs / peak) if scan_gbs else None,
-                         "note": "gather-bound scan (SURVEY.md 8d): `achieved` = algorithmic corner bytes 32 B x (4 x reference-visited windows + 10 x reference weak evaluations) per frame / CUDA-event time of both stage-0 kernels. They are served by L1 (~15 % hits) and L2, not HBM (" + peak_src + ", given for scale only: DRAM is ~5 % busy), so the roof is the L1TEX data pipe every 16-byte-per-lane load goes through. ncu on the even-column launch (profiles/r1_ncu_scan_final.txt): that pipe is 88 % busy -- a 512-byte warp load costs 5.6 wavefronts instead of the ideal 4 (misaligned start, fills of the 85 % that miss) -- LTS 75 %, issue 57 %. `l2_to_l1_achieved_gbs` = sectors L2 delivered in that launch (ncu l1tex__m_xbar2l1tex_read_bytes) / the launch's live duration; `stream_probe_gbs` = sc_probe_stream, coalesced 16-byte loads over a 32 MB table, measured live (an L1-resident table gives the same figure: the probe is LSU-bound, so it is a reference point, not a ceiling)",
+                         "note": "gather-bound scan (SURVEY.md 8d): `achieved` = algorithmic corner bytes 32 B x (4 x reference-visited windows + 10 x reference weak evaluations) per frame / CUDA-event time of both stage-0 kernels. They are served by L1 and L2, not HBM (" + peak_src + ", given for scale only), so the roof is the L1TEX data pipe every 16-byte-per-lane load goes through. ncu on the even-column launch (profiles/r1_ncu_scan_final.txt, figures in ncu_pct_of_peak_even_launch): that pipe is the busiest unit -- a 512-byte warp load costs 5.6-5.9 wavefronts instead of the ideal 4 (the run starts at an arbitrary 16-byte offset and the compacted lanes span ~38 lattice positions; the ~85 % of sectors that miss are filled through the same pipe) -- then LTS, then issue. `l2_to_l1_achieved_gbs` = sectors L2 delivered in that launch (ncu l1tex__m_xbar2l1tex_read_bytes) / the launch's live duration; `stream_probe_gbs` = sc_probe_stream, coalesced 16-byte loads over a 32 MB table, measured live (an L1-resident table gives the same figure: the probe is LSU-bound, so it is a reference point, not a ceiling)",
                          "share_of_step": st0_ms / total_k_ms},
             "roofline_integral": {"kernel": "k_strip_carry+k_integral_walk", "bound": "hbm", "achieved": int_gbs, "peak": peak, "unit": "GB/s",
                                   "frac": (int_gbs / peak) if int_gbs else None, "traffic": traffic_int,
