@@ -117,6 +117,10 @@ int sc_project_patches(int tmpl, int l, const sc_rect* patches, int n, sc_rect* 
  * H x W (row stride in bytes) -> the (H+1) x (W+1) x 8 float32 interleaved integral, kept on the device for the
  * calls below and, when out is non-null, copied to the host. */
 int sc_integral(sc_handle* h, const uint8_t* gray, int W, int H, int stride, float* out);
+/* The same image through the memory layout the cascade scan reads for lattice step `step` (the kernels and layout of
+ * sc_detect's integral stage; sc_integral keeps a step-1 layout for explicit rects), copied to the host in the reference's
+ * interleaved form.  Parity hook for IntegralImage (DenseSURFFeatureExtractor.cpp:65-87) on the production path. */
+int sc_integral_scan_layout(sc_handle* h, const uint8_t* gray, int W, int H, int stride, int step, float* out);
 /* DenseSURFFeatureExtractor::CalcFeature (+GetRectsFromPatch, Normalize; :360-457) on the current integral. */
 int sc_features(sc_handle* h, const sc_rect* rects, int n, float* out /* [n][32] */);
 /* DenseSURFFeatureExtractor::sum (:351-358). */

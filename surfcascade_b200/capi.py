@@ -44,7 +44,7 @@ EXPORTS = ["sc_create", "sc_destroy", "sc_last_error", "sc_version", "sc_set_cas
            "sc_integral", "sc_features", "sc_window_sum", "sc_stage_scores", "sc_weak_predict", "sc_stage_predict", "sc_detect",
            "sc_detect_device", "sc_sync", "sc_last_counters", "sc_stream", "sc_launch_count", "sc_group_rectangles",
            "sc_set_profiling", "sc_kernel_stats", "sc_model_flatten", "sc_model_resave", "sc_pool_eval", "sc_pool_hist_device",
-           "sc_pool_auc_device", "sc_probe_gather", "sc_probe_stream", "sc_stage0_fast_check", "sc_detect_submit", "sc_detect_collect", "sc_extract_pool_features", "sc_extract_pool_features_device", "sc_mine_negatives"]
+           "sc_pool_auc_device", "sc_probe_gather", "sc_probe_stream", "sc_stage0_fast_check", "sc_detect_submit", "sc_detect_collect", "sc_extract_pool_features", "sc_extract_pool_features_device", "sc_mine_negatives", "sc_integral_scan_layout"]
 
 _lib = None
 
@@ -76,6 +76,7 @@ def lib():
         L.sc_pool_patches.argtypes = [C.c_int, C.c_void_p, C.c_int]
         L.sc_project_patches.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.sc_integral.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.sc_integral_scan_layout.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.sc_features.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.sc_window_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.sc_stage_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -211,6 +212,14 @@ class Handle:
         h, w = img.shape
         out = np.empty((h + 1, w + 1, 8), np.float32) if want_output else None
         self._check(lib().sc_integral(self._h, img.ctypes.data, w, h, w, out.ctypes.data if want_output else None))
+        return out
+
+    def integral_scan_layout(self, img: np.ndarray, step: int = 2) -> np.ndarray:
+        """The integral image computed through the scan's own layout for lattice step `step` (parity hook of the detect path)."""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        out = np.empty((h + 1, w + 1, 8), np.float32)
+        self._check(lib().sc_integral_scan_layout(self._h, img.ctypes.data, w, h, w, step, out.ctypes.data))
         return out
 
     def features(self, rects) -> np.ndarray:

@@ -384,7 +384,14 @@ int run_integral(sc_handle* h, const uint8_t* d_img, int n, int slot0) {
     float4* S = h->d_S.as<float4>() + (size_t)slot0 * p.lay.frame4;
     { KernelSpan ks(h, K_CARRY); sck::k_strip_carry<<<(rows + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, n, carry); }
     const int warps = n * p.n_strips;
-    { KernelSpan ks(h, K_WALK); sck::k_integral_walk<<<(warps + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, n, carry, S, p.lay); }
+    {
+        KernelSpan ks(h, K_WALK);
+#if SC_WALK_TILED
+        sck::k_integral_walk_tiled<<<(warps + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, n, carry, S, p.lay);
+#else
+        sck::k_integral_walk<<<(warps + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, n, carry, S, p.lay);
+#endif
+    }
     SC_CUDA(h, cudaGetLastError());
     return SC_OK;
 }
@@ -772,8 +779,13 @@ int sc_integral(sc_handle* h, const uint8_t* gray, int W, int H, int stride, flo
     SC_CUDA(h, h->d_hook_S.ensure((size_t)L.frame4 * 16));
     SC_CUDA(h, cudaMemcpy2DAsync(h->d_hook_img.p, W, gray, stride, W, H, cudaMemcpyHostToDevice, h->stream));
     sck::k_strip_carry<<<(H + 3) / 4, 128, 0, h->stream>>>(h->d_hook_img.as<uint8_t>(), W, H, n_strips, 1, h->d_hook_carry.as<int>());
+#if SC_WALK_TILED
+    sck::k_integral_walk_tiled<<<(n_strips + 3) / 4, 128, 0, h->stream>>>(h->d_hook_img.as<uint8_t>(), W, H, n_strips, 1, h->d_hook_carry.as<int>(),
+                                                                            h->d_hook_S.as<float4>(), L);
+#else
     sck::k_integral_walk<<<(n_strips + 3) / 4, 128, 0, h->stream>>>(h->d_hook_img.as<uint8_t>(), W, H, n_strips, 1, h->d_hook_carry.as<int>(),
                                                                       h->d_hook_S.as<float4>(), L);
+#endif
     h->launches += 2;
     SC_CUDA(h, cudaGetLastError());
     if (out) {
@@ -791,6 +803,39 @@ int sc_integral(sc_handle* h, const uint8_t* gray, int W, int H, int stride, flo
     }
     SC_CUDA(h, cudaStreamSynchronize(h->stream));
     h->have_integral = true; h->cur_W = W; h->cur_H = H; h->hook_lay = L;
+    return SC_OK;
+}
+
+// Parity hook for the layout the scan reads: the same two kernels as the detect path (run_integral) with the detection
+// plan's deinterleave factors for lattice step `step` (columns by 2 * step, rows by step), exported to the reference layout.
+int sc_integral_scan_layout(sc_handle* h, const uint8_t* gray, int W, int H, int stride, int step, float* out) {
+    if (!h || !gray || !out || W < 2 || H < 2 || stride < W || step < 1 || step > 64) return fail(h, SC_ERR_INVALID, "bad image arguments");
+    SC_CUDA(h, cudaSetDevice(h->device));
+    const int n_strips = (W + SC_STRIP - 1) / SC_STRIP;
+    const ScLayout L = sc_host::make_layout(W, H, 2 * step, step);
+    if (L.hp > 4096 || L.frame4 * 16 > 0xffffffffLL) return fail(h, SC_ERR_INVALID, "frame too large for the scan layout");
+    DevBuf d_img, d_carry, d_S, d_out;
+    const size_t bytes = (size_t)(H + 1) * (W + 1) * 32;
+    cudaError_t e = d_img.ensure(align256((size_t)W * H));
+    if (e == cudaSuccess) e = d_carry.ensure(align256((size_t)H * n_strips * 32));
+    if (e == cudaSuccess) e = d_S.ensure((size_t)L.frame4 * 16);
+    if (e == cudaSuccess) e = d_out.ensure(bytes);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(d_img.p, W, gray, stride, W, H, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        sck::k_strip_carry<<<(H + 3) / 4, 128, 0, h->stream>>>(d_img.as<uint8_t>(), W, H, n_strips, 1, d_carry.as<int>());
+#if SC_WALK_TILED
+        sck::k_integral_walk_tiled<<<(n_strips + 3) / 4, 128, 0, h->stream>>>(d_img.as<uint8_t>(), W, H, n_strips, 1, d_carry.as<int>(), d_S.as<float4>(), L);
+#else
+        sck::k_integral_walk<<<(n_strips + 3) / 4, 128, 0, h->stream>>>(d_img.as<uint8_t>(), W, H, n_strips, 1, d_carry.as<int>(), d_S.as<float4>(), L);
+#endif
+        sck::k_export_integral<<<h->n_sms * 8, 256, 0, h->stream>>>(d_S.as<float4>(), L, W, H, d_out.as<float4>());
+        h->launches += 3;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out.p, bytes, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    d_img.release(); d_carry.release(); d_S.release(); d_out.release();
+    if (e != cudaSuccess) return cuda_fail(h, e, "sc_integral_scan_layout");
     return SC_OK;
 }
 

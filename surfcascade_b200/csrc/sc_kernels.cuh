@@ -158,6 +158,122 @@ __global__ void __launch_bounds__(128) k_integral_walk(const uint8_t* __restrict
     }
 }
 
+// Second form of the walk (default, SC_WALK_TILED): the same recurrence, but the row prefixes of a 16-row x 32-column tile
+// are computed with the lanes turned by 90 degrees.  In k_integral_walk every row costs four 5-level shuffle scans
+// (80 SHFL + 80 SEL + 80 adds per four rows: 60 % of its 190 instructions per row, and 20 of its 55 L1 data-pipe
+// wavefronts); here lane (r, half) walks 16 columns of tile row r SERIALLY -- a running sum, no shuffles -- from a byte
+// tile staged in shared memory and leaves the packed prefixes in shared memory, then the lanes become columns again for
+// the reference's sequential float32 recurrence down the 16 rows.  Because the column phase reads its prefixes from shared
+// memory, its lane -> column map is free: for the detection layout (sx = 4) lanes 8 rx .. 8 rx + 7 take the eight columns
+// of plane residue rx, so a quarter-warp's 16-byte stores fill one 128-byte line (5 data-pipe wavefronts per STG.128
+// instead of 16; the prefixes are stored in that lane order, so both shared-memory passes are conflict-free).
+// Values, rounding order and layout are identical to k_integral_walk (tests: bit-exact against the oracle).
+#define SC_WT 16
+__global__ void __launch_bounds__(128) k_integral_walk_tiled(const uint8_t* __restrict__ img, int W, int H, int n_strips, int nframes,
+                                                              const int* __restrict__ carry, float4* __restrict__ S, const ScLayout L) {
+    __shared__ __align__(16) uint4 s_pre[4][SC_WT][33];      // packed inclusive row prefixes (4 channel pairs) in column-phase lane order
+    __shared__ __align__(16) uint4 s_off[4][SC_WT];          // per tile row: total of the strip's columns 0..15
+    __shared__ __align__(16) int4 s_car[4][SC_WT][2];        // strip carries of the tile's rows
+    __shared__ __align__(16) uint8_t s_px[4][SC_WT + 2][40]; // rows y0-1 .. y0+16 (clamped), columns x0-1 .. x0+32 (clamped) at bytes 3 .. 36
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    const int wid = blockIdx.x * (blockDim.x >> 5) + wq;
+    if (wid >= nframes * n_strips) return;  // whole warps leave: only __syncwarp below
+    const int f = wid / n_strips, s = wid - f * n_strips;
+    const uint8_t* base = img + (size_t)f * W * H;
+    const int x0 = s * SC_STRIP;
+    float4* Sf = S + (size_t)f * L.frame4;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    // column phase: this lane's strip column c (integral column X = x0 + c + 1)
+    int c = lane;
+    if (L.sx == 4) {  // u = c + 1 = 4 q + rx: lanes 8 rx + k hold q = k (+1 for rx == 0), consecutive float4s of plane column residue rx
+        const int rxl = lane >> 3, k = lane & 7;
+        c = 4 * (k + (rxl == 0 ? 1 : 0)) + rxl - 1;
+    }
+    const int x = x0 + c;
+    const bool valid = x < W;
+    const int X = x + 1, px = X / L.sx, rx = X - px * L.sx;
+    const bool upper = c >= 16;
+    if (valid) { float4* o = Sf + (size_t)rx * L.plane4 + SC_COL(px); o[0] = zero; o[SC_HI(L.hp)] = zero; }      // row Y = 0
+    if (s == 0 && lane == 0)                                                                      // column X = 0
+        for (int Y = 0; Y <= H; Y++) { float4* o = Sf + sc_layout_index(L, 0, Y); o[0] = zero; o[SC_HI(L.hp)] = zero; }
+    // row phase: lane (r, half) owns tile row r, strip columns 16 half .. 16 half + 15
+    const int r = lane & 15, half = lane >> 4;
+    // position of strip column cc in the column-phase lane order (identity unless sx == 4)
+    auto slot_of = [&](int cc) -> int {
+        if (L.sx != 4) return cc;
+        const int u = cc + 1, rxu = u & 3, q = u >> 2;
+        return 8 * rxu + q - (rxu == 0 ? 1 : 0);
+    };
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int4* cr = reinterpret_cast<const int4*>(carry + (((size_t)f * H) * n_strips + s) * 8);
+    const size_t cr_step = (size_t)n_strips * 2;
+    int py = 0, ry = 0;  // plane row / residue of Y = y + 1, advanced incrementally
+    const int xl = min(x0 + lane, W - 1);                                   // fill: this lane's image column
+    const int xh = lane == 0 ? max(x0 - 1, 0) : min(x0 + 32, W - 1);         // halo columns (lanes 0 and 1)
+    for (int y0 = 0; y0 < H; y0 += SC_WT) {
+        // ---- stage the byte tile and the strip carries of these rows
+#pragma unroll
+        for (int t = 0; t < SC_WT + 2; t++) {
+            const uint8_t* row = base + (size_t)min(max(y0 - 1 + t, 0), H - 1) * W;
+            s_px[wq][t][4 + lane] = __ldg(row + xl);
+            if (lane < 2) s_px[wq][t][lane == 0 ? 3 : 36] = __ldg(row + xh);
+        }
+        {
+            const int yq = min(y0 + (lane >> 1), H - 1);
+            s_car[wq][lane >> 1][lane & 1] = __ldg(cr + (size_t)yq * cr_step + (lane & 1));
+        }
+        __syncwarp();
+        // ---- row phase: serial packed prefix of 16 columns of tile row r
+        {
+            const uint32_t* pm = reinterpret_cast<const uint32_t*>(&s_px[wq][r][16 * half]);      // image row y - 1
+            const uint32_t* pc = reinterpret_cast<const uint32_t*>(&s_px[wq][r + 1][16 * half]);  // y
+            const uint32_t* pn = reinterpret_cast<const uint32_t*>(&s_px[wq][r + 2][16 * half]);  // y + 1
+            uint32_t wm[6], wc[6], wn[6];
+#pragma unroll
+            for (int i = 0; i < 6; i++) { wm[i] = pm[i]; wc[i] = pc[i]; wn[i] = pn[i]; }
+            // byte b of the 24 loaded bytes = strip column 16 half + b - 4
+            auto byte_of = [](const uint32_t* w, int b) -> int { return (int)((w[b >> 2] >> (8 * (b & 3))) & 0xffu); };
+            Row3 prev, cur, next;
+            prev.a = byte_of(wm, 3); prev.b = byte_of(wm, 4);
+            cur.a = byte_of(wc, 3); cur.b = byte_of(wc, 4);
+            next.a = byte_of(wn, 3); next.b = byte_of(wn, 4);
+            uint4 run = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                prev.c = byte_of(wm, 5 + k); cur.c = byte_of(wc, 5 + k); next.c = byte_of(wn, 5 + k);
+                uint32_t p[4];
+                channel_pairs(prev, cur, next, p);
+                run.x += p[0]; run.y += p[1]; run.z += p[2]; run.w += p[3];
+                s_pre[wq][r][slot_of(16 * half + k)] = run;
+                prev.a = prev.b; prev.b = prev.c; cur.a = cur.b; cur.b = cur.c; next.a = next.b; next.b = next.c;
+            }
+            if (half == 0) s_off[wq][r] = run;
+        }
+        __syncwarp();
+        // ---- column phase: the reference's sequential recurrence down the tile's rows
+        const int nrow = min(SC_WT, H - y0);
+        for (int i = 0; i < nrow; i++) {
+            uint4 pr = s_pre[wq][i][lane];
+            if (upper) { const uint4 o = s_off[wq][i]; pr.x += o.x; pr.y += o.y; pr.z += o.z; pr.w += o.w; }
+            const int4 clo = s_car[wq][i][0], chi = s_car[wq][i][1];
+            const uint32_t p[4] = {pr.x, pr.y, pr.z, pr.w};
+            const int cy[8] = {clo.x, clo.y, clo.z, clo.w, chi.x, chi.y, chi.z, chi.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                acc[2 * k] = __fadd_rn(acc[2 * k], (float)(cy[2 * k] + (int)(p[k] & 0xffffu)));
+                acc[2 * k + 1] = __fadd_rn(acc[2 * k + 1], (float)(cy[2 * k + 1] + (int)(p[k] >> 16)));
+            }
+            if (++ry == L.sy) { ry = 0; py++; }
+            if (valid) {
+                float4* o = Sf + (size_t)(ry * L.sx + rx) * L.plane4 + (size_t)py * L.ppitch + SC_COL(px);
+                o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                o[SC_HI(L.hp)] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // Layout -> the reference's interleaved (H+1) x (W+1) x 8 float image (parity hook output of sc_integral).
 __global__ void k_export_integral(const float4* __restrict__ S, const ScLayout L, int W, int H, float4* __restrict__ out) {
     const int n = (W + 1) * (H + 1);

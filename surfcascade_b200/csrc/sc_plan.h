@@ -39,6 +39,9 @@
 
 // Integral strips: one warp walks one 32-column strip down the frame, SC_WALK_RB rows per prefetch block.
 #define SC_STRIP 32
+#ifndef SC_WALK_TILED
+#define SC_WALK_TILED 1        // k_integral_walk_tiled (row prefixes by lanes turned 90 degrees) instead of k_integral_walk (shuffle scans)
+#endif
 #ifndef SC_WALK_RB
 #define SC_WALK_RB 4
 #endif

@@ -140,3 +140,30 @@ def test_random_cascades_with_square_patches_match_oracle(seed, n_weak, thetas, 
             assert np.abs(fs.astype(np.float64) - es.astype(np.float64)).max() < margin / 4
     finally:
         h.close()
+
+
+@pytest.mark.parametrize("theta0,width", [(0.29, 1400), (0.40, 1027), (None, 1400)])
+def test_wide_frames_long_odd_suffixes(oracle_cascade, theta0, width):
+    """k_scan_odd's 128-window units: wide, flat frames (up to 681 lattice columns per row, several units per row suffix,
+    suffixes starting at every residue of the 32-bit mask words) with stage-0 thresholds low enough that rows switch the
+    stride parity early and often; also with the prefilter off (every lane of a unit survives) and the trained thresholds."""
+    c = oracle_cascade.c
+    theta = c.theta.copy()
+    if theta0 is not None:
+        theta[0] = np.float32(theta0)
+    bc = O.BoundCascade(dataclasses.replace(c, theta=theta))
+    h = capi.Handle(0)
+    try:
+        h.set_cascade(40, bc.theta, bc.n_weak, bc.rects, bc.w, bc.bias)
+        for img, pf in ((synth.frame(120, width, 90), 6), (synth.noise_frame(97, width, 91), 6), (synth.frame(64, width, 92), -1)):
+            dets, cnts = h.detect([img, img[:, ::-1].copy()], capi.params(prefilter=pf), cap=1 << 21)
+            for f, im in enumerate((img, img[:, ::-1].copy())):
+                want = O.detect(O.integral(im), bc, O.params(base=40, prefilter=pf, nthreads=8), cap=1 << 21)
+                mine = dets[dets["frame"] == f]
+                assert cnts[f].visited == want.counters[O.C_VISITED] and cnts[f].prefilter_pass == want.counters[O.C_PREFILTER]
+                assert [cnts[f].reach[s] for s in range(4)] == [int(want.counters[O.C_REACH0 + s]) for s in range(4)]
+                assert cnts[f].visited <= cnts[f].evaluated <= cnts[f].grid
+                assert np.array_equal(mine["x"], want.x) and np.array_equal(mine["y"], want.y) and np.array_equal(mine["l"], want.l)
+                np.testing.assert_allclose(mine["score"], want.score, rtol=1e-6, atol=0)
+    finally:
+        h.close()

@@ -36,6 +36,21 @@ def test_integral_bit_exact(gpu_handle, shape, kind):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
+@pytest.mark.parametrize("shape,kind,step", [((117, 203), "frame", 2), ((480, 640), "frame", 2), ((2, 2), "noise", 2), ((3, 33), "noise", 2), ((17, 31), "noise", 2),
+                                             ((65, 32), "noise", 2), ((200, 97), "noise", 1), ((301, 517), "frame", 3), ((600, 700), "stripes", 2),
+                                             ((1080, 1920), "noise", 2), ((1080, 1920), "frame", 2), ((95, 1400), "noise", 5)])
+def test_integral_bit_exact_in_the_scan_layout(gpu_handle, shape, kind, step):
+    """The integral stage of the detect path itself: same kernels, the scan's lattice-deinterleaved layout (columns by
+    2 * step, rows by step; for step 2 the column phase of the walk runs in its plane-major lane order)."""
+    h, w = shape
+    img = {"frame": lambda: synth.frame(h, w, 3) if min(h, w) >= 64 else synth.noise_frame(h, w, 3), "noise": lambda: synth.noise_frame(h, w, 5),
+           "stripes": lambda: stripes(h, w)}[kind]()
+    got = gpu_handle.integral_scan_layout(img, step)
+    want = O.integral(img)
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
 def test_features_and_window_sums_bit_exact(gpu_handle):
     img = synth.frame(240, 320, 11)
     S = O.integral(img)
