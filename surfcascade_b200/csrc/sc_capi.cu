@@ -376,7 +376,11 @@ int ensure_group_buffers(sc_handle* h, int want_frames, bool own_images) {
 }
 
 // Channels + integral images of `n` frames (device images) into frame slots slot0.. of d_S, on the main stream
-int run_integral(sc_handle* h, const uint8_t* d_img, int n, int slot0) {
+// `under_scan`: this launch will share the SMs with a scan group of the previous chunk (synchronous host path).  The tiled
+// walk holds 40 KB of shared memory per CTA; next to four stage-0 CTAs that exceeds the scan's shared-memory carve-out, and
+// the synchronous path dropped from 2 720 to 2 250 frames/s when its overlapped chunks used it -- those chunks keep the
+// shuffle-scan form, which needs no shared memory.  Both forms produce identical bits.
+int run_integral(sc_handle* h, const uint8_t* d_img, int n, int slot0, bool under_scan = false) {
     const ScPlan& p = h->plan;
     cudaStream_t st = h->stream;
     const int rows = n * p.H;
@@ -386,11 +390,10 @@ int run_integral(sc_handle* h, const uint8_t* d_img, int n, int slot0) {
     const int warps = n * p.n_strips;
     {
         KernelSpan ks(h, K_WALK);
-#if SC_WALK_TILED
-        sck::k_integral_walk_tiled<<<(warps + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, n, carry, S, p.lay);
-#else
-        sck::k_integral_walk<<<(warps + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, n, carry, S, p.lay);
-#endif
+        if (SC_WALK_TILED && !under_scan)
+            sck::k_integral_walk_tiled<<<(warps + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, n, carry, S, p.lay);
+        else
+            sck::k_integral_walk<<<(warps + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, n, carry, S, p.lay);
     }
     SC_CUDA(h, cudaGetLastError());
     return SC_OK;
@@ -549,7 +552,7 @@ int run_supergroup(sc_handle* h, const uint8_t* const* frames, int stride, const
             SC_CUDA(h, cudaEventRecord(h->ev_chunk[2 * c], h->copy_st));
             SC_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[2 * c], 0));
         }
-        int rc = run_integral(h, img, n, c0);
+        int rc = run_integral(h, img, n, c0, c > 0);
         if (rc != SC_OK) return rc;
         SC_CUDA(h, cudaEventRecord(h->ev_chunk[2 * c + 1], h->stream));
     }
