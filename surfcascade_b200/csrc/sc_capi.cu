@@ -629,7 +629,7 @@ void sort_detections(sc_detection* d, size_t n) {
 
 extern "C" {
 
-const char* sc_version(void) { return "surfcascade-b200 0.2 (sm_100a)"; }
+const char* sc_version(void) { return "surfcascade-b200 0.3 (sm_100a)"; }
 
 int sc_create(int device, sc_handle** out) {
     if (!out) return SC_ERR_INVALID;
