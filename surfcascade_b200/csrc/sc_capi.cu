@@ -401,20 +401,22 @@ int run_integral(sc_handle* h, const uint8_t* d_img, int n, int slot0, bool unde
 
 // Launches the whole path for `g` frames already in d_img (device).  Detections are appended to det / det_count.
 // The scan kernels are instantiated per half-row distance of the layout (sc_plan.h): 256 .. 4096 float4.
-template <bool FAST, typename... A>
+template <bool FAST, bool ALL, typename... A>
 void launch_stage0_hp(int hp, int grid, size_t smem, cudaStream_t st, A... a) {
     switch (hp) {
-        case 256: sck::k_scan_stage0<256, FAST><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
-        case 512: sck::k_scan_stage0<512, FAST><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
-        case 1024: sck::k_scan_stage0<1024, FAST><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
-        case 2048: sck::k_scan_stage0<2048, FAST><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
-        default: sck::k_scan_stage0<4096, FAST><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
+        case 256: sck::k_scan_stage0<256, FAST, ALL><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
+        case 512: sck::k_scan_stage0<512, FAST, ALL><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
+        case 1024: sck::k_scan_stage0<1024, FAST, ALL><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
+        case 2048: sck::k_scan_stage0<2048, FAST, ALL><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
+        default: sck::k_scan_stage0<4096, FAST, ALL><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
     }
 }
+// fast: certified fast filter; all: exact variant that also runs stages 1..N-1 in place (force_all)
 template <typename... A>
-void launch_stage0(bool fast, int hp, int grid, size_t smem, cudaStream_t st, A... a) {
-    if (fast) launch_stage0_hp<true>(hp, grid, smem, st, a...);
-    else launch_stage0_hp<false>(hp, grid, smem, st, a...);
+void launch_stage0(bool fast, bool all, int hp, int grid, size_t smem, cudaStream_t st, A... a) {
+    if (fast) launch_stage0_hp<true, false>(hp, grid, smem, st, a...);
+    else if (all) launch_stage0_hp<false, true>(hp, grid, smem, st, a...);
+    else launch_stage0_hp<false, false>(hp, grid, smem, st, a...);
 }
 template <typename... A>
 void launch_stage(int hp, int grid, size_t smem, cudaStream_t st, A... a) {
@@ -444,14 +446,17 @@ int run_group(sc_handle* h, sc_handle::Lane& L, int s0, int g, int frame0, sc_de
         uint32_t* pass = L.d_pass.as<uint32_t>();
         uint32_t* visited = L.d_visited.as<uint32_t>();
         ScRecord* rec = L.d_rec.as<ScRecord>();
+        // force_all: every stage of every window is evaluated inside the stage-0 tile kernel (its ALL variant), as long as
+        // the whole cascade's weights and geometry fit its shared memory (200 B per weak classifier)
+        const bool all_in_tile = p.force_all && !h->use_fast && p.n_stages > 1 && p.total_weak <= 200;
         {
             // even lattice columns everywhere, then the odd columns the reference's stride can reach
-            const size_t smem = (size_t)p.n_weak[0] * (SC_W_PITCH * 4 + 8 + sizeof(ScGeom));
+            const size_t smem = (size_t)(all_in_tile ? p.total_weak : p.n_weak[0]) * (SC_W_PITCH * 4 + 8 + sizeof(ScGeom));
             int* start_odd = L.d_start.as<int>();
             const int rows0 = g * p.rows_per_frame;
             {
                 KernelSpan ks(h, K_STAGE0, st);
-                launch_stage0(h->use_fast, p.lay.hp, g * p.blocks_per_frame, smem, st, h->fast[0], dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, 0, start_odd);
+                launch_stage0(h->use_fast, all_in_tile, p.lay.hp, g * p.blocks_per_frame, smem, st, h->fast[0], dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, 0, start_odd);
             }
             // odd columns: with the adaptive stride they are reachable only as ragged row suffixes -> list of 32-window runs
             // and persistent warps (k_scan_odd); without it (or without the fast filter) the tile kernel does them all
@@ -486,13 +491,13 @@ int run_group(sc_handle* h, sc_handle::Lane& L, int s0, int g, int frame0, sc_de
 #undef SC_ODD
                 }
             } else {
-                launch_stage0(h->use_fast, p.lay.hp, g * p.blocks_per_frame, smem, st, h->fast[1], dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, 1, start_odd);
+                launch_stage0(h->use_fast, all_in_tile, p.lay.hp, g * p.blocks_per_frame, smem, st, h->fast[1], dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, 1, start_odd);
             }
         }
         const int tail_grid = h->n_sms * 8;
         // with the fast filter, stage 0's undecided windows are live records: k_scan_stage(0) gives them the exact arithmetic
         const int s_begin = h->use_fast ? 0 : 1;
-        for (int s = s_begin; s < p.n_stages; s++) {
+        for (int s = s_begin; s < p.n_stages && !all_in_tile; s++) {
             const bool first = s == s_begin || p.force_all;
             const uint32_t* in_idx = first ? nullptr : L.d_idx[(s - 1) & 1].as<uint32_t>();
             const uint32_t* in_cnt = first ? small + SM_REC : small + SM_STAGE0 + (s - 1);

@@ -544,8 +544,11 @@ __device__ __forceinline__ uint32_t spread16(uint32_t x) {  // bit i (i < 16) ->
 // record and goes through the exact arithmetic of k_scan_stage(stage 0) afterwards.  Keeping the exact path out of this
 // kernel lets it fit 64 registers: four CTAs (32 warps) per SM instead of three, 0.278 -> 0.254 ms/frame.  fp carries
 // the weights / geometry / limits in the constant bank.  !FAST evaluates stage 0 exactly in place and ignores fp.
-template <int HP, bool FAST>
-__global__ void __launch_bounds__(SC_TILE_THREADS, FAST ? SC_FAST_MIN_CTAS : SC_STAGE0_MIN_CTAS) k_scan_stage0(const __grid_constant__ ScFastParams fp, const ScPlan* __restrict__ plan, const float4* __restrict__ S,
+// ALL (exact variant only): force_all mode evaluates every stage of every window; the stages 1..N-1 then run right here,
+// on the window whose corners this thread just gathered, instead of as N-1 more passes of k_scan_stage over a record per
+// window (C4: 242 M records re-read three times).  The records it pushes are final.
+template <int HP, bool FAST, bool ALL = false>
+__global__ void __launch_bounds__(SC_TILE_THREADS, FAST ? SC_FAST_MIN_CTAS : (ALL ? 2 : SC_STAGE0_MIN_CTAS)) k_scan_stage0(const __grid_constant__ ScFastParams fp, const ScPlan* __restrict__ plan, const float4* __restrict__ S,
                                                                   const ScGeom* __restrict__ geom_all, const float* __restrict__ w_all,
                                                                   const double* __restrict__ wb_all, uint32_t* __restrict__ multi_bits,
                                                                   uint32_t* __restrict__ pass_bits, ScRecord* __restrict__ rec,
@@ -592,12 +595,13 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, FAST ? SC_FAST_MIN_CTAS : SC_
     const int n_weak = plan->n_weak[0], total_weak = plan->total_weak;
     constexpr int ppitch = 2 * HP;
     const float4* lo4 = S + (size_t)f * plan->lay.frame4 + (size_t)s_sc.gy0 * ppitch;  // lattice row gy0 is row 0 of this plan
-    ScGeom* sg = reinterpret_cast<ScGeom*>(s_dyn);                                                          // [n_weak] 48 B each
-    float* sw = reinterpret_cast<float*>(s_dyn + (size_t)n_weak * sizeof(ScGeom));                          // [n_weak][36]
-    double* swb = reinterpret_cast<double*>(s_dyn + (size_t)n_weak * (sizeof(ScGeom) + SC_W_PITCH * 4));    // [n_weak]
+    const int n_ld = ALL ? total_weak : n_weak;  // weak classifiers staged in shared memory: stage 0, or every stage
+    ScGeom* sg = reinterpret_cast<ScGeom*>(s_dyn);                                                        // [n_ld] 48 B each
+    float* sw = reinterpret_cast<float*>(s_dyn + (size_t)n_ld * sizeof(ScGeom));                          // [n_ld][36]
+    double* swb = reinterpret_cast<double*>(s_dyn + (size_t)n_ld * (sizeof(ScGeom) + SC_W_PITCH * 4));    // [n_ld]
     if (!FAST) {
-        for (int i = tid; i < n_weak * SC_W_PITCH; i += SC_TILE_THREADS) sw[i] = w_all[i];
-        for (int i = tid; i < n_weak; i += SC_TILE_THREADS) {
+        for (int i = tid; i < n_ld * SC_W_PITCH; i += SC_TILE_THREADS) sw[i] = w_all[i];
+        for (int i = tid; i < n_ld; i += SC_TILE_THREADS) {
             swb[i] = wb_all[i];
             sg[i] = geom_all[((size_t)phase * plan->n_scales + si) * total_weak + i];
         }
@@ -696,15 +700,35 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, FAST ? SC_FAST_MIN_CTAS : SC_
             const int gx = 2 * j + phase, gy = ty * SC_TILE_Y + row;
             float score = 0.f;
             bool rejected = false;
+            int rej = -1;  // FAST: still alive, k_scan_stage(0) decides
             if (!FAST) {
-                score = stage_score<HP>(reinterpret_cast<const char*>(lo4 + (gy * ppitch + SC_COL(j))), sg, sw, swb, n_weak, HP);
+                const char* base = reinterpret_cast<const char*>(lo4 + (gy * ppitch + SC_COL(j)));
+                score = stage_score<HP>(base, sg, sw, swb, n_weak, HP);
                 rejected = score < theta0;
                 if (rejected && rejected_skips(score, 0, n_stages)) atomicOr(&s_multi[row][2 * half + (ln >> 4)], 1u << (2 * (ln & 15) + phase));
+                rej = rejected ? 0 : (n_stages == 1 ? 1 : -1);
+                if (ALL) {
+                    // every later stage is evaluated (force_all); the first rejection keeps its stage and score,
+                    // exactly as k_scan_stage would leave the record after its N-1 passes
+                    for (int st = 1; st < n_stages; st++) {
+                        const int wbs = plan->weak_base[st];
+                        const float sc = stage_score<HP>(base, sg + wbs, sw + (size_t)wbs * SC_W_PITCH, swb + wbs, plan->n_weak[st], HP);
+                        if (rej < 0) {
+                            score = sc;
+                            if (sc < plan->theta[st]) {
+                                rej = st;
+                                if (rejected_skips(sc, st, n_stages)) atomicOr(&s_multi[row][2 * half + (ln >> 4)], 1u << (2 * (ln & 15) + phase));
+                            } else if (st == n_stages - 1) {
+                                rej = n_stages;
+                            }
+                        }
+                    }
+                }
             }
             push = !rejected || force;
             r.fs = ((uint32_t)f << 8) | (uint32_t)si;
             r.yx = ((uint32_t)gy << 16) | (uint32_t)gx;
-            r.rej = FAST ? -1 : (rejected ? 0 : (n_stages == 1 ? 1 : -1));  // FAST: still alive, k_scan_stage(0) decides
+            r.rej = rej;
             r.score = __float_as_uint(score);
         }
         const uint32_t m = __ballot_sync(0xffffffffu, push);
