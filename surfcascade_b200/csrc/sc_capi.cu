@@ -82,6 +82,7 @@ struct sc_handle {
     bool allow_fast = true;     // SC_DISABLE_FAST=1 in the environment forces the exact-only kernel (A/B tests)
     bool use_fast = false;
     ScFastParams fast[2];
+    bool group_attr_set = false;  // k_group_frames' dynamic shared-memory limit raised on this handle's device
     int group_max = 8;  // frames per scan group (SC_GROUP_FRAMES overrides, 1..32)
 
     // group buffers
@@ -1274,8 +1275,10 @@ int sc_detect_submit(sc_handle* h, const uint8_t* const* frames, int nframes, in
         SC_CUDA(h, cudaMemsetAsync(per_frame, 0, tab_bytes, h->stream));
         const sck::ScDetOut* det = reinterpret_cast<const sck::ScDetOut*>(t.d_det.p);
         const size_t gsmem = (size_t)SC_GROUP_MAX * (8 + 8 + 6 * 4);
-        static bool attr_set = false;
-        if (!attr_set) { cudaFuncSetAttribute(sck::k_group_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem); attr_set = true; }
+        if (!h->group_attr_set) {  // per handle: the attribute belongs to the handle's device
+            SC_CUDA(h, cudaFuncSetAttribute(sck::k_group_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+            h->group_attr_set = true;
+        }
         {
             KernelSpan ks(h, K_GROUP);  // the three small table kernels ride in the same span
             sck::k_group_count<<<h->n_sms * 2, 256, 0, h->stream>>>(det, t.d_cnt.as<uint32_t>(), t.det_cap, 0, nframes, per_frame);
