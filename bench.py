@@ -91,6 +91,17 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def cpu_model() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def make_frames(n: int):
     from surfcascade_b200 import synth
     return [synth.frame(H, W, 100 + i) for i in range(n)]
@@ -134,7 +145,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "1080p full-scale-range detection throughput", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "frames_per_step": per_step},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "cpu_model": cpu_model(),
                              "sample": f"{per_step} frame(s) of the C2 workload per step, OpenMP over scales as in ObjDetector.cpp:177"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -342,7 +353,7 @@ def run_ours(args):
                 cpu_detect_once(fr[:1], th)
                 dt, kind, _ = cpu_detect_once(fr, th)
                 dt1, _, _ = cpu_detect_once(fr[:1], 1)
-                cpu = {"value": len(fr) / dt, "unit": "frames/s", "cores": th, "kind": kind,
+                cpu = {"value": len(fr) / dt, "unit": "frames/s", "cores": th, "kind": kind, "cpu_model": cpu_model(),
                        "sample": f"2 frames of the C2 workload, all {th} host threads (OpenMP over scales, ObjDetector.cpp:177); single-thread: {1.0 / dt1:.3f} frames/s"}
             except Exception as e:  # the checker is optional for the product arm
                 cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
