@@ -167,3 +167,37 @@ def test_wide_frames_long_odd_suffixes(oracle_cascade, theta0, width):
                 np.testing.assert_allclose(mine["score"], want.score, rtol=1e-6, atol=0)
     finally:
         h.close()
+
+
+@pytest.mark.parametrize("seed,n_weak,thetas", [(11, [2, 3, 2, 2, 2], [0.45, 0.60, 0.50, 0.50, 0.50]),
+                                                 (12, [2] * 10, [0.45, 0.47, 0.48, 0.48, 0.48, 0.48, 0.48, 0.48, 0.48, 0.48]),
+                                                 (13, [3, 2, 2, 2, 2, 2], [0.50, 0.50, 0.50, 0.50, 0.50, 0.50])])
+def test_deep_cascades_match_oracle(seed, n_weak, thetas):
+    """More than four stages: a reject at a LATER stage can still mean stride 2 (score = (s + p + 1) / N < 0.5,
+    ObjDetector.cpp:201,214) -- score-dependent at stage 1 of a 5-stage cascade, always up to stage 1 / 3 of 6 / 10 stages.
+    The same cascades run through the reference's own loader and loop in tests/test_oracle_vs_ref.py.  Also with every stage
+    forced (the tile kernel's ALL variant sets those bits itself) and without the fast filter."""
+    from cascade_util import random_cascade
+    bc = O.BoundCascade(random_cascade(seed, n_weak, thetas))
+    n = len(n_weak)
+    handles = [capi.Handle(0)]
+    os.environ["SC_DISABLE_FAST"] = "1"
+    try:
+        handles.append(capi.Handle(0))
+    finally:
+        del os.environ["SC_DISABLE_FAST"]
+    try:
+        for h in handles:
+            h.set_cascade(40, bc.theta, bc.n_weak, bc.rects, bc.w, bc.bias)
+        for img in (synth.frame(200, 260, 5), synth.frame(97, 333, 6)):
+            want = O.detect(O.integral(img), bc, O.params(base=40, nthreads=8), cap=1 << 21)
+            for h, prm in ((handles[0], {}), (handles[1], {}), (handles[0], {"force_all_stages": True})):
+                dets, cnts = h.detect([img], capi.params(**prm), cap=1 << 21)
+                assert cnts[0].visited == want.counters[O.C_VISITED] and cnts[0].prefilter_pass == want.counters[O.C_PREFILTER]
+                if not prm:
+                    assert [cnts[0].reach[s] for s in range(n)] == [int(want.counters[O.C_REACH0 + s]) for s in range(n)]
+                assert np.array_equal(dets["x"], want.x) and np.array_equal(dets["y"], want.y) and np.array_equal(dets["l"], want.l)
+                np.testing.assert_allclose(dets["score"], want.score, rtol=1e-6, atol=0)
+    finally:
+        for h in handles:
+            h.close()

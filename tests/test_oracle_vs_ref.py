@@ -87,3 +87,31 @@ def test_pool_eval():
         for n in range(N):
             prior[n] = np.float32(prior[n] + np.float32(O.weak(prev_w[t], 1.0, X[n, prev_patch[t]])))
     assert np.array_equal(bits(O.pool_eval(X, n_pos, W, b, prior, 3)), bits(R.pool_eval(X, n_pos, W, b, prev_patch, prev_w, [1.0] * 3)))
+
+
+@pytest.mark.parametrize("seed,n_weak,thetas", [(11, [2, 3, 2, 2, 2], [0.45, 0.60, 0.50, 0.50, 0.50]),
+                                                 (12, [2] * 10, [0.45, 0.47, 0.48, 0.48, 0.48, 0.48, 0.48, 0.48, 0.48, 0.48]),
+                                                 (13, [3, 2, 2, 2, 2, 2], [0.50, 0.50, 0.50, 0.50, 0.50, 0.50])])
+def test_detect_identical_on_deep_synthetic_cascades(tmp_path, seed, n_weak, thetas):
+    """The stride rule multi = (score < 0.5 ? 2 : 1) with score = (s + p + 1) / N (ObjDetector.cpp:201,214) depends on the
+    stage count: the trained 4-stage cascade only ever skips after a stage-0 reject.  With 5 stages a stage-1 reject skips
+    iff s < 0.5, with 6 and 10 stages rejects up to stage 1 / 3 always skip and later ones never: cascades written in the
+    reference's model.cfg schema, loaded by its own Model::Load, run through its own detect loop, against the oracle."""
+    from cascade_util import random_cascade, write_model_cfg
+    from oracle import modelcfg
+    c = random_cascade(seed, n_weak, thetas)
+    cfg = str(tmp_path / "deep.cfg")
+    write_model_cfg(cfg, c)
+    back = modelcfg.load(cfg)  # what both loaders see: %.10g text -> double -> float32
+    assert back.n_stages == len(n_weak) and np.array_equal(back.patch_index, c.patch_index) and np.array_equal(back.theta, c.theta)
+    assert np.array_equal(back.w, c.w)
+    bc = O.BoundCascade(back)
+    for shape, fs in (((200, 260), 5), ((97, 333), 6)):
+        img = synth.frame(*shape, fs)
+        r = R.detect([img], cfg, base=40, nthreads=2, group=False)
+        d = O.detect(O.integral(img), bc, O.params(base=40, nthreads=2), cap=1 << 21)
+        assert np.array_equal(d.x, r.x) and np.array_equal(d.y, r.y) and np.array_equal(d.l, r.l) and np.array_equal(d.score, r.score)
+        cr = r.counters[0]
+        assert (d.counters[O.C_VISITED], d.counters[O.C_PREFILTER], d.counters[O.C_WEAK], d.counters[O.C_RAW]) == (cr[0], cr[1], cr[2], cr[3])
+        reach = d.counters[O.C_REACH0:O.C_REACH0 + len(n_weak)]
+        assert d.counters[O.C_VISITED] < d.counters[O.C_GRID] and (reach > 0).all()  # strides of 2 happen, every stage is entered
