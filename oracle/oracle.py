@@ -97,10 +97,7 @@ def features(S: np.ndarray, rects) -> tuple[np.ndarray, np.ndarray]:
     r = np.ascontiguousarray(rects, np.int32)
     out = np.zeros((len(r), 32), np.float32)
     sums = np.zeros(len(r), np.float32)
-    L = lib()
-    for i in range(len(r)):
-        L.so_feature(_p(S, C.c_float), W, _p(r[i:i + 1], C.c_int), _p(out[i:i + 1], C.c_float))
-        sums[i] = L.so_window_sum(_p(S, C.c_float), W, int(r[i, 0]), int(r[i, 1]), int(r[i, 2]), int(r[i, 3]))
+    lib().so_features(_p(S, C.c_float), W, _p(r, C.c_int), len(r), _p(out, C.c_float), _p(sums, C.c_float))
     return out, sums
 
 

@@ -333,4 +333,44 @@ int ref_train(const char* prefix, const char* pos_list, const char* neg_list, co
     return (int)cascade_classifier.stage_classifiers.size();
 }
 
+// DenseSURFFeatureExtractor::FillNegSamples (DenseSURFFeatureExtractor.cpp:124-195) itself, on PGM files, called
+// `n_calls` times in a row on one extractor the way CascadeClassifier::Train does (CascadeClassifier.cpp:37): call c starts
+// with an empty sample set and fills it to n_totals[c]; the function's static image cursor carries over from call to call.
+// first != 0: every window is taken (stage 0 of the trainer); else the cascade of model_cfg decides (Predict).
+// One thread, so the scale loop runs in index order.  out: [sum of counts][P][32]; counts[c] / dones[c] per call.
+// The cursor is function-static in the reference, so this can run ONCE per process.
+int ref_fill_neg(const char* prefix, const char* neg_list, const char* model_cfg, int tmpl, const int* n_totals, int n_calls, int first,
+                 float* out, long long cap_floats, int* counts, int* dones, int* pool_size) {
+    static bool used = false;
+    if (used) return -100;
+    used = true;
+    CoutSilencer quiet(true);
+    omp_set_num_threads(1);
+    DenseSURFFeatureExtractor ex;
+    ex.size = Size(tmpl, tmpl);
+    ex.LoadFileList(neg_list, prefix, false);
+    vector<Rect> patches;
+    ex.ExtractPatches(patches);
+    *pool_size = (int)patches.size();
+    CascadeClassifier cascade;
+    if (!first) {
+        Model model(model_cfg);
+        if (model.Load(cascade) != EXIT_SUCCESS) return -1;
+    }
+    long long off = 0;
+    for (int c = 0; c < n_calls; c++) {
+        vector<vector<vector<float>>> X;
+        const bool done = ex.FillNegSamples(patches, X, n_totals[c], cascade, first != 0);
+        counts[c] = (int)X.size();
+        dones[c] = done ? 1 : 0;
+        for (size_t i = 0; i < X.size(); i++)
+            for (size_t k = 0; k < X[i].size(); k++) {
+                if (off + 32 > cap_floats) return -2;
+                for (int d = 0; d < 32; d++) out[off + d] = X[i][k][d];
+                off += 32;
+            }
+    }
+    return 0;
+}
+
 }  // extern "C"

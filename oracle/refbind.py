@@ -178,3 +178,60 @@ def write_pgm(path: str, img: np.ndarray) -> None:
     with open(path, "wb") as f:
         f.write(b"P5\n%d %d\n255\n" % (img.shape[1], img.shape[0]))
         f.write(img.tobytes())
+
+
+def _write_pgm(path: str, img) -> None:
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    with open(path, "wb") as f:
+        f.write(b"P5\n%d %d\n255\n" % (img.shape[1], img.shape[0]))
+        f.write(img.tobytes())
+
+
+_FILL_NEG_CHILD = r"""
+import ctypes as C, sys, numpy as np
+lib = C.CDLL(sys.argv[1])
+prefix, lst, cfg, out_path = sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5]
+tmpl, first = int(sys.argv[6]), int(sys.argv[7])
+totals = np.array([int(v) for v in sys.argv[8].split(",")], np.int32)
+cap = int(sys.argv[9])
+out = np.zeros(cap, np.float32)
+counts = np.zeros(len(totals), np.int32); dones = np.zeros(len(totals), np.int32); pool = C.c_int(0)
+rc = lib.ref_fill_neg(prefix.encode(), lst.encode(), cfg.encode(), tmpl, totals.ctypes.data_as(C.POINTER(C.c_int)), len(totals), first,
+                      out.ctypes.data_as(C.POINTER(C.c_float)), C.c_longlong(cap), counts.ctypes.data_as(C.POINTER(C.c_int)),
+                      dones.ctypes.data_as(C.POINTER(C.c_int)), C.byref(pool))
+if rc != 0:
+    sys.exit(10 - rc)
+n = int(counts.sum())
+np.savez(out_path, X=out[: n * pool.value * 32].reshape(n, pool.value, 32), counts=counts, dones=dones)
+"""
+
+
+def fill_neg(frames, model_cfg: str, n_totals, first: bool, tmpl: int = 40):
+    """DenseSURFFeatureExtractor::FillNegSamples (DenseSURFFeatureExtractor.cpp:124-195) called len(n_totals) times in a row
+    on one extractor over `frames` (written as PGM files), single thread.  The reference keeps its image cursor in a
+    function-local static, so every invocation runs in a fresh child process.
+    Returns (list of per-call sample arrays [n][608][32], list of per-call `done` flags)."""
+    import subprocess
+    import sys
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        names = []
+        for i, img in enumerate(frames):
+            names.append(f"neg{i:04d}.pgm")
+            _write_pgm(os.path.join(d, names[-1]), img)
+        with open(os.path.join(d, "neg.list"), "w") as f:
+            f.write("\n".join(names) + "\n")
+        out_path = os.path.join(d, "out.npz")
+        per_sample = 608 * 32 if tmpl == 40 else 4096 * 32
+        cap = int(sum(int(v) for v in n_totals)) * per_sample + 32
+        r = subprocess.run([sys.executable, "-c", _FILL_NEG_CHILD, LIB_PATH, d + "/", "neg.list", model_cfg or "", out_path, str(tmpl),
+                            "1" if first else "0", ",".join(str(int(v)) for v in n_totals), str(cap)], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"ref_fill_neg child failed ({r.returncode}): {r.stderr[-400:]}")
+        z = np.load(out_path)
+        X, counts, dones = z["X"], z["counts"], z["dones"]
+    outs, o = [], 0
+    for c in counts:
+        outs.append(X[o:o + int(c)].copy())
+        o += int(c)
+    return outs, [bool(v) for v in dones]

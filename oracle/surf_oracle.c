@@ -154,6 +154,15 @@ void so_feature(const float* S, int W, const int* rect, float* out) {
     for (int i = 0; i < SO_DIM; i++) out[i] = out[i] * inv;
 }
 
+/* so_feature + so_window_sum over n rects (x, y, w, h): a loop around the two functions above for the Python binding */
+void so_features(const float* S, int W, const int* rects, int n, float* out, float* sums) {
+    for (int i = 0; i < n; i++) {
+        const int* r = rects + 4 * (size_t)i;
+        if (out) so_feature(S, W, r, out + 32 * (size_t)i);
+        if (sums) sums[i] = so_window_sum(S, W, r[0], r[1], r[2], r[3]);
+    }
+}
+
 /* LogisticRegression::Predict, CascadeClassifier/LogisticRegression.cpp:46-68 */
 float so_weak(const float* w, double bias, const float* x) {
     float s[4] = {0.f, 0.f, 0.f, 0.f};

@@ -51,6 +51,7 @@ void so_channels(const uint8_t* img, int W, int H, uint8_t* out);
 void so_integral(const uint8_t* img, int W, int H, float* S);
 float so_window_sum(const float* S, int W, int x, int y, int w, int h);
 void so_feature(const float* S, int W, const int* rect, float* out);
+void so_features(const float* S, int W, const int* rects, int n, float* out, float* sums);
 float so_weak(const float* w33, double bias, const float* x);
 int so_num_scales(int W, int H, const so_params* p, int* sides, int cap);
 float so_stage_score(const float* S, int W, const so_cascade* c, int tmpl, int stage, int x, int y, int l);

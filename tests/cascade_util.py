@@ -51,3 +51,34 @@ def write_model_cfg(path: str, c: Cascade) -> None:
     out += ["  );", "};", ""]
     with open(path, "w") as f:
         f.write("\n".join(out))
+
+
+def fill_neg_restated(frames, need, first, bc):
+    """FillNegSamples (DenseSURFFeatureExtractor.cpp:124-195) in its single-thread order, restated from the oracle's pieces:
+    every window of the scale ladder on a 10-pixel lattice (prefilter and stride rule off), taken when `first` or when the
+    cascade accepts it, its sample = the descriptors of all 608 pool patches projected into it; stops at `need` samples and
+    reports how many images were consumed (the reference's static cursor idx = i + 1).  Pinned against the reference's own
+    function in tests/test_oracle_vs_ref.py::test_fill_neg_samples_restatement."""
+    from oracle import oracle as O
+    pool = O.pool_patches(40)
+    out, used = [], len(frames)
+    for i, img in enumerate(frames):
+        if len(out) >= need:
+            break
+        H, W = img.shape
+        if W < 40 or H < 40:
+            continue
+        S = O.integral(img)
+        prm = O.params(base=40, step=10, prefilter=-1, skip_rule=False)
+        if first:
+            wins = [(x, y, l) for l in O.scales(W, H, prm) for y in range(0, H - l + 1, 10) for x in range(0, W - l + 1, 10)]
+        else:
+            d = O.detect(S, bc, prm)
+            wins = list(zip(d.x.tolist(), d.y.tolist(), d.l.tolist()))
+        for (x, y, l) in wins[: need - len(out)]:
+            r = O.project(40, l, pool)
+            r[:, 0] += x; r[:, 1] += y
+            out.append(O.features(S, r)[0])
+        if len(out) == need:
+            used = i + 1
+    return (np.stack(out) if out else np.zeros((0, 608, 32), np.float32)), used

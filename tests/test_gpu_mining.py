@@ -1,38 +1,15 @@
-"""GPU: hard-negative mining (next row N2) == FillNegSamples in its single-thread order, restated from pinned oracle pieces
-(the cascade's accept decision is the oracle's detect with the prefilter and stride rule off on a 10-pixel lattice; the
-samples are the oracle's descriptors of all 608 pool patches projected into each taken window)."""
+"""GPU: hard-negative mining (next row N2) == FillNegSamples in its single-thread order.  The checker is the restatement in
+tests/cascade_util.py (the cascade's accept decision is the oracle's detect with the prefilter and stride rule off on a
+10-pixel lattice; the samples are the oracle's descriptors of all 608 pool patches projected into each taken window), which
+tests/test_oracle_vs_ref.py pins against the reference's own FillNegSamples."""
 import numpy as np
 import pytest
 
+from cascade_util import fill_neg_restated as _fill_neg
 from oracle import oracle as O
 from surfcascade_b200 import capi, synth
 
 pytestmark = pytest.mark.gpu
-
-
-def _fill_neg(frames, need, first, bc):
-    pool = O.pool_patches(40)
-    out, used = [], len(frames)
-    for i, img in enumerate(frames):
-        if len(out) >= need:
-            break
-        H, W = img.shape
-        if W < 40 or H < 40:
-            continue
-        S = O.integral(img)
-        prm = O.params(base=40, step=10, prefilter=-1, skip_rule=False)
-        if first:
-            wins = [(x, y, l) for l in O.scales(W, H, prm) for y in range(0, H - l + 1, 10) for x in range(0, W - l + 1, 10)]
-        else:
-            d = O.detect(S, bc, prm)
-            wins = list(zip(d.x.tolist(), d.y.tolist(), d.l.tolist()))
-        for (x, y, l) in wins[: need - len(out)]:
-            r = O.project(40, l, pool)
-            r[:, 0] += x; r[:, 1] += y
-            out.append(O.features(S, r)[0])
-        if len(out) == need:
-            used = i + 1
-    return (np.stack(out) if out else np.zeros((0, 608, 32), np.float32)), used
 
 
 @pytest.mark.parametrize("first,need", [(True, 700), (False, 60), (False, 100000)])

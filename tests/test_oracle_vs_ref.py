@@ -115,3 +115,36 @@ def test_detect_identical_on_deep_synthetic_cascades(tmp_path, seed, n_weak, the
         assert (d.counters[O.C_VISITED], d.counters[O.C_PREFILTER], d.counters[O.C_WEAK], d.counters[O.C_RAW]) == (cr[0], cr[1], cr[2], cr[3])
         reach = d.counters[O.C_REACH0:O.C_REACH0 + len(n_weak)]
         assert d.counters[O.C_VISITED] < d.counters[O.C_GRID] and (reach > 0).all()  # strides of 2 happen, every stage is entered
+
+
+@pytest.mark.parametrize("first,totals", [(True, [700, 300]), (False, [60, 25]), (False, [100000])])
+def test_fill_neg_samples_restatement(tmp_path, oracle_cascade, first, totals):
+    """Next row N2: the reference's own DenseSURFFeatureExtractor::FillNegSamples (:124-195), run on PGM files in a child
+    process (its image cursor is a function-local static), against the restatement the GPU mining test checks against:
+    same windows in the same order, bit-identical 608 x 32 samples, the same `done`, and -- through a second call on the same
+    extractor, the way CascadeClassifier::Train calls it -- the same cursor (the image after the one that completed a call)."""
+    import dataclasses
+    from cascade_util import fill_neg_restated, write_model_cfg
+    frames = [synth.negative_frame(20, 120, 160), np.zeros((30, 30), np.uint8), synth.frame(150, 200, 21), synth.negative_frame(22, 240, 320),
+              synth.frame(97, 131, 23)]
+    cfg = ""
+    bc = oracle_cascade
+    if not first:
+        # the trained cascade rejects almost everything on these frames: its first stage with a lower threshold accepts some
+        c = oracle_cascade.c
+        k = int(c.n_weak[0])
+        cut = dataclasses.replace(c, theta=np.array([0.40], np.float32), n_weak=c.n_weak[:1].copy(), patch_index=c.patch_index[:k].copy(),
+                                  w=c.w[:k].copy(), bias=c.bias[:k].copy())
+        cfg = str(tmp_path / "stage0.cfg")
+        write_model_cfg(cfg, cut)
+        from oracle import modelcfg
+        bc = O.BoundCascade(modelcfg.load(cfg))
+    got, dones = R.fill_neg(frames, cfg, totals, first)
+    start = 0
+    for call, need in enumerate(totals):
+        want, used = fill_neg_restated(frames[start:], need, first, bc)
+        assert got[call].shape == want.shape, (call, got[call].shape, want.shape)
+        assert np.array_equal(bits(got[call]), bits(want))
+        assert dones[call] == (len(want) == need)
+        start += used
+    assert len(got[0]) > 0
