@@ -101,3 +101,65 @@ def test_group_rectangles_matches_oracle():
         gr, gs = capi.group_rectangles(rects, scores)
         wr, ws = O.group_rectangles(rects, scores)
         assert np.array_equal(gr, wr) and np.array_equal(gs, ws)
+
+
+def _ref_load(path):
+    """The reference's own Model::Load (libconfig 1.4.9) through the harness, where it was compiled."""
+    import ctypes as C
+    from oracle import refbind as R
+    th = np.zeros(16, np.float32); nw = np.zeros(16, np.int32); pi = np.zeros(2048, np.int32); w = np.zeros((2048, 33), np.float32); bb = np.zeros(2048)
+    P = lambda x, t: x.ctypes.data_as(C.POINTER(t))
+    s = R.lib().ref_model_load(path.encode(), P(th, C.c_float), P(nw, C.c_int), 16, P(pi, C.c_int), P(w, C.c_float), P(bb, C.c_double), 2048)
+    k = int(nw[:max(s, 0)].sum())
+    return s, th[:max(s, 0)].copy(), nw[:max(s, 0)].copy(), pi[:k].copy(), w[:k].copy(), bb[:k].copy()
+
+
+def _restyle(text: str, style: int) -> str:
+    """The same settings in other spellings libconfig's grammar accepts (scanner.l / grammar.y of 1.4.9)."""
+    if style == 1:   # ':' for '=', comments of all three kinds, tabs, no ';' after groups and lists
+        text = text.replace(" = ", " : ").replace("};", "}").replace(");", ")")
+        text = "# model written by a test\n// another comment\n/* and a\n   block */\n" + text.replace("\n      ", "\n\t")
+    elif style == 2:  # ',' as the setting terminator, everything on few lines
+        text = text.replace(";\n", ",\n").replace("\n          ", " ")
+    return text
+
+
+@pytest.mark.parametrize("seed,n_weak,style", [(21, [2, 3], 0), (22, [1] * 10, 1), (23, [40, 7, 1], 2), (24, [3, 3, 3, 3], 1)])
+def test_model_reader_on_synthetic_models_matches_reference_loader(tmp_path, seed, n_weak, style):
+    """Row A12 beyond the one trained file: synthetic cascades (1..10 stages, up to 40 weak classifiers in a stage, weights over 60
+    orders of magnitude and in every float spelling libconfig scans) in three spellings of the format, read by the product's own
+    reader, by the oracle's parser and -- where it was compiled -- by the reference's Model::Load on libconfig 1.4.9."""
+    from cascade_util import random_cascade, write_model_cfg
+    rng = np.random.default_rng(seed)
+    c = random_cascade(seed, n_weak, list(rng.uniform(0.3, 0.7, len(n_weak))))
+    # stretch the weights: tiny, huge, exact integers, negative zero
+    flat = c.w.reshape(-1)
+    k = len(flat)
+    flat[rng.integers(0, k, k // 8)] *= np.float32(1e-30)
+    flat[rng.integers(0, k, k // 8)] *= np.float32(1e+30)
+    flat[rng.integers(0, k, k // 16)] = np.float32(3.0)
+    flat[rng.integers(0, k, k // 16)] = np.float32(-0.0)
+    path = str(tmp_path / "m.cfg")
+    write_model_cfg(path, c)
+    text = _restyle(open(path).read(), style)
+    if style == 2:  # other float spellings of the same values: "+x", "x." / ".x", exponent without a point
+        text = text.replace("bias = 1.0", "bias = +1.").replace("theta = 0.", "theta = .").replace("eps = 0.01", "eps = 1e-2").replace("C = 0.1", "C = 1E-1")
+    open(path, "w").write(text)
+    got = capi.model_flatten(path, 40)
+    want = M.load(path)
+    assert len(got["theta"]) == len(n_weak) == want.n_stages
+    assert np.array_equal(got["theta"].view(np.uint32), want.theta.view(np.uint32)) and np.array_equal(got["n_weak"], want.n_weak)
+    assert np.array_equal(got["patch_index"], want.patch_index) and np.array_equal(got["w"].view(np.uint32), want.w.view(np.uint32))
+    assert np.array_equal(got["bias"], want.bias)
+    assert np.array_equal(want.w.view(np.uint32), c.w.view(np.uint32)), "%.10g text does not round-trip float32"
+    from oracle import refbind as R
+    if R.available():
+        s, th, nw, pi, w, bb = _ref_load(path)
+        assert s == len(n_weak) and np.array_equal(th.view(np.uint32), got["theta"].view(np.uint32)) and np.array_equal(nw, got["n_weak"])
+        assert np.array_equal(pi, got["patch_index"]) and np.array_equal(w.view(np.uint32), got["w"].view(np.uint32)) and np.array_equal(bb, got["bias"])
+        # the product's writer (Model::Save) on the same cascade, read back by the reference's loader
+        out = str(tmp_path / "resaved.cfg")
+        capi.model_resave(path, out)
+        s2, th2, nw2, pi2, w2, bb2 = _ref_load(out)
+        assert s2 == s and np.array_equal(th2.view(np.uint32), th.view(np.uint32)) and np.array_equal(nw2, nw) and np.array_equal(pi2, pi)
+        assert np.array_equal(w2.view(np.uint32), w.view(np.uint32)) and np.array_equal(bb2, bb)
