@@ -112,12 +112,23 @@ void group_rectangles(std::vector<sc_rect>* rects, std::vector<double>* scores, 
     const std::vector<sc_rect>& r = *rects;
     std::vector<int> parent(n), cls(n, -1), first(n, -1);
     for (int i = 0; i < n; i++) parent[i] = i;
-    for (int i = 0; i < n; i++)
-        for (int j = i + 1; j < n; j++)
-            if (similar(r[i], r[j], eps)) {
-                const int a = find_root(parent, i), b = find_root(parent, j);
-                if (a != b) parent[std::max(a, b)] = std::min(a, b);
-            }
+    // cv::partition tests every pair; the classes are the connected components of `similar`, whatever the order the
+    // pairs are met in.  similar(a, b) needs |a.x - b.x| <= delta <= eps (a.w + a.h) / 2, so with the rectangles ordered
+    // by x only the partners inside that reach are tested (raw detection lists: 1080p frames with ~500 windows, ~6 x fewer
+    // tests).  Class numbers below are still given in index order, as cv::partition's first-seen labels are.
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return r[a].x != r[b].x ? r[a].x < r[b].x : a < b; });
+    for (int oi = 0; oi < n; oi++) {
+        const int i = order[oi];
+        const double reach = eps * (r[i].w + r[i].h) * 0.5;
+        for (int oj = oi + 1; oj < n; oj++) {
+            const int j = order[oj];
+            if ((double)(r[j].x - r[i].x) > reach) break;
+            const int a = find_root(parent, i), b = find_root(parent, j);
+            if (a != b && similar(r[i], r[j], eps)) parent[std::max(a, b)] = std::min(a, b);  // same class already: nothing to learn
+        }
+    }
     int k = 0;
     for (int i = 0; i < n; i++) {
         const int root = find_root(parent, i);

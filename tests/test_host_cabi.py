@@ -103,6 +103,40 @@ def test_group_rectangles_matches_oracle():
         assert np.array_equal(gr, wr) and np.array_equal(gs, ws)
 
 
+def test_group_rectangles_on_dense_and_spread_sets(oracle_cascade):
+    """The host grouping orders the rectangles by x and skips pairs that are out of reach or already in one class; the
+    classes, their first-seen numbering, means, swallow filter and scores must stay those of the all-pairs definition
+    (oracle = restatement of cv::groupRectangles): raw window lists of real frames (hundreds of windows in a few dense
+    clusters), crowded random sets of mixed sizes, chains that merge late, non-square rectangles, other thresholds."""
+    from surfcascade_b200 import synth
+    cases = []
+    for seed in (100, 101):
+        img = synth.frame(480, 640, seed)
+        d = O.detect(O.integral(img), oracle_cascade, O.params(base=40, nthreads=8))
+        cases.append((np.stack([d.x, d.y, d.l, d.l], 1).astype(np.int32), d.score.copy(), 2, 0.2))
+    rng = np.random.default_rng(7)
+    for n, span, lo, hi, thr, eps in ((1500, 900, 40, 300, 2, 0.2), (800, 200, 40, 60, 3, 0.2), (600, 3000, 40, 44, 1, 0.5), (400, 100, 30, 200, 2, 0.05)):
+        xy = rng.integers(0, span, size=(n, 2))
+        wh = rng.integers(lo, hi, size=(n, 2))
+        wh[: n // 2, 1] = wh[: n // 2, 0]  # half squares, half arbitrary
+        cases.append((np.concatenate([xy, wh], 1).astype(np.int32), rng.random(n) + 1.0, thr, eps))
+    # a chain along x whose links are each similar to the next only: one class, found across the ordered sweep
+    k = 300
+    chain = np.stack([np.arange(k) * 7, np.zeros(k, np.int64), np.full(k, 100), np.full(k, 100)], 1).astype(np.int32)
+    cases.append((chain[rng.permutation(k)], rng.random(k), 2, 0.2))
+    for rects, scores, thr, eps in cases:
+        gr, gs = capi.group_rectangles(rects, scores, thr, eps)
+        wr, ws = O.group_rectangles(rects, scores, thr, eps)
+        assert np.array_equal(gr, wr) and np.array_equal(gs, ws), (len(rects), thr, eps)
+        try:
+            import cv2  # the real OpenCV where the wheel is present (this container): same rectangles in the same order
+        except ImportError:
+            continue
+        cr, _ = cv2.groupRectangles(rects.tolist(), thr, eps)
+        assert np.array_equal(np.array(cr, np.int32).reshape(-1, 4), gr.reshape(-1, 4)), (len(rects), thr, eps)
+    assert len(cases[0][0]) > 100
+
+
 def _ref_load(path):
     """The reference's own Model::Load (libconfig 1.4.9) through the harness, where it was compiled."""
     import ctypes as C
