@@ -110,43 +110,78 @@ def make_frames(n: int):
 # ------------------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU detect path on the host cores
 # ------------------------------------------------------------------------------------------------------------
-def cpu_detect_once(frames, threads: int):
-    """Returns (seconds, kind, counters) for one pass of the reference CPU path over `frames`."""
+def cpu_reference_timing(frames, threads: int, warmup: int = 1):
+    """Per-frame (IntegralImage ms, scan ms) of the reference CPU path over `frames`, after `warmup` untimed frames.
+    oracle/_ref: the reference's own classes and lifted detect loop WITHOUT counter hooks, model loaded once, the two
+    phases timed separately (ref_detect_timed); else the plain-C port, timed the same way."""
     from oracle import refbind
     if refbind.available():
-        t = time.perf_counter()
-        r = refbind.detect(frames, MODEL, base=40, nthreads=threads, group=False)
-        return time.perf_counter() - t, "reference", r.counters[:, :4].sum(0).tolist()
+        ms_i, ms_s, raw = refbind.detect_timed(frames, MODEL, base=40, nthreads=threads, warmup=warmup)
+        return ms_i, ms_s, "reference", int(raw.sum())
     from oracle import modelcfg, oracle
     bc = oracle.BoundCascade(modelcfg.load(MODEL))
     prm = oracle.params(base=40, nthreads=threads)
-    t = time.perf_counter()
-    vis = 0
-    for f in frames:
-        d = oracle.detect(oracle.integral(f), bc, prm)
-        vis += int(d.counters[oracle.C_VISITED])
-    return time.perf_counter() - t, "port", [vis]
+    ms_i, ms_s, raw = [], [], 0
+    for k in range(-warmup, len(frames)):
+        f = frames[k % len(frames)]
+        t0 = time.perf_counter()
+        S = oracle.integral(f)
+        t1 = time.perf_counter()
+        d = oracle.detect(S, bc, prm)
+        t2 = time.perf_counter()
+        if k >= 0:
+            ms_i.append(1e3 * (t1 - t0)); ms_s.append(1e3 * (t2 - t1)); raw += len(d.x)
+    return np.array(ms_i), np.array(ms_s), "port", raw
+
+
+def cpu_baseline_block(n_all: int, n_single: int, threads: int) -> dict:
+    """`cpu_baseline` of a bench line: n_all frames on all host threads and n_single frames on one thread."""
+    fr = make_frames(max(n_all, n_single, 2))
+    ms_i, ms_s, kind, raw = cpu_reference_timing([fr[i % len(fr)] for i in range(n_all)], threads, warmup=1)
+    tot = ms_i + ms_s
+    out = {"value": 1e3 * len(tot) / float(tot.sum()), "unit": "frames/s", "cores": threads, "kind": kind, "cpu_model": cpu_model(),
+           "median_ms_per_frame": float(np.median(tot)), "median_ms_integral": float(np.median(ms_i)), "median_ms_scan": float(np.median(ms_s)),
+           "raw_detections": raw}
+    single = None
+    if n_single > 0 and threads > 1:
+        si, ss, _, _ = cpu_reference_timing([fr[i % len(fr)] for i in range(n_single)], 1, warmup=0)
+        single = float(np.median(si + ss))
+        out["single_thread"] = {"frames_per_s": 1e3 / single, "median_ms_integral": float(np.median(si)), "median_ms_scan": float(np.median(ss)),
+                                "parallel_efficiency": (single / float(np.median(tot))) / threads}
+    out["sample"] = (f"{n_all} frames of the C2 workload after 1 warm-up frame on all {threads} host threads (OpenMP over scales as in "
+                     f"ObjDetector.cpp:177, OMP_PROC_BIND=spread), value = frames / summed per-frame time; hook-free timing build of the "
+                     f"reference (no counters in the window loop), model loaded once, IntegralImage and scan timed separately"
+                     + (f"; {n_single} frame(s) on 1 thread" if single else ""))
+    return out
+
+
+CONFIG = {"workload": WORKLOAD, "frame": "1920x1080", "base": 40, "step": 2, "scale": 1.1, "cascade": "tests/golden/model_c1.cfg (4 stages, 3/6/7/6 weak classifiers)"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ.setdefault("OMP_PROC_BIND", "spread")
     threads = os.cpu_count() or 1
-    frames = make_frames(2)
-    per_step = 1  # frames per step: a bounded sample of the C2 workload
-    for i in range(args.warmup):
-        cpu_detect_once(frames[:per_step], threads)
-    t_total, kind = 0.0, "port"
-    for i in range(args.steps):
-        dt, kind, _ = cpu_detect_once([frames[i % len(frames)]] * per_step, threads)
-        t_total += dt
-    fps = args.steps * per_step / t_total
+    fr = make_frames(min(max(args.steps, 1), N_UNIQUE))
+    frames = [fr[i % len(fr)] for i in range(args.steps)]
+    ms_i, ms_s, kind, raw = cpu_reference_timing(frames, threads, warmup=args.warmup)
+    tot = ms_i + ms_s
+    t_total = float(tot.sum()) / 1e3
+    fps = args.steps / t_total
+    single = cpu_reference_timing(frames[:1], 1, warmup=0) if threads > 1 else None
     line = {"impl": "reference", "metric": "1080p full-scale-range detection throughput", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "frames_per_step": per_step},
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
+            "run": {"frames_per_step": 1, "threads": threads},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "cpu_model": cpu_model(),
-                             "sample": f"{per_step} frame(s) of the C2 workload per step, OpenMP over scales as in ObjDetector.cpp:177"},
+                             "median_ms_per_frame": float(np.median(tot)), "median_ms_integral": float(np.median(ms_i)),
+                             "median_ms_scan": float(np.median(ms_s)), "raw_detections": raw,
+                             "single_thread_frames_per_s": (1e3 / float((single[0] + single[1])[0])) if single else None,
+                             "sample": f"{args.steps} step(s) of 1 frame of the C2 workload after {args.warmup} warm-up frame(s), all {threads} host threads "
+                                       "(OpenMP over scales as in ObjDetector.cpp:177); hook-free timing build of the reference, model loaded once, "
+                                       "IntegralImage and scan timed separately; value = frames / summed per-frame time"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -155,6 +190,7 @@ def run_reference(args):
 # our arm
 # ------------------------------------------------------------------------------------------------------------
 def run_ours(args):
+    os.environ.setdefault("OMP_PROC_BIND", "spread")  # for the cpu_baseline leg (read when the OpenMP runtime starts)
     import torch
     import torch.distributed as dist
     from surfcascade_b200 import capi
@@ -348,21 +384,16 @@ def run_ours(args):
         cpu = None
         if world == 1:
             try:
-                th = os.cpu_count() or 1
-                fr = make_frames(2)
-                cpu_detect_once(fr[:1], th)
-                dt, kind, _ = cpu_detect_once(fr, th)
-                dt1, _, _ = cpu_detect_once(fr[:1], 1)
-                cpu = {"value": len(fr) / dt, "unit": "frames/s", "cores": th, "kind": kind, "cpu_model": cpu_model(),
-                       "sample": f"2 frames of the C2 workload, all {th} host threads (OpenMP over scales, ObjDetector.cpp:177); single-thread: {1.0 / dt1:.3f} frames/s"}
+                cpu = cpu_baseline_block(5, 2, os.cpu_count() or 1)
             except Exception as e:  # the checker is optional for the product arm
                 cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
         line = {
             "metric": "1080p full-scale-range detection throughput", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "parallelism": f"frames sharded over {world} GPU(s)",
-                       "l2": f"inputs rotate over {n_sets} batches ({n_sets * B * W * H / 1e6:.0f} MB) and each step writes {B * 66.4:.0f} MB of integral images: larger than the 126 MB L2"},
+            "config": CONFIG,
+            "run": {"frames_per_step_per_gpu": B, "parallelism": f"frames sharded over {world} GPU(s)",
+                    "l2": f"inputs rotate over {n_sets} batches ({n_sets * B * W * H / 1e6:.0f} MB) and each step writes {B * 99.7:.0f} MB of integral images: larger than the 126 MB L2"},
             "windows_per_s": {"grid": fps * grid, "reference_visited": fps * mean(lambda x: x.visited)},
             "work_per_frame": {"grid_windows": grid, "visited": mean(lambda x: x.visited), "prefilter_pass": mean(lambda x: x.prefilter_pass),
                                "weak_evals_reference": weak_ref, "raw_detections": mean(lambda x: x.raw)},

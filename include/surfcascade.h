@@ -101,8 +101,9 @@ int sc_set_cascade(sc_handle* h, const sc_cascade_desc* desc);
 /* Model::Load (Model.cpp:97-193) on a libconfig model.cfg, ExtractPatches (DenseSURFFeatureExtractor.cpp:49-63) on a
  * tmpl x tmpl template, flatten and upload. */
 int sc_load_model(sc_handle* h, const char* model_cfg_path, int tmpl);
-/* Host-only: Model::Load + flatten without touching a device.  Fills at most max_stages / max_weak entries and
- * returns the number of stages (or a negative sc_status); *total_weak receives the weak classifier count. */
+/* Host-only: Model::Load + flatten without touching a device.  Returns the number of stages (or a negative sc_status);
+ * *total_weak receives the weak classifier count.  A cascade with more than max_stages stages or max_weak weak
+ * classifiers returns SC_ERR_CAPACITY (nothing truncated is handed out; *total_weak still tells the size needed). */
 int sc_model_flatten(const char* model_cfg_path, int tmpl, float* theta, int32_t* n_weak, int max_stages,
                      sc_rect* rects, int32_t* patch_index, float* w /* [max_weak][33] */, double* bias, int max_weak, int* total_weak);
 /* Host-only: Model::Load followed by Model::Save (Model.cpp:21-95) to another path. */
@@ -121,6 +122,18 @@ int sc_integral(sc_handle* h, const uint8_t* gray, int W, int H, int stride, flo
  * sc_detect's integral stage; sc_integral keeps a step-1 layout for explicit rects), copied to the host in the reference's
  * interleaved form.  Parity hook for IntegralImage (DenseSURFFeatureExtractor.cpp:65-87) on the production path. */
 int sc_integral_scan_layout(sc_handle* h, const uint8_t* gray, int W, int H, int stride, int step, float* out);
+/* Parity hooks of the compact integer plane the stage-0 filter reads beside the float32 integral (16 bytes per corner;
+ * csrc/sc_plan.h).  It restates the same IntegralImage (DenseSURFFeatureExtractor.cpp:65-87) as exact integers:
+ * word k of pixel (X,Y) = (I[2k+1] << 16) + I[2k] mod 2^32, I[c] = exact integral of channel c.
+ *   sc_integral_compact : that plane through the scan's kernels and layout for lattice step `step`, in pixel order,
+ *                         out[(H+1)][(W+1)][4] uint32;
+ *   sc_box_sums_compact : CalcFeature's 32 box sums (:379-415, before Normalize) of explicit rects read from the compact
+ *                         plane of the current sc_integral image -- valid where every cell's sums are < 65536;
+ *   sc_cell_bounds      : the per-frame certificate: for each cell edge ce[i] an upper bound of every ce x ce box sum of
+ *                         every channel of the current sc_integral image (the filter uses the plane iff bound < 65536). */
+int sc_integral_compact(sc_handle* h, const uint8_t* gray, int W, int H, int stride, int step, uint32_t* out);
+int sc_box_sums_compact(sc_handle* h, const sc_rect* rects, int n, float* out /* [n][32] */);
+int sc_cell_bounds(sc_handle* h, const int32_t* ce, int n, uint32_t* out /* [n] */);
 /* DenseSURFFeatureExtractor::CalcFeature (+GetRectsFromPatch, Normalize; :360-457) on the current integral. */
 int sc_features(sc_handle* h, const sc_rect* rects, int n, float* out /* [n][32] */);
 /* DenseSURFFeatureExtractor::sum (:351-358). */

@@ -289,6 +289,52 @@ int ref_detect_frames(const uint8_t* const* frames, int nframes, int W, int H, c
     return 0;
 }
 
+// Timing entry (bench.py's CPU legs): the same lifted setup and loop as ref_detect_frames, but with the counter
+// hooks compiled to nothing -- ref_detect_frames increments SHARED counters with `omp atomic` inside the innermost
+// window loop (tens of millions of contended atomics per 1080p frame), which slows the reference down and would
+// inflate every GPU / CPU ratio.  The model is loaded and the pool built ONCE per call, outside the timed per-frame
+// regions; IntegralImage and the scan are timed separately per frame; `warmup` leading
+// frames are run untimed (frames[0..warmup) are processed first, then all nframes are timed).
+// Returns 0; n_raw[j] = raw windows of frame j (sanity check against the counting build).
+int ref_detect_timed(const uint8_t* const* frames, int nframes, int W, int H, const char* model_cfg, int base, int nthreads, int warmup,
+                     double* ms_integral, double* ms_scan, int64_t* n_raw) {
+    CoutSilencer quiet(true);
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+    Model model(model_cfg);
+    int length = base;
+    Rect win(0, 0, length, length);
+    {
+        std::ifstream probe(model_cfg);
+        if (!probe.good()) return -1;
+    }
+#include "detect_setup.inc"
+    if (cascade_classifier.stage_classifiers.empty()) return -2;
+#define REF_VISIT() do {} while (0)
+#define REF_PREFILTER() do {} while (0)
+#define REF_STAGE(p, nweak) do {} while (0)
+    for (int jj = -warmup; jj < nframes; jj++) {
+        const int j = jj < 0 ? (jj + warmup) % nframes : jj;
+        Mat img = wrap_u8(frames[j], W, H);
+        double t0 = now_ms();
+        dense_surf_feature_extractor.IntegralImage(img);
+        double t1 = now_ms();
+#include "detect_loop.inc"
+        double t2 = now_ms();
+        release_integral(dense_surf_feature_extractor);
+        if (jj >= 0) {
+            if (ms_integral) ms_integral[j] = t1 - t0;
+            if (ms_scan) ms_scan[j] = t2 - t1;
+            if (n_raw) n_raw[j] = (int64_t)wins.size();
+        }
+        wins.clear();
+        scores.clear();
+    }
+#undef REF_VISIT
+#undef REF_PREFILTER
+#undef REF_STAGE
+    return 0;
+}
+
 // Candidate scoring of one boosting round exactly as GentleAdaboost::Train does it (GentleAdaboost.cpp:145-148): the
 // stage holds the T already chosen weak classifiers (prev_* arrays), candidate k is pushed, StageClassifier::Evaluate
 // (StageClassifier.cpp:35-70) is called on the whole set, the candidate is popped.  X [N][P][32], positives first.

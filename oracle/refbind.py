@@ -145,6 +145,22 @@ def detect(frames, model_cfg: str, base: int = 40, nthreads: int = 1, group: boo
                          gf[:g].copy(), gr[:g].copy(), gs[:g].copy())
 
 
+def detect_timed(frames, model_cfg: str, base: int = 40, nthreads: int = 1, warmup: int = 1):
+    """Timing build of the reference detect loop: no counter hooks in the window loop, model loaded once per call,
+    IntegralImage and scan timed separately per frame (ref_detect_timed).  Returns (ms_integral[n], ms_scan[n], n_raw[n])."""
+    frames = [np.ascontiguousarray(f, dtype=np.uint8) for f in frames]
+    h, w = frames[0].shape
+    assert all(f.shape == (h, w) for f in frames)
+    n = len(frames)
+    ptrs = (C.POINTER(C.c_uint8) * n)(*[f.ctypes.data_as(C.POINTER(C.c_uint8)) for f in frames])
+    ms_i = np.zeros(n, np.float64); ms_s = np.zeros(n, np.float64); raw = np.zeros(n, np.int64)
+    P = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    rc = lib().ref_detect_timed(ptrs, n, w, h, model_cfg.encode(), base, nthreads, warmup, P(ms_i, C.c_double), P(ms_s, C.c_double), P(raw, C.c_int64))
+    if rc != 0:
+        raise RuntimeError(f"ref_detect_timed failed ({rc})")
+    return ms_i, ms_s, raw
+
+
 def train(prefix: str, pos_list: str, neg_list: str, out_cfg: str, verbose: bool = False) -> int:
     """The reference --train branch (ObjDetector.cpp:66-91).  Once per process (static cursors)."""
     if not prefix.endswith("/"):

@@ -44,7 +44,8 @@ EXPORTS = ["sc_create", "sc_destroy", "sc_last_error", "sc_version", "sc_set_cas
            "sc_integral", "sc_features", "sc_window_sum", "sc_stage_scores", "sc_weak_predict", "sc_stage_predict", "sc_detect",
            "sc_detect_device", "sc_sync", "sc_last_counters", "sc_stream", "sc_launch_count", "sc_group_rectangles",
            "sc_set_profiling", "sc_kernel_stats", "sc_model_flatten", "sc_model_resave", "sc_pool_eval", "sc_pool_hist_device",
-           "sc_pool_auc_device", "sc_probe_gather", "sc_probe_stream", "sc_stage0_fast_check", "sc_detect_submit", "sc_detect_collect", "sc_extract_pool_features", "sc_extract_pool_features_device", "sc_mine_negatives", "sc_integral_scan_layout"]
+           "sc_pool_auc_device", "sc_probe_gather", "sc_probe_stream", "sc_stage0_fast_check", "sc_detect_submit", "sc_detect_collect", "sc_extract_pool_features", "sc_extract_pool_features_device", "sc_mine_negatives", "sc_integral_scan_layout",
+           "sc_integral_compact", "sc_box_sums_compact", "sc_cell_bounds"]
 
 _lib = None
 
@@ -77,6 +78,9 @@ def lib():
         L.sc_project_patches.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.sc_integral.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.sc_integral_scan_layout.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.sc_integral_compact.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.sc_box_sums_compact.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.sc_cell_bounds.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.sc_features.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.sc_window_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.sc_stage_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -220,6 +224,28 @@ class Handle:
         h, w = img.shape
         out = np.empty((h + 1, w + 1, 8), np.float32)
         self._check(lib().sc_integral_scan_layout(self._h, img.ctypes.data, w, h, w, step, out.ctypes.data))
+        return out
+
+    def integral_compact(self, img: np.ndarray, step: int = 2) -> np.ndarray:
+        """The compact integer plane (csrc/sc_plan.h) through the scan's kernels and layout: uint32 [H+1][W+1][4]."""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        out = np.empty((h + 1, w + 1, 4), np.uint32)
+        self._check(lib().sc_integral_compact(self._h, img.ctypes.data, w, h, w, step, out.ctypes.data))
+        return out
+
+    def box_sums_compact(self, rects) -> np.ndarray:
+        """CalcFeature's 32 box sums (before Normalize) of explicit rects, read from the compact plane of the last integral()."""
+        r = np.ascontiguousarray(rects, np.int32).reshape(-1, 4)
+        out = np.zeros((len(r), 32), np.float32)
+        self._check(lib().sc_box_sums_compact(self._h, r.ctypes.data, len(r), out.ctypes.data))
+        return out
+
+    def cell_bounds(self, ces) -> np.ndarray:
+        """Per cell edge: certified upper bound of every ce x ce box sum of every channel of the last integral()."""
+        c = np.ascontiguousarray(ces, np.int32).reshape(-1)
+        out = np.zeros(len(c), np.uint32)
+        self._check(lib().sc_cell_bounds(self._h, c.ctypes.data, len(c), out.ctypes.data))
         return out
 
     def features(self, rects) -> np.ndarray:

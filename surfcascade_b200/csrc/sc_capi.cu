@@ -82,6 +82,10 @@ struct sc_handle {
     bool allow_fast = true;     // SC_DISABLE_FAST=1 in the environment forces the exact-only kernel (A/B tests)
     bool use_fast = false;
     ScFastParams fast[2];
+    // compact integer plane (sc_plan.h): distinct projected cell edges of the stage-0 patches that need a per-frame bound
+    bool allow_compact = true;  // SC_DISABLE_COMPACT=1 in the environment keeps the filter on the float planes (A/B tests)
+    std::vector<int> cert_ce;
+    DevBuf d_cert_items, d_cert;   // [n_items] cell edges; [int_frames][n_items] bounds (k_cell_bounds)
     bool group_attr_set = false;  // k_group_frames' dynamic shared-memory limit raised on this handle's device
     int group_max = 8;  // frames per scan group (SC_GROUP_FRAMES overrides, 1..32)
 
@@ -142,6 +146,8 @@ namespace {
 // d_small layout (uint32): [0] rec_count, [1..16] per-stage index-list counts, [17] det_count
 enum { SM_REC = 0, SM_STAGE0 = 1, SM_DET = 17, SM_CHUNKS = 18, SM_CURSOR = 19, SM_WORDS = 32 };
 
+bool any_ticket_busy(const sc_handle* h) { return h->tickets[0].busy || h->tickets[1].busy; }
+
 int fail(sc_handle* h, int code, const std::string& msg) {
     if (h) h->err = msg;
     return code;
@@ -157,9 +163,9 @@ int cuda_fail(sc_handle* h, cudaError_t e, const char* what) {
         if (e_ != cudaSuccess) return cuda_fail((h), e_, #call); \
     } while (0)
 
-enum { K_CARRY = 0, K_WALK, K_STAGE0, K_STAGE, K_REPLAY, K_FINALIZE, K_EVENTS, K_POOL, K_STAGE0_ODD, K_GROUP, K_POOLFEAT, K_COUNT };
+enum { K_CARRY = 0, K_WALK, K_STAGE0, K_STAGE, K_REPLAY, K_FINALIZE, K_EVENTS, K_POOL, K_STAGE0_ODD, K_GROUP, K_POOLFEAT, K_CERT, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"k_strip_carry", "k_integral_walk", "k_scan_stage0", "k_scan_stage", "k_replay_rows", "k_finalize",
-                                            "k_row_events", "k_pool_hist", "k_scan_stage0_odd", "k_group_frames", "k_pool_features"};
+                                            "k_row_events", "k_pool_hist", "k_scan_stage0_odd", "k_group_frames", "k_pool_features", "k_cell_bounds"};
 
 cudaEvent_t take_event(sc_handle* h) {
     cudaEvent_t e = nullptr;
@@ -215,6 +221,21 @@ double fast_margin(const sc_handle* h) {
         margin += 2.0 * (0.25 * 121.0 * u * std::sqrt(n2) + 1.5e-6);
     }
     return margin + (double)n0 * n0 * 4.0 * u + 8.0 * u * n0;
+}
+
+// Compact-plane certification item of one projected stage-0 patch (sc_kernels.cuh, k_cell_bounds): its cells are ce x ce
+// (GetRectsFromPatch, DenseSURFFeatureExtractor.cpp:360-377).  255 ce^2 < 65536 needs no frame-dependent bound.
+uint32_t cert_item(sc_handle* h, int l, const sc_rect& patch) {
+    if (!h->allow_compact) return SC_CERT_NEVER;
+    const sc_rect r = sc_host::project_patch(h->tmpl, l, patch);
+    const int ce = r.w == r.h ? r.w / 2 : std::min(r.w, r.h);
+    if (ce < 1) return SC_CERT_NEVER;
+    if (255LL * ce * ce < (long long)SC_CELL_LIMIT) return SC_CERT_ALWAYS;
+    for (size_t i = 0; i < h->cert_ce.size(); i++)
+        if (h->cert_ce[i] == ce) return (uint32_t)i;
+    if ((int)h->cert_ce.size() >= SC_CERT_MAX_ITEMS) return SC_CERT_NEVER;
+    h->cert_ce.push_back(ce);
+    return (uint32_t)(h->cert_ce.size() - 1);
 }
 
 // Scale ladder, lattice and per-(scale, weak) projected geometry.  Host arithmetic mirrors ObjDetector.cpp:139,174,180
@@ -284,6 +305,7 @@ int build_plan(sc_handle* h, int W, int H, const sc_detect_params& prm, std::vec
     // Certified fast filter for stage 0 (sc_kernels.cuh, "Error budget").  Limits are on the float sum of the fast weak outputs.
     const int n0 = h->n_weak[0];
     h->use_fast = fast_plan && nsc >= 1;
+    h->cert_ce.clear();
     if (h->use_fast) {
         const double margin = fast_margin(h);
         const double tau = 0.5 * h->n_stages - 1.0;           // rejected at stage 0: multi == 2  <=>  score < tau (ObjDetector.cpp:201,214)
@@ -305,6 +327,7 @@ int build_plan(sc_handle* h, int W, int H, const sc_detect_params& prm, std::vec
                     const ScGeom& g = (*geom_out)[((size_t)ph * nsc + i) * h->total_weak + q];
                     for (int k = 0; k < 10; k++) fp.geom[i][q][k] = g.c[k];
                     fp.geom[i][q][10] = (uint32_t)g.shape;
+                    fp.geom[i][q][11] = cert_item(h, p.sc[i].l, h->rects[q]);
                 }
             }
         }
@@ -324,10 +347,13 @@ int ensure_plan(sc_handle* h, int W, int H, const sc_detect_params& prm) {
     SC_CUDA(h, cudaStreamSynchronize(h->stream));
     SC_CUDA(h, cudaMemcpy(h->d_plan.p, &h->plan, sizeof(ScPlan), cudaMemcpyHostToDevice));
     if (!geom.empty()) SC_CUDA(h, cudaMemcpy(h->d_geom.p, geom.data(), geom.size() * sizeof(ScGeom), cudaMemcpyHostToDevice));
+    SC_CUDA(h, h->d_cert_items.ensure(std::max<size_t>(h->cert_ce.size(), 1) * sizeof(int)));
+    if (!h->cert_ce.empty()) SC_CUDA(h, cudaMemcpy(h->d_cert_items.p, h->cert_ce.data(), h->cert_ce.size() * sizeof(int), cudaMemcpyHostToDevice));
     h->pparams = prm;
     h->have_plan = true;
     h->group_frames = 0;  // buffers are re-sized for the new plan
     h->int_frames = 0;
+    h->n_lanes = 0;       // and the lane count is chosen from the new plan alone (a C4-sized plan must not inherit 4 lanes)
     return SC_OK;
 }
 
@@ -340,11 +366,15 @@ int ensure_group_buffers(sc_handle* h, int want_frames, bool own_images) {
                              (size_t)p.H * p.n_strips * 32 + (size_t)p.W * p.H;
     int g = (int)std::max<size_t>(1, std::min<size_t>((size_t)h->group_max, ((size_t)6 << 30) / std::max<size_t>(per_frame, 1)));
     g = std::min(g, std::max(want_frames, 1));
+    // k_scan_odd's work list packs (row index of the group) << 10 | unit: at most 2^22 lattice rows per scan group
+    // (units per row <= ceil(32768 / SC_ODD_UNIT) = 256 < 1024 because a scale has at most 65535 columns)
+    if ((long long)p.rows_per_frame >= (1LL << 22)) return fail(h, SC_ERR_INVALID, "too many lattice rows per frame for the scan's work list");
+    while (g > 1 && (long long)g * p.rows_per_frame >= (1LL << 22)) g--;
     // the integral stage runs on a larger super-group (its warps walk rows sequentially and need many frames in flight)
     const size_t int_frame = (size_t)p.lay.frame4 * 16 + (size_t)p.H * p.n_strips * 32 + (size_t)p.W * p.H;
     int gi = (int)std::max<size_t>(1, std::min<size_t>(32, ((size_t)4 << 30) / std::max<size_t>(int_frame, 1)));
     gi = std::max(g, std::min(gi, std::max(want_frames, 1)));
-    g = std::max(g, h->group_frames);
+    g = std::max(g, h->group_frames);  // (group_frames obeyed the same limits when it was chosen for this plan)
     gi = std::max(gi, h->int_frames);
     const unsigned long long recs = (unsigned long long)p.windows_per_frame * g;
     if (recs > 0xfffffff0ull) return fail(h, SC_ERR_INVALID, "too many windows per group");
@@ -353,6 +383,7 @@ int ensure_group_buffers(sc_handle* h, int want_frames, bool own_images) {
     if (own_images) SC_CUDA(h, h->d_img.ensure(align256((size_t)gi * p.W * p.H)));
     SC_CUDA(h, h->d_carry.ensure(align256((size_t)gi * p.H * p.n_strips * 32)));
     SC_CUDA(h, h->d_S.ensure((size_t)gi * p.lay.frame4 * 16));
+    SC_CUDA(h, h->d_cert.ensure(std::max<size_t>((size_t)gi * h->cert_ce.size(), 1) * 4));
     // a second lane only when more than one scan group can be in flight and the worst-case record arrays stay modest
     h->n_lanes = want_lanes;
     for (int li = 0; li < h->n_lanes; li++) {
@@ -395,6 +426,15 @@ int run_integral(sc_handle* h, const uint8_t* d_img, int n, int slot0, bool unde
             sck::k_integral_walk_tiled<<<(warps + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, n, carry, S, p.lay);
         else
             sck::k_integral_walk<<<(warps + 3) / 4, 128, 0, st>>>(d_img, p.W, p.H, p.n_strips, n, carry, S, p.lay);
+    }
+    const int n_items = (int)h->cert_ce.size();
+    if (h->use_fast && n_items > 0) {
+        // per-frame cell-sum bounds that certify the compact plane for this batch's stage-0 filter (k_cell_bounds)
+        uint32_t* cert = h->d_cert.as<uint32_t>() + (size_t)slot0 * n_items;
+        SC_CUDA(h, cudaMemsetAsync(cert, 0, (size_t)n * n_items * 4, st));
+        const int chunks = 4;
+        KernelSpan ks(h, K_CERT);
+        sck::k_cell_bounds<<<dim3(n_items * chunks, n), 256, 0, st>>>(S, p.lay, p.W, p.H, h->d_cert_items.as<int>(), n_items, chunks, cert);
     }
     SC_CUDA(h, cudaGetLastError());
     return SC_OK;
@@ -447,6 +487,8 @@ int run_group(sc_handle* h, sc_handle::Lane& L, int s0, int g, int frame0, sc_de
         uint32_t* pass = L.d_pass.as<uint32_t>();
         uint32_t* visited = L.d_visited.as<uint32_t>();
         ScRecord* rec = L.d_rec.as<ScRecord>();
+        const int n_items = (int)h->cert_ce.size();
+        const uint32_t* cert = (h->use_fast && h->allow_compact) ? h->d_cert.as<uint32_t>() + (size_t)s0 * n_items : nullptr;
         // force_all: every stage of every window is evaluated inside the stage-0 tile kernel (its ALL variant), as long as
         // the whole cascade's weights and geometry fit its shared memory (200 B per weak classifier)
         const bool all_in_tile = p.force_all && !h->use_fast && p.n_stages > 1 && p.total_weak <= 200;
@@ -457,7 +499,7 @@ int run_group(sc_handle* h, sc_handle::Lane& L, int s0, int g, int frame0, sc_de
             const int rows0 = g * p.rows_per_frame;
             {
                 KernelSpan ks(h, K_STAGE0, st);
-                launch_stage0(h->use_fast, all_in_tile, p.lay.hp, g * p.blocks_per_frame, smem, st, h->fast[0], dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, 0, start_odd);
+                launch_stage0(h->use_fast, all_in_tile, p.lay.hp, g * p.blocks_per_frame, smem, st, h->fast[0], dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, 0, start_odd, cert, n_items);
             }
             // odd columns: with the adaptive stride they are reachable only as ragged row suffixes -> list of 32-window runs
             // and persistent warps (k_scan_odd); without it (or without the fast filter) the tile kernel does them all
@@ -483,7 +525,7 @@ int run_group(sc_handle* h, sc_handle::Lane& L, int s0, int g, int frame0, sc_de
                 const int grid = h->n_sms * SC_STAGE0_MIN_CTAS;
                 switch (p.lay.hp) {
 #define SC_ODD(HPV) sck::k_scan_odd<HPV><<<grid, 256, 0, st>>>(h->fast[1], dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, start_odd, \
-                                                            L.d_chunks.as<uint32_t>() + rows0 + (rows0 + 1023) / 1024, small + SM_CHUNKS, small + SM_CURSOR)
+                                                            L.d_chunks.as<uint32_t>() + rows0 + (rows0 + 1023) / 1024, small + SM_CHUNKS, small + SM_CURSOR, cert, n_items)
                     case 256: SC_ODD(256); break;
                     case 512: SC_ODD(512); break;
                     case 1024: SC_ODD(1024); break;
@@ -492,7 +534,7 @@ int run_group(sc_handle* h, sc_handle::Lane& L, int s0, int g, int frame0, sc_de
 #undef SC_ODD
                 }
             } else {
-                launch_stage0(h->use_fast, all_in_tile, p.lay.hp, g * p.blocks_per_frame, smem, st, h->fast[1], dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, 1, start_odd);
+                launch_stage0(h->use_fast, all_in_tile, p.lay.hp, g * p.blocks_per_frame, smem, st, h->fast[1], dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, 1, start_odd, cert, n_items);
             }
         }
         const int tail_grid = h->n_sms * 8;
@@ -650,6 +692,8 @@ int sc_create(int device, sc_handle** out) {
     cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device);
     const char* nofast = getenv("SC_DISABLE_FAST");
     h->allow_fast = !(nofast && nofast[0] == '1');
+    const char* nocompact = getenv("SC_DISABLE_COMPACT");
+    h->allow_compact = !(nocompact && nocompact[0] == '1');
     const char* sgf = getenv("SC_GROUP_FRAMES");
     if (sgf) h->group_max = std::min(32, std::max(1, atoi(sgf)));
     const char* sln = getenv("SC_LANES");
@@ -675,7 +719,7 @@ void sc_destroy(sc_handle* h) {
     }
     for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
     if (h->copy_st) { cudaStreamSynchronize(h->copy_st); cudaStreamDestroy(h->copy_st); }
-    DevBuf* bufs[] = {&h->d_w, &h->d_wb, &h->d_plan, &h->d_geom, &h->d_img, &h->d_carry, &h->d_S, &h->d_counters, &h->d_det, &h->d_detcount, &h->d_pool_w, &h->d_pool_wb, &h->d_pool_auc, &h->d_pool_x, &h->d_pool_aux, &h->d_hook_img, &h->d_hook_carry, &h->d_hook_S, &h->d_ext_img, &h->d_ext_geom, &h->d_ext_X};
+    DevBuf* bufs[] = {&h->d_w, &h->d_wb, &h->d_plan, &h->d_geom, &h->d_img, &h->d_carry, &h->d_S, &h->d_counters, &h->d_det, &h->d_detcount, &h->d_pool_w, &h->d_pool_wb, &h->d_pool_auc, &h->d_pool_x, &h->d_pool_aux, &h->d_hook_img, &h->d_hook_carry, &h->d_hook_S, &h->d_ext_img, &h->d_ext_geom, &h->d_ext_X, &h->d_cert_items, &h->d_cert};
     for (DevBuf* b : bufs) b->release();
     h->h_stage.release();
     for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -689,13 +733,36 @@ int64_t sc_launch_count(const sc_handle* h) { return h ? h->launches : 0; }
 
 int sc_set_cascade(sc_handle* h, const sc_cascade_desc* d) {
     if (!h || !d) return SC_ERR_INVALID;
+    if (any_ticket_busy(h)) return fail(h, SC_ERR_STATE, "a batch is in flight: collect it before changing the cascade");
     if (d->n_stages < 1 || d->n_stages > SC_MAX_STAGES || d->tmpl < 12) return fail(h, SC_ERR_INVALID, "n_stages must be 1..16, tmpl >= 12");
+    if (!d->theta || !d->n_weak || !d->rects || !d->w || !d->bias) return fail(h, SC_ERR_INVALID, "null cascade arrays");
     SC_CUDA(h, cudaSetDevice(h->device));
+    // everything is validated and staged in locals first; the handle changes only after the uploads succeeded, and from
+    // here until then it holds no cascade at all (a failed call must not leave new host data beside old device weights)
     int total = 0;
     for (int s = 0; s < d->n_stages; s++) {
         if (d->n_weak[s] < 1) return fail(h, SC_ERR_INVALID, "stage without weak classifiers");
         total += d->n_weak[s];
     }
+    for (int k = 0; k < total; k++) {
+        const sc_rect& r = d->rects[k];
+        const bool ok = r.w > 0 && r.h > 0 && r.x >= 0 && r.y >= 0 && r.x + r.w <= d->tmpl && r.y + r.h <= d->tmpl &&
+                        (r.w == r.h || r.w == 4 * r.h || r.h == 4 * r.w);
+        if (!ok) return fail(h, SC_ERR_INVALID, "weak classifier rect outside the template or not 2x2 / 4x1 / 1x4 cells");
+    }
+    std::vector<float> w36((size_t)total * SC_W_PITCH, 0.f);
+    std::vector<double> wb(total);
+    for (int k = 0; k < total; k++) {
+        memcpy(&w36[(size_t)k * SC_W_PITCH], &d->w[(size_t)k * 33], 33 * sizeof(float));
+        wb[k] = (double)d->w[(size_t)k * 33 + 32] * d->bias[k];  // prob += w[32] * bias, LogisticRegression.cpp:64
+    }
+    h->have_cascade = false;
+    h->have_plan = false;
+    SC_CUDA(h, cudaStreamSynchronize(h->stream));
+    SC_CUDA(h, h->d_w.ensure(w36.size() * sizeof(float)));
+    SC_CUDA(h, h->d_wb.ensure(wb.size() * sizeof(double)));
+    SC_CUDA(h, cudaMemcpy(h->d_w.p, w36.data(), w36.size() * sizeof(float), cudaMemcpyHostToDevice));
+    SC_CUDA(h, cudaMemcpy(h->d_wb.p, wb.data(), wb.size() * sizeof(double), cudaMemcpyHostToDevice));
     h->tmpl = d->tmpl; h->n_stages = d->n_stages; h->total_weak = total;
     h->theta.assign(d->theta, d->theta + d->n_stages);
     h->n_weak.assign(d->n_weak, d->n_weak + d->n_stages);
@@ -704,25 +771,7 @@ int sc_set_cascade(sc_handle* h, const sc_cascade_desc* d) {
     h->rects.assign(d->rects, d->rects + total);
     h->w.assign(d->w, d->w + (size_t)total * 33);
     h->bias.assign(d->bias, d->bias + total);
-    for (int k = 0; k < total; k++) {
-        const sc_rect& r = h->rects[k];
-        const bool ok = r.w > 0 && r.h > 0 && r.x >= 0 && r.y >= 0 && r.x + r.w <= d->tmpl && r.y + r.h <= d->tmpl &&
-                        (r.w == r.h || r.w == 4 * r.h || r.h == 4 * r.w);
-        if (!ok) return fail(h, SC_ERR_INVALID, "weak classifier rect outside the template or not 2x2 / 4x1 / 1x4 cells");
-    }
-    std::vector<float> w36((size_t)total * SC_W_PITCH, 0.f);
-    std::vector<double> wb(total);
-    for (int k = 0; k < total; k++) {
-        memcpy(&w36[(size_t)k * SC_W_PITCH], &h->w[(size_t)k * 33], 33 * sizeof(float));
-        wb[k] = (double)h->w[(size_t)k * 33 + 32] * h->bias[k];  // prob += w[32] * bias, LogisticRegression.cpp:64
-    }
-    SC_CUDA(h, cudaStreamSynchronize(h->stream));
-    SC_CUDA(h, h->d_w.ensure(w36.size() * sizeof(float)));
-    SC_CUDA(h, h->d_wb.ensure(wb.size() * sizeof(double)));
-    SC_CUDA(h, cudaMemcpy(h->d_w.p, w36.data(), w36.size() * sizeof(float), cudaMemcpyHostToDevice));
-    SC_CUDA(h, cudaMemcpy(h->d_wb.p, wb.data(), wb.size() * sizeof(double), cudaMemcpyHostToDevice));
     h->have_cascade = true;
-    h->have_plan = false;
     return SC_OK;
 }
 
@@ -745,6 +794,7 @@ int sc_model_flatten(const char* path, int tmpl, float* theta, int32_t* n_weak, 
     if (!sc_host::load_flat_cascade(path, tmpl, &fc, &why)) return SC_ERR_IO;
     const int S = (int)fc.theta.size(), T = (int)fc.bias.size();
     if (total_weak) *total_weak = T;
+    if (S > max_stages || T > max_weak) return SC_ERR_CAPACITY;  // the caller's arrays would hold a truncated cascade
     for (int s = 0; s < S && s < max_stages; s++) {
         if (theta) theta[s] = fc.theta[s];
         if (n_weak) n_weak[s] = fc.n_weak[s];
@@ -783,6 +833,7 @@ int sc_integral(sc_handle* h, const uint8_t* gray, int W, int H, int stride, flo
     const int n_strips = (W + SC_STRIP - 1) / SC_STRIP;
     // the hooks keep their own single-frame integral in the step-1 layout (explicit rects sit on any pixel)
     const ScLayout L = sc_host::make_layout(W, H, 1, 1);
+    if (L.frame4 * 16 > 0xffffffffLL) return fail(h, SC_ERR_INVALID, "image too large for the hooks (corner offsets are 32-bit byte offsets: 4 GiB of integral image)");
     SC_CUDA(h, h->d_hook_img.ensure(align256((size_t)W * H)));
     SC_CUDA(h, h->d_hook_carry.ensure(align256((size_t)H * n_strips * 32)));
     SC_CUDA(h, h->d_hook_S.ensure((size_t)L.frame4 * 16));
@@ -845,6 +896,84 @@ int sc_integral_scan_layout(sc_handle* h, const uint8_t* gray, int W, int H, int
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     d_img.release(); d_carry.release(); d_S.release(); d_out.release();
     if (e != cudaSuccess) return cuda_fail(h, e, "sc_integral_scan_layout");
+    return SC_OK;
+}
+
+// Parity hook: the compact plane through the scan layout for lattice step `step`, exported in pixel order.
+int sc_integral_compact(sc_handle* h, const uint8_t* gray, int W, int H, int stride, int step, uint32_t* out) {
+    if (!h || !gray || !out || W < 2 || H < 2 || stride < W || step < 1 || step > 64) return fail(h, SC_ERR_INVALID, "bad image arguments");
+    SC_CUDA(h, cudaSetDevice(h->device));
+    const int n_strips = (W + SC_STRIP - 1) / SC_STRIP;
+    const ScLayout L = sc_host::make_layout(W, H, 2 * step, step);
+    if (L.hp > 4096 || L.frame4 * 16 > 0xffffffffLL) return fail(h, SC_ERR_INVALID, "frame too large for the scan layout");
+    DevBuf d_img, d_carry, d_S, d_out;
+    const size_t bytes = (size_t)(H + 1) * (W + 1) * 16;
+    cudaError_t e = d_img.ensure(align256((size_t)W * H));
+    if (e == cudaSuccess) e = d_carry.ensure(align256((size_t)H * n_strips * 32));
+    if (e == cudaSuccess) e = d_S.ensure((size_t)L.frame4 * 16);
+    if (e == cudaSuccess) e = d_out.ensure(bytes);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(d_img.p, W, gray, stride, W, H, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        sck::k_strip_carry<<<(H + 3) / 4, 128, 0, h->stream>>>(d_img.as<uint8_t>(), W, H, n_strips, 1, d_carry.as<int>());
+        // both forms of the walk write the plane: odd steps take the shuffle-scan form here so that both stay covered
+        if (SC_WALK_TILED && (step & 1) == 0)
+            sck::k_integral_walk_tiled<<<(n_strips + 3) / 4, 128, 0, h->stream>>>(d_img.as<uint8_t>(), W, H, n_strips, 1, d_carry.as<int>(), d_S.as<float4>(), L);
+        else
+            sck::k_integral_walk<<<(n_strips + 3) / 4, 128, 0, h->stream>>>(d_img.as<uint8_t>(), W, H, n_strips, 1, d_carry.as<int>(), d_S.as<float4>(), L);
+        sck::k_export_compact<<<h->n_sms * 8, 256, 0, h->stream>>>(d_S.as<float4>(), L, W, H, d_out.as<uint4>());
+        h->launches += 3;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out.p, bytes, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    d_img.release(); d_carry.release(); d_S.release(); d_out.release();
+    if (e != cudaSuccess) return cuda_fail(h, e, "sc_integral_compact");
+    return SC_OK;
+}
+
+int sc_box_sums_compact(sc_handle* h, const sc_rect* rects, int n, float* out) {
+    if (!h || !rects || !out || n < 0) return SC_ERR_INVALID;
+    if (!h->have_integral) return fail(h, SC_ERR_STATE, "sc_integral has not been called");
+    if (n == 0) return SC_OK;
+    SC_CUDA(h, cudaSetDevice(h->device));
+    for (int i = 0; i < n; i++) {
+        const sc_rect& r = rects[i];
+        const bool inside = r.x >= 0 && r.y >= 0 && r.w > 0 && r.h > 0 && r.x + r.w <= h->cur_W && r.y + r.h <= h->cur_H;
+        const bool cells = (r.w == r.h && r.w >= 2) || r.w == 4 * r.h || r.h == 4 * r.w;
+        if (!inside || !cells) return fail(h, SC_ERR_INVALID, "rect outside the image or not 2x2 / 4x1 / 1x4 cells");
+    }
+    DevBuf d_r, d_o;
+    SC_CUDA(h, d_r.ensure((size_t)n * sizeof(sc_rect)));
+    SC_CUDA(h, d_o.ensure((size_t)n * 32 * sizeof(float)));
+    SC_CUDA(h, cudaMemcpyAsync(d_r.p, rects, (size_t)n * sizeof(sc_rect), cudaMemcpyHostToDevice, h->stream));
+    sck::k_box_sums_compact<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_hook_S.as<float4>(), h->hook_lay, d_r.as<int4>(), n, d_o.as<float>());
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_o.p, (size_t)n * 32 * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    d_r.release(); d_o.release();
+    if (e != cudaSuccess) return cuda_fail(h, e, "sc_box_sums_compact");
+    return SC_OK;
+}
+
+int sc_cell_bounds(sc_handle* h, const int32_t* ce, int n, uint32_t* out) {
+    if (!h || !ce || !out || n < 1 || n > SC_CERT_MAX_ITEMS) return SC_ERR_INVALID;
+    if (!h->have_integral) return fail(h, SC_ERR_STATE, "sc_integral has not been called");
+    for (int i = 0; i < n; i++)
+        if (ce[i] < 1) return fail(h, SC_ERR_INVALID, "cell edge must be positive");
+    SC_CUDA(h, cudaSetDevice(h->device));
+    DevBuf d_c, d_o;
+    SC_CUDA(h, d_c.ensure((size_t)n * 4));
+    SC_CUDA(h, d_o.ensure((size_t)n * 4));
+    SC_CUDA(h, cudaMemcpyAsync(d_c.p, ce, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    SC_CUDA(h, cudaMemsetAsync(d_o.p, 0, (size_t)n * 4, h->stream));
+    sck::k_cell_bounds<<<dim3(n * 4, 1), 256, 0, h->stream>>>(h->d_hook_S.as<float4>(), h->hook_lay, h->cur_W, h->cur_H, d_c.as<int>(), n, 4, d_o.as<uint32_t>());
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_o.p, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    d_c.release(); d_o.release();
+    if (e != cudaSuccess) return cuda_fail(h, e, "sc_cell_bounds");
     return SC_OK;
 }
 
@@ -1104,6 +1233,7 @@ int sc_extract_pool_features(sc_handle* h, const uint8_t* imgs, int N, int tmpl,
 int sc_detect_device(sc_handle* h, const uint8_t* d_frames, int nframes, int W, int H, const sc_detect_params* params, sc_detection* d_out,
                      size_t cap, uint32_t* d_n) {
     if (!h || !d_frames || nframes < 1 || !d_out || !d_n) return fail(h, SC_ERR_INVALID, "bad arguments");
+    if (any_ticket_busy(h)) return fail(h, SC_ERR_STATE, "a submitted batch is in flight (its counters are read against the current plan): collect it first");
     SC_CUDA(h, cudaSetDevice(h->device));
     const sc_detect_params prm = params ? *params : default_params();
     int rc = ensure_plan(h, W, H, prm);

@@ -5,6 +5,7 @@
 //   k_integral_walk    one warp per (frame,strip): fused gradient + channel + packed warp-shuffle row scan, then the
 //                      reference's SEQUENTIAL float32 column recurrence, stored in the lattice-deinterleaved,
 //                      half-split layout (sc_plan.h) with two 16 B stores per lane
+//   k_cell_bounds      per frame: upper bound of every cell's box sums per projected cell edge (certifies the compact plane)
 //   k_scan_stage0      64x16-window tiles: prefilter -> in-block compaction (ballot + shared prefix) -> stage 0 on
 //                      the dense survivor list -> warp-aggregated push of survivors, multi/prefilter bitmasks
 //   k_scan_stage       stages 1..N-1 on the compacted survivor index lists (ballot + atomic prefix between stages)
@@ -23,6 +24,12 @@
 #include "sc_plan.h"
 
 namespace sck {
+
+#ifdef SC_EXP_NW2  // timing experiment only (wrong results): the filter stops after two weak classifiers
+#define SC_EXP_NWEAK(n) min(n, 2)
+#else
+#define SC_EXP_NWEAK(n) (n)
+#endif
 
 // ---------------------------------------------------------------------------------------------------------
 // Gradient channels (T2bFilter, DenseSURFFeatureExtractor.cpp:199-349) as four packed pairs:
@@ -96,10 +103,11 @@ __global__ void __launch_bounds__(128) k_integral_walk(const uint8_t* __restrict
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     // this lane's integral column X = x + 1: in-plane column and the plane column residue are fixed
     const int X = x + 1, px = X / L.sx, rx = X - px * L.sx;
-    if (valid) { float4* o = Sf + (size_t)rx * L.plane4 + SC_COL(px); o[0] = zero; o[SC_HI(L.hp)] = zero; }      // row Y = 0
+    if (valid) { float4* o = Sf + (size_t)rx * L.plane4 + SC_COL(px); o[0] = zero; o[SC_HI(L.hp)] = zero; o[SC_NOFF(L.hp)] = zero; }      // row Y = 0
     if (s == 0 && lane == 0)                                                                      // column X = 0
-        for (int Y = 0; Y <= H; Y++) { float4* o = Sf + sc_layout_index(L, 0, Y); o[0] = zero; o[SC_HI(L.hp)] = zero; }
+        for (int Y = 0; Y <= H; Y++) { float4* o = Sf + sc_layout_index(L, 0, Y); o[0] = zero; o[SC_HI(L.hp)] = zero; o[SC_NOFF(L.hp)] = zero; }
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    uint32_t nacc[4] = {0u, 0u, 0u, 0u};  // compact plane: (I[2k+1] << 16) + I[2k] mod 2^32 of the exact integer integral (sc_plan.h)
     const int4* cr = reinterpret_cast<const int4*>(carry + (((size_t)f * H) * n_strips + s) * 8);
     const size_t cr_step = (size_t)n_strips * 2;
     // Rows are processed in blocks of RB with the next block's inputs (pixel rows and strip carries) loaded a whole
@@ -143,12 +151,14 @@ __global__ void __launch_bounds__(128) k_integral_walk(const uint8_t* __restrict
                 for (int k = 0; k < 4; k++) {
                     acc[2 * k] = __fadd_rn(acc[2 * k], (float)(cy[2 * k] + (int)(p[k] & 0xffffu)));
                     acc[2 * k + 1] = __fadd_rn(acc[2 * k + 1], (float)(cy[2 * k + 1] + (int)(p[k] >> 16)));
+                    nacc[k] += p[k] + (uint32_t)cy[2 * k] + ((uint32_t)cy[2 * k + 1] << 16);
                 }
                 if (++ry == L.sy) { ry = 0; py++; }
                 if (valid) {
                     float4* o = Sf + (size_t)(ry * L.sx + rx) * L.plane4 + (size_t)py * L.ppitch + SC_COL(px);
                     o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
                     o[SC_HI(L.hp)] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                    reinterpret_cast<uint4*>(o)[SC_NOFF(L.hp)] = make_uint4(nacc[0], nacc[1], nacc[2], nacc[3]);
                 }
                 prev = cur; cur = nx[i];
             }
@@ -193,9 +203,9 @@ __global__ void __launch_bounds__(128) k_integral_walk_tiled(const uint8_t* __re
     const bool valid = x < W;
     const int X = x + 1, px = X / L.sx, rx = X - px * L.sx;
     const bool upper = c >= 16;
-    if (valid) { float4* o = Sf + (size_t)rx * L.plane4 + SC_COL(px); o[0] = zero; o[SC_HI(L.hp)] = zero; }      // row Y = 0
+    if (valid) { float4* o = Sf + (size_t)rx * L.plane4 + SC_COL(px); o[0] = zero; o[SC_HI(L.hp)] = zero; o[SC_NOFF(L.hp)] = zero; }      // row Y = 0
     if (s == 0 && lane == 0)                                                                      // column X = 0
-        for (int Y = 0; Y <= H; Y++) { float4* o = Sf + sc_layout_index(L, 0, Y); o[0] = zero; o[SC_HI(L.hp)] = zero; }
+        for (int Y = 0; Y <= H; Y++) { float4* o = Sf + sc_layout_index(L, 0, Y); o[0] = zero; o[SC_HI(L.hp)] = zero; o[SC_NOFF(L.hp)] = zero; }
     // row phase: lane (r, half) owns tile row r, strip columns 16 half .. 16 half + 15
     const int r = lane & 15, half = lane >> 4;
     // position of strip column cc in the column-phase lane order (identity unless sx == 4)
@@ -205,6 +215,7 @@ __global__ void __launch_bounds__(128) k_integral_walk_tiled(const uint8_t* __re
         return 8 * rxu + q - (rxu == 0 ? 1 : 0);
     };
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    uint32_t nacc[4] = {0u, 0u, 0u, 0u};  // compact plane (sc_plan.h), as in k_integral_walk
     const int4* cr = reinterpret_cast<const int4*>(carry + (((size_t)f * H) * n_strips + s) * 8);
     const size_t cr_step = (size_t)n_strips * 2;
     int py = 0, ry = 0;  // plane row / residue of Y = y + 1, advanced incrementally
@@ -262,12 +273,14 @@ __global__ void __launch_bounds__(128) k_integral_walk_tiled(const uint8_t* __re
             for (int k = 0; k < 4; k++) {
                 acc[2 * k] = __fadd_rn(acc[2 * k], (float)(cy[2 * k] + (int)(p[k] & 0xffffu)));
                 acc[2 * k + 1] = __fadd_rn(acc[2 * k + 1], (float)(cy[2 * k + 1] + (int)(p[k] >> 16)));
+                nacc[k] += p[k] + (uint32_t)cy[2 * k] + ((uint32_t)cy[2 * k + 1] << 16);
             }
             if (++ry == L.sy) { ry = 0; py++; }
             if (valid) {
                 float4* o = Sf + (size_t)(ry * L.sx + rx) * L.plane4 + (size_t)py * L.ppitch + SC_COL(px);
                 o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
                 o[SC_HI(L.hp)] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                reinterpret_cast<uint4*>(o)[SC_NOFF(L.hp)] = make_uint4(nacc[0], nacc[1], nacc[2], nacc[3]);
             }
         }
         __syncwarp();
@@ -282,6 +295,15 @@ __global__ void k_export_integral(const float4* __restrict__ S, const ScLayout L
         const float4* p = S + sc_layout_index(L, X, Y);
         out[2 * (size_t)i] = p[0];
         out[2 * (size_t)i + 1] = p[SC_HI(L.hp)];
+    }
+}
+
+// Layout -> the compact integer plane in pixel order, (H+1) x (W+1) x 4 words (parity hook of sc_integral_compact).
+__global__ void k_export_compact(const float4* __restrict__ S, const ScLayout L, int W, int H, uint4* __restrict__ out) {
+    const int n = (W + 1) * (H + 1);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int Y = i / (W + 1), X = i - Y * (W + 1);
+        out[i] = reinterpret_cast<const uint4*>(S + sc_layout_index(L, X, Y))[SC_NOFF(L.hp)];
     }
 }
 
@@ -302,13 +324,11 @@ __device__ __forceinline__ Px load_px(const char* __restrict__ base, uint32_t of
         r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w; r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
         return r;
     }
-#if SC_PAIRED
-    Px q;  // one 256-bit load: both halves of the pixel
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(q.v[0]), "=f"(q.v[1]), "=f"(q.v[2]), "=f"(q.v[3]), "=f"(q.v[4]), "=f"(q.v[5]), "=f"(q.v[6]), "=f"(q.v[7]) : "l"(p));
-    return q;
-#endif
+#ifdef SC_EXP_HALF  // timing experiment only (wrong results): 16 bytes per corner
+    const float4 lo = __ldg(p), hi = lo;
+#else
     const float4 lo = __ldg(p), hi = __ldg(p + (HP ? HP : hp));
+#endif
     Px r;
     r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w; r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
     return r;
@@ -505,6 +525,126 @@ __device__ __forceinline__ void box_sums_p(const char* __restrict__ base, const 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Box sums from the compact integer plane (sc_plan.h): 16 bytes per corner instead of 32.
+// For a cell, X = N(A) + N(D) - N(B) - N(C) (mod 2^32) holds the exact box sums of a channel pair in its two 16-bit
+// fields whenever both are below 65536 (certified per frame by k_cell_bounds, see there); float(field) then equals the
+// reference's fl(fl(A + D) - fl(B + C)) bit for bit as long as the integrals involved are <= 2^23 (certified per tile /
+// unit by compact_far_ok()).  The fields are turned into floats without the conversion pipe: PRMT builds
+// 0x4B00'xxxx = 2^23 + field, one packed subtraction removes the 2^23.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cell_sum_c(const uint4& A, const uint4& B, const uint4& C, const uint4& D, float* v) {
+    const uint32_t x[4] = {A.x + D.x - B.x - C.x, A.y + D.y - B.y - C.y, A.z + D.z - B.z - C.z, A.w + D.w - B.w - C.w};
+    const float2 bias = make_float2(8388608.f, 8388608.f);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float2 r = sub2(make_float2(__uint_as_float(__byte_perm(x[k], 0x4B000000u, 0x7610)), __uint_as_float(__byte_perm(x[k], 0x4B000000u, 0x7632))), bias);
+        v[2 * k] = r.x; v[2 * k + 1] = r.y;
+    }
+}
+
+template <int HP>
+__device__ __forceinline__ uint4 load_n(const char* __restrict__ base, uint32_t off, int hp) {
+    return __ldg(reinterpret_cast<const uint4*>(base + off) + SC_NOFF(HP ? HP : hp));
+}
+
+// box_sums() from the compact plane (same values as box_sums() / box_sums_p() under the two certified conditions)
+template <int HP>
+__device__ __forceinline__ void box_sums_c(const char* __restrict__ base, const ScGeom& g, int hp, float* v) {
+    if (g.shape == 0) {
+        uint4 a0 = load_n<HP>(base, g.c[0], hp), a1 = load_n<HP>(base, g.c[1], hp), a2 = load_n<HP>(base, g.c[2], hp);
+        const uint4 b0 = load_n<HP>(base, g.c[3], hp), b1 = load_n<HP>(base, g.c[4], hp), b2 = load_n<HP>(base, g.c[5], hp);
+        cell_sum_c(a0, a1, b0, b1, v);
+        cell_sum_c(a1, a2, b1, b2, v + 8);
+        a0 = load_n<HP>(base, g.c[6], hp); a1 = load_n<HP>(base, g.c[7], hp); a2 = load_n<HP>(base, g.c[8], hp);
+        cell_sum_c(b0, b1, a0, a1, v + 16);
+        cell_sum_c(b1, b2, a1, a2, v + 24);
+    } else {
+        uint4 t0 = load_n<HP>(base, g.c[0], hp), u0 = load_n<HP>(base, g.c[5], hp);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint4 t1 = load_n<HP>(base, g.c[k + 1], hp), u1 = load_n<HP>(base, g.c[k + 6], hp);
+            cell_sum_c(t0, t1, u0, u1, v + 8 * k);
+            t0 = t1; u0 = u1;
+        }
+    }
+}
+
+// Every integral value at or left / above layout element `far` (the far corner of a tile's or unit's last window) is
+// <= 2^23: then fl(A + D), fl(B + C) and their difference are exact for every corner the tile touches (the integrals
+// are monotone in x and y), i.e. the reference's float box sums ARE the integer box sums the compact plane yields.
+template <int HP>
+__device__ __forceinline__ bool compact_far_ok(const float4* __restrict__ far) {
+    const float4 lo = __ldg(far), hi = __ldg(far + HP);
+    const float m = fmaxf(fmaxf(fmaxf(lo.x, lo.y), fmaxf(lo.z, lo.w)), fmaxf(fmaxf(hi.x, hi.y), fmaxf(hi.z, hi.w)));
+    return m <= 8388608.f;
+}
+
+// Certification of the compact path, once per frame: an upper bound of EVERY ce x ce cell's box sums, for each cell edge
+// `ce` the stage-0 patches of the plan project to ("items", host-built).  Every ce x ce cell at any pixel position lies
+// inside the box [g i, g i + ce + g) x [g j, g j + ce + g) of a pitch-g grid, and the channels are non-negative, so the
+// largest such box sum (all eight channels) bounds every cell sum.  g = max(ce / 4, SC_CERT_MIN_PITCH): the looser boxes of
+// small cells (whose sums are far below the limit anyway) keep the pass cheap (~40 MB of cached corner reads per 1080p frame).
+// Box sums are formed in double from the float32 integrals; where an integral has passed 2^24 its accumulated
+// rounding (at most half an ulp per image row) is added as slack, so the bound stays an upper bound on any frame.
+// cert[frame][item] = min(bound, 0xffffffff); a weak classifier may use the compact plane iff cert < SC_CELL_LIMIT.
+#define SC_CERT_MIN_PITCH 16
+#define SC_CERT_MAX_ITEMS 256
+#define SC_CERT_ALWAYS 0xfffffffeu   // item code: 255 ce^2 < 65536, no frame-dependent bound needed
+#define SC_CERT_NEVER 0xffffffffu    // item code: compact path not available for this (scale, weak classifier)
+__global__ void __launch_bounds__(256) k_cell_bounds(const float4* __restrict__ S, const ScLayout L, int W, int H, const int* __restrict__ item_ce,
+                                                      int n_items, int chunks, uint32_t* __restrict__ cert) {
+    const int item = blockIdx.x / chunks, chunk = blockIdx.x - item * chunks, f = blockIdx.y;
+    const int ce = item_ce[item];
+    const int g = max(ce / 4, SC_CERT_MIN_PITCH), b = ce + g;
+    const int nbx = (W + g - 1) / g, nby = (H + g - 1) / g;
+    const float4* Sf = S + (size_t)f * L.frame4;
+    double best = 0.0;
+    for (int i = chunk * blockDim.x + threadIdx.x; i < nbx * nby; i += chunks * blockDim.x) {
+        const int by = i / nbx, bx = i - by * nbx;
+        const int x0 = bx * g, y0 = by * g, x1 = min(x0 + b, W), y1 = min(y0 + b, H);
+        const float4* pa = Sf + sc_layout_index(L, x0, y0);
+        const float4* pb = Sf + sc_layout_index(L, x1, y0);
+        const float4* pc = Sf + sc_layout_index(L, x0, y1);
+        const float4* pd = Sf + sc_layout_index(L, x1, y1);
+        double m = 0.0, far = 0.0;
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+            const float4 A = __ldg(pa + hh * L.hp), B = __ldg(pb + hh * L.hp), C = __ldg(pc + hh * L.hp), D = __ldg(pd + hh * L.hp);
+            m = fmax(m, fmax(fmax(((double)A.x + D.x) - ((double)B.x + C.x), ((double)A.y + D.y) - ((double)B.y + C.y)),
+                             fmax(((double)A.z + D.z) - ((double)B.z + C.z), ((double)A.w + D.w) - ((double)B.w + C.w))));
+            far = fmax(far, fmax(fmax((double)D.x, (double)D.y), fmax((double)D.z, (double)D.w)));
+        }
+        if (far >= 16777216.0) {  // inexact integrals: each of the four corners is off by at most (rows) x ulp(far) / 2
+            int e = 0;
+            frexp(far, &e);                                  // far in [2^(e-1), 2^e): ulp = 2^(e-24)
+            m += 2.0 * (double)(H + 1) * ldexp(1.0, e - 24);
+        }
+        best = fmax(best, m);
+    }
+    // block maximum -> one atomicMax per CTA (values are non-negative: integer order == float order after the clamp)
+    __shared__ uint32_t s_best;
+    if (threadIdx.x == 0) s_best = 0u;
+    __syncthreads();
+    const uint32_t q = best >= 4294967295.0 ? 0xffffffffu : (uint32_t)ceil(best);
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, q);
+    if ((threadIdx.x & 31) == 0) atomicMax(&s_best, wmax);
+    __syncthreads();
+    if (threadIdx.x == 0) atomicMax(&cert[(size_t)f * n_items + item], s_best);
+}
+
+// Bit q set: stage-0 weak classifier q of scale si may read the compact plane in frame slot f (per-frame cell bound).
+__device__ __forceinline__ uint32_t compact_mask(const ScFastParams& fp, int si, const uint32_t* __restrict__ cert, int n_items, int f) {
+    uint32_t m = 0;
+    for (int q = 0; q < fp.n_weak; q++) {
+        const uint32_t item = fp.geom[si][q][11];
+        const bool ok = item == SC_CERT_ALWAYS || (item != SC_CERT_NEVER && cert[(size_t)f * n_items + item] < SC_CELL_LIMIT);
+        m |= (ok ? 1u : 0u) << q;
+    }
+    return m;
+}
+
+
 // Normalize + LogisticRegression::Predict on box sums v, approximate arithmetic (error budget above).
 // With t = theta |v| the clip is  clip(v_i) = 2t g_i,  g_i = sat(v_i / (2t) + 1/2) - 1/2  (one saturating FMA and one add);
 // the common factor 2t cancels in  z = w . clip(v) / |clip(v)| = (w . g) / sqrt(|g|^2 + eps / (2t)^2).
@@ -553,7 +693,7 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, FAST ? SC_FAST_MIN_CTAS : (AL
                                                                   const double* __restrict__ wb_all, uint32_t* __restrict__ multi_bits,
                                                                   uint32_t* __restrict__ pass_bits, ScRecord* __restrict__ rec,
                                                                   uint32_t* __restrict__ rec_count, uint32_t rec_cap, int phase,
-                                                                  const int* __restrict__ start_odd) {
+                                                                  const int* __restrict__ start_odd, const uint32_t* __restrict__ cert, int n_items) {
     constexpr int SC_TILE_Y = FAST ? SC_TILE_Y_FAST : SC_TILE_Y_EXACT;  // tile rows of this variant (sc_plan.h)
     const uint32_t block = blockIdx.x;
     __shared__ uint32_t s_multi[SC_TILE_Y][4];
@@ -561,7 +701,7 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, FAST ? SC_FAST_MIN_CTAS : (AL
     __shared__ uint16_t s_list[SC_TILE_X * SC_TILE_Y];
     __shared__ uint16_t s_list2[FAST ? SC_TILE_X * SC_TILE_Y : 1];
     __shared__ int s_start[SC_TILE_Y];
-    __shared__ uint32_t s_count, s_count2;
+    __shared__ uint32_t s_count, s_count2, s_cmask;
     __shared__ ScScale s_sc;
     extern __shared__ __align__(16) unsigned char s_dyn[];  // stage-0 weights, wb, geometry
 
@@ -593,8 +733,20 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, FAST ? SC_FAST_MIN_CTAS : (AL
         if (!__syncthreads_or(need)) return;
     }
     const int n_weak = plan->n_weak[0], total_weak = plan->total_weak;
-    constexpr int ppitch = 2 * HP;
+    constexpr int ppitch = SC_ROW_ELEMS(HP);
     const float4* lo4 = S + (size_t)f * plan->lay.frame4 + (size_t)s_sc.gy0 * ppitch;  // lattice row gy0 is row 0 of this plan
+    if (FAST && tid == 32) {
+        // which weak classifiers may read the compact plane in this tile (sc_plan.h): the frame's cell-sum bound per weak
+        // classifier, and every integral up to the far corner of the tile's last window at most 2^23
+        uint32_t cm = 0;
+        const int jlast = (nx - 1 - phase) >> 1;  // last valid column index of this parity (negative: none)
+        if (cert != nullptr && nx - 1 - phase >= 0 && tx * SC_TILE_X <= jlast) {
+            const int jm = min(tx * SC_TILE_X + SC_TILE_X - 1, jlast), gym = min(ty * SC_TILE_Y + SC_TILE_Y - 1, ny - 1);
+            const char* wbase = reinterpret_cast<const char*>(lo4 + (gym * ppitch + SC_COL(jm)));
+            if (compact_far_ok<HP>(reinterpret_cast<const float4*>(wbase + s_sc.pf[phase][3]))) cm = compact_mask(fp, si, cert, n_items, f);
+        }
+        s_cmask = cm;
+    }
     const int n_ld = ALL ? total_weak : n_weak;  // weak classifiers staged in shared memory: stage 0, or every stage
     ScGeom* sg = reinterpret_cast<ScGeom*>(s_dyn);                                                        // [n_ld] 48 B each
     float* sw = reinterpret_cast<float*>(s_dyn + (size_t)n_ld * sizeof(ScGeom));                          // [n_ld][36]
@@ -645,6 +797,11 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, FAST ? SC_FAST_MIN_CTAS : (AL
     // phase B1: certified fast filter on the dense list; what it cannot decide is compacted into s_list2
     if (FAST) {
         const uint32_t n_pass = s_count;
+#ifdef SC_EXP_NOCMASK  // timing experiment only: no compact path in the loop
+        const uint32_t cmask = 0;
+#else
+        const uint32_t cmask = s_cmask;
+#endif
         for (uint32_t i0 = 0; i0 < n_pass; i0 += SC_TILE_THREADS) {
             const uint32_t i = i0 + tid;
             bool undecided = false;
@@ -657,13 +814,14 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, FAST ? SC_FAST_MIN_CTAS : (AL
                 const char* base = reinterpret_cast<const char*>(lo4 + (gy * ppitch + SC_COL(j)));
                 float sum = 0.f;
 #pragma unroll 1
-                for (int q = 0; q < fp.n_weak; q++) {
+                for (int q = 0; q < SC_EXP_NWEAK(fp.n_weak); q++) {
                     ScGeom g;
 #pragma unroll
                     for (int k = 0; k < 10; k++) g.c[k] = fp.geom[si][q][k];
                     g.shape = (int)fp.geom[si][q][10]; g.pad = 0;
                     float v[32];
-                    box_sums_p<HP>(base, g, HP, v);
+                    if ((cmask >> q) & 1u) box_sums_c<HP>(base, g, HP, v);
+                    else box_sums_p<HP>(base, g, HP, v);
                     sum = __fadd_rn(sum, fast_tail(v, fp.w[q], fp.wb[q]));
                 }
                 if (!(sum < fp.lim_reject && sum < fp.lim_skip)) {  // not "rejected and skips for certain": rare
@@ -865,7 +1023,7 @@ __global__ void __launch_bounds__(256, SC_STAGE0_MIN_CTAS) k_scan_odd(const __gr
                                                                       uint32_t* __restrict__ pass_bits, ScRecord* __restrict__ rec,
                                                                       uint32_t* __restrict__ rec_count, uint32_t rec_cap, const int* __restrict__ start_odd,
                                                                       const uint32_t* __restrict__ chunk_list, const uint32_t* __restrict__ chunk_count,
-                                                                      uint32_t* __restrict__ cursor) {
+                                                                      uint32_t* __restrict__ cursor, const uint32_t* __restrict__ cert, int n_items) {
     constexpr int NWARP = 8, WORDS = 2 * SC_ODD_UNIT / 32 + 2;  // a unit spans 2 * SC_ODD_UNIT lattice columns at an odd offset
     __shared__ uint8_t s_q[NWARP][SC_ODD_UNIT];
     __shared__ uint32_t s_mb[NWARP][WORDS], s_pb[NWARP][WORDS];
@@ -873,7 +1031,7 @@ __global__ void __launch_bounds__(256, SC_STAGE0_MIN_CTAS) k_scan_odd(const __gr
     const uint32_t n_chunks = *chunk_count;
     const int rows = plan->rows_per_frame;
     const bool use_pf = plan->use_prefilter != 0;
-    constexpr int ppitch = 2 * HP;
+    constexpr int ppitch = SC_ROW_ELEMS(HP);
     const uint32_t lt = (1u << lane) - 1u;
     // claim of a unit, lane 0 only: index, list entry, first reachable odd column of its row
     uint32_t c = 0, e = 0;
@@ -900,6 +1058,14 @@ __global__ void __launch_bounds__(256, SC_STAGE0_MIN_CTAS) k_scan_odd(const __gr
         const float4* row4 = S + (size_t)f * plan->lay.frame4 + (size_t)(gy + sc->gy0) * ppitch;
         const size_t word0 = (size_t)f * plan->words_per_frame + sc->word_base + (size_t)gy * sc->wpr + (g0 >> 5);
         if (lane < WORDS) { s_mb[warp][lane] = 0; s_pb[warp][lane] = 0; }
+        // compact-plane eligibility of this unit (as in k_scan_stage0): per-frame cell bounds, far corner of its last window
+        uint32_t cmask = 0;
+        if (lane == 0 && cert != nullptr) {
+            const int glast = min(g0 + 2 * (SC_ODD_UNIT - 1), ((nx - 1) & 1) ? nx - 1 : nx - 2);  // last odd column of the unit
+            if (glast >= g0 && glast < nx && compact_far_ok<HP>(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(row4 + SC_COL(glast >> 1)) + sc->pf[1][3])))
+                cmask = compact_mask(fp, si, cert, n_items, f);
+        }
+        cmask = __shfl_sync(0xffffffffu, cmask, 0);
         __syncwarp();
         // prefilter; pass / prefilter-failed bits of lane i sit at bit (gc & 31) + 2 i of the 96-bit run starting at word wb
         int n = 0;
@@ -941,13 +1107,14 @@ __global__ void __launch_bounds__(256, SC_STAGE0_MIN_CTAS) k_scan_odd(const __gr
                 const char* base = reinterpret_cast<const char*>(row4 + SC_COL(gx >> 1));
                 float sum = 0.f;
 #pragma unroll 1
-                for (int q = 0; q < fp.n_weak; q++) {
+                for (int q = 0; q < SC_EXP_NWEAK(fp.n_weak); q++) {
                     ScGeom g;
 #pragma unroll
                     for (int i = 0; i < 10; i++) g.c[i] = fp.geom[si][q][i];
                     g.shape = (int)fp.geom[si][q][10]; g.pad = 0;
                     float v[32];
-                    box_sums_p<HP>(base, g, HP, v);
+                    if ((cmask >> q) & 1u) box_sums_c<HP>(base, g, HP, v);
+                    else box_sums_p<HP>(base, g, HP, v);
                     sum = __fadd_rn(sum, fast_tail(v, fp.w[q], fp.wb[q]));
                 }
                 if (!(sum < fp.lim_reject && sum < fp.lim_skip)) {
@@ -1006,7 +1173,7 @@ __global__ void __launch_bounds__(128) k_scan_stage(const ScPlan* __restrict__ p
     __syncthreads();
     const uint32_t count = min(*in_count, cap);
     const int n_stages = plan->n_stages;
-    constexpr int ppitch = 2 * HP;
+    constexpr int ppitch = SC_ROW_ELEMS(HP);
     const bool force = plan->force_all != 0, last = stage == n_stages - 1;
     const float theta = plan->theta[stage];
     const int lane = threadIdx.x & 31;
@@ -1393,6 +1560,32 @@ __global__ void k_features(const float4* __restrict__ S, const ScLayout L, const
         descriptor<0>(base, g, L.hp, v);
         for (int k = 0; k < 32; k++) out[(size_t)i * 32 + k] = v[k];
     }
+}
+
+// Parity hook: CalcFeature's box sums (no Normalize) of explicit rects from the compact plane (layout step 1).
+__global__ void k_box_sums_compact(const float4* __restrict__ S, const ScLayout L, const int4* __restrict__ rects, int n, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 r = rects[i];  // x, y, w, h
+    const int pitch = L.ppitch;
+    const char* base = reinterpret_cast<const char*>(S + ((size_t)r.y * pitch + SC_COL(r.x)));
+    ScGeom g;
+    g.pad = 0;
+    if (r.z == r.w) {
+        const int ce = r.z / 2;
+        g.shape = 0;
+        for (int b = 0; b < 3; b++)
+            for (int a = 0; a < 3; a++) g.c[3 * b + a] = 16u * (uint32_t)(b * ce * pitch + SC_COL(a * ce));
+        g.c[9] = 0;
+    } else {
+        const int ce = min(r.z, r.w);
+        const int along = r.z > r.w ? SC_COL(ce) : ce * pitch, across = r.z > r.w ? ce * pitch : SC_COL(ce);
+        g.shape = 1;
+        for (int k = 0; k < 5; k++) { g.c[k] = 16u * (uint32_t)(k * along); g.c[5 + k] = 16u * (uint32_t)(k * along + across); }
+    }
+    float v[32];
+    box_sums_c<0>(base, g, L.hp, v);
+    for (int k = 0; k < 32; k++) out[(size_t)i * 32 + k] = v[k];
 }
 
 // Training-side descriptor extraction (next row N3): ExtractNextImageFeatures -> IntegralImage + ExtractFeatures over the

@@ -46,34 +46,38 @@
 #define SC_WALK_RB 4
 #endif
 
-// Integral-image layout in HBM ("lattice-deinterleaved, half-split"):
+// Integral-image layout in HBM ("lattice-deinterleaved, half-split, with a compact exact-integer third"):
 //   the reference keeps 8 interleaved floats (32 B) per pixel; a warp of 32 neighbouring windows on a step-s
 //   lattice would then touch 32 sectors in 16 cache lines per 16-byte load.  Here pixel (X, Y) lives in plane
-//   (Y mod s, X mod s) at (Y div s, X div s), and every plane is stored as two float4 half-planes (channels 0-3,
-//   channels 4-7).  Neighbouring lattice windows read neighbouring float4s: one corner fetch of a warp is two
-//   fully coalesced 512-byte loads.  Detection plans deinterleave rows by sy = lattice step and columns by
-//   sx = 2 * step, because one launch of the scan walks lattice columns of a single parity (2j or 2j + 1, see
-//   SC_TILE_X): consecutive j are then consecutive float4s.  The explicit-rect hooks use sx = sy = 1.
-//   The two halves of a plane are interleaved row by row at a power-of-two distance hp: a plane row is
-//   [hp float4: channels 0-3][hp float4: channels 4-7], so the second 16-byte load of a corner is the first one's
-//   address plus a compile-time constant (the scan kernels are instantiated per hp) and costs no address arithmetic.
-//   SC_PAIRED=1 (option; measured equal to the default on C2, 0.355 vs 0.351 ms/frame in stage 0): the two halves of a pixel are adjacent instead (32 contiguous bytes per pixel inside the
-//   plane row), so one corner is ONE 256-bit load (LDG.E.256 on sm_100a): a warp's corner fetch is 1024 contiguous
-//   bytes = 8-9 L1 wavefronts instead of 2 x 5-6 for the two 512-byte half loads, and half the load instructions.
-#ifndef SC_PAIRED
-#define SC_PAIRED 0
-#endif
-#if SC_PAIRED
-#define SC_COL(x) (2 * (x))      // float4 index of plane column x inside a plane row
-#define SC_HI(hp) 1              // float4 distance from a pixel's channels 0-3 to its channels 4-7
+//   (Y mod s, X mod s) at (Y div s, X div s), and every plane row is stored as three runs of hp 16-byte elements:
+//       [hp float4: channels 0-3][hp float4: channels 4-7][hp uint4: compact integer integral N]
+//   Neighbouring lattice windows read neighbouring 16-byte elements: one corner fetch of a warp is fully coalesced
+//   512-byte loads.  Detection plans deinterleave rows by sy = lattice step and columns by sx = 2 * step, because one
+//   launch of the scan walks lattice columns of a single parity (2j or 2j + 1, see SC_TILE_X): consecutive j are then
+//   consecutive elements.  The explicit-rect hooks use sx = sy = 1.  hp is a power of two, so the second and third
+//   run of a pixel sit at the first one's address plus a compile-time constant (the scan kernels are instantiated
+//   per hp) and cost no address arithmetic.
+//
+//   Compact plane: word k of N holds  (I[2k+1] << 16) + I[2k]  mod 2^32, with I[c] the EXACT integer integral of channel c
+//   (the walk kernels carry it beside the float32 recurrence).  N is linear in the integrals, so for a box
+//       N(A) + N(D) - N(B) - N(C)  =  (V[2k+1] << 16) + V[2k]   (mod 2^32),   V[c] = exact box sum of channel c;
+//   whenever every V[c] < 65536 the two 16-bit fields ARE the box sums, and they equal the reference's float32 box
+//   sums bit for bit as long as the integrals involved are below 2^23 (then fl(A + D), fl(B + C) and their difference are
+//   exact).  The stage-0 fast filter reads 16 bytes per corner instead of 32 wherever both conditions are certified
+//   (k_cell_bounds + the tile's far-corner check); the scan is bound by L2 -> SM bytes, so this is where its time goes.
+#define SC_COL(x) (x)                 // 16-byte element index of plane column x inside a plane row
+#define SC_HI(hp) (hp)                // element distance from a pixel's channels 0-3 to its channels 4-7
+#define SC_NOFF(hp) (2 * (hp))        // element distance from a pixel's channels 0-3 to its compact integer word
+#ifdef SC_EXP_LAYOUT2   // timing experiment only: round-1 row pitch (the compact plane then aliases the next row: results wrong)
+#define SC_ROW_ELEMS(hp) (2 * (hp))
 #else
-#define SC_COL(x) (x)
-#define SC_HI(hp) (hp)
+#define SC_ROW_ELEMS(hp) (3 * (hp))   // 16-byte elements per plane row
 #endif
+#define SC_CELL_LIMIT 65536u          // a compact box sum is valid below this
 struct ScLayout {
     int sx, sy;            // column / row deinterleave factors
-    int hp;                // float4 elements per half-row: power of two >= ceil((W+1)/sx), one of 256..4096
-    int ppitch;            // float4 elements per plane row   = 2 * hp
+    int hp;                // 16-byte elements per run of a plane row: power of two >= ceil((W+1)/sx), one of 256..4096
+    int ppitch;            // 16-byte elements per plane row  = 3 * hp (SC_ROW_ELEMS)
     int prows;             // plane rows                      = ceil((H+1)/sy)
     int pad;
     long long plane4;      // float4 elements per plane       = prows * ppitch

@@ -75,7 +75,7 @@ ScLayout make_layout(int W, int H, int sx, int sy, int min_hp) {
     const int cols = (W + 1 + L.sx - 1) / L.sx;
     L.hp = min_hp < 8 ? 8 : min_hp;  // the scan kernels are instantiated for 256..4096 (callers reject more); hooks take any power of two
     while (L.hp < cols) L.hp *= 2;
-    L.ppitch = 2 * L.hp;
+    L.ppitch = SC_ROW_ELEMS(L.hp);
     L.prows = (H + 1 + L.sy - 1) / L.sy;
     L.pad = 0;
     L.plane4 = (long long)L.ppitch * L.prows;
