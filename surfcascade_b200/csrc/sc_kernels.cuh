@@ -799,6 +799,8 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, FAST ? SC_FAST_MIN_CTAS : (AL
         const uint32_t n_pass = s_count;
 #ifdef SC_EXP_NOCMASK  // timing experiment only: no compact path in the loop
         const uint32_t cmask = 0;
+#elif defined(SC_EXP_ALLC)  // timing experiment only (wrong results): every weak classifier reads the compact plane
+        const uint32_t cmask = 0xffu;
 #else
         const uint32_t cmask = s_cmask;
 #endif
@@ -1066,6 +1068,9 @@ __global__ void __launch_bounds__(256, SC_STAGE0_MIN_CTAS) k_scan_odd(const __gr
                 cmask = compact_mask(fp, si, cert, n_items, f);
         }
         cmask = __shfl_sync(0xffffffffu, cmask, 0);
+#ifdef SC_EXP_ALLC
+        cmask = 0xffu;
+#endif
         __syncwarp();
         // prefilter; pass / prefilter-failed bits of lane i sit at bit (gc & 31) + 2 i of the 96-bit run starting at word wb
         int n = 0;
