@@ -442,22 +442,25 @@ int run_integral(sc_handle* h, const uint8_t* d_img, int n, int slot0, bool unde
 
 // Launches the whole path for `g` frames already in d_img (device).  Detections are appended to det / det_count.
 // The scan kernels are instantiated per half-row distance of the layout (sc_plan.h): 256 .. 4096 float4.
-template <bool FAST, bool ALL, typename... A>
+template <bool FAST, bool ALL, int NW, typename... A>
 void launch_stage0_hp(int hp, int grid, size_t smem, cudaStream_t st, A... a) {
     switch (hp) {
-        case 256: sck::k_scan_stage0<256, FAST, ALL><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
-        case 512: sck::k_scan_stage0<512, FAST, ALL><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
-        case 1024: sck::k_scan_stage0<1024, FAST, ALL><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
-        case 2048: sck::k_scan_stage0<2048, FAST, ALL><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
-        default: sck::k_scan_stage0<4096, FAST, ALL><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
+        case 256: sck::k_scan_stage0<256, FAST, ALL, NW><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
+        case 512: sck::k_scan_stage0<512, FAST, ALL, NW><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
+        case 1024: sck::k_scan_stage0<1024, FAST, ALL, NW><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
+        case 2048: sck::k_scan_stage0<2048, FAST, ALL, NW><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
+        default: sck::k_scan_stage0<4096, FAST, ALL, NW><<<grid, SC_TILE_THREADS, smem, st>>>(a...); break;
     }
 }
-// fast: certified fast filter; all: exact variant that also runs stages 1..N-1 in place (force_all)
+// fast: certified fast filter (nw0 = weak classifiers of stage 0: 2 and 3 have unrolled instantiations);
+// all: exact variant that also runs stages 1..N-1 in place (force_all)
 template <typename... A>
-void launch_stage0(bool fast, bool all, int hp, int grid, size_t smem, cudaStream_t st, A... a) {
-    if (fast) launch_stage0_hp<true, false>(hp, grid, smem, st, a...);
-    else if (all) launch_stage0_hp<false, true>(hp, grid, smem, st, a...);
-    else launch_stage0_hp<false, false>(hp, grid, smem, st, a...);
+void launch_stage0(bool fast, bool all, int nw0, int hp, int grid, size_t smem, cudaStream_t st, A... a) {
+    if (fast && nw0 == 3) launch_stage0_hp<true, false, 3>(hp, grid, smem, st, a...);
+    else if (fast && nw0 == 2) launch_stage0_hp<true, false, 2>(hp, grid, smem, st, a...);
+    else if (fast) launch_stage0_hp<true, false, 0>(hp, grid, smem, st, a...);
+    else if (all) launch_stage0_hp<false, true, 0>(hp, grid, smem, st, a...);
+    else launch_stage0_hp<false, false, 0>(hp, grid, smem, st, a...);
 }
 template <typename... A>
 void launch_stage(int hp, int grid, size_t smem, cudaStream_t st, A... a) {
@@ -499,7 +502,7 @@ int run_group(sc_handle* h, sc_handle::Lane& L, int s0, int g, int frame0, sc_de
             const int rows0 = g * p.rows_per_frame;
             {
                 KernelSpan ks(h, K_STAGE0, st);
-                launch_stage0(h->use_fast, all_in_tile, p.lay.hp, g * p.blocks_per_frame, smem, st, h->fast[0], dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, 0, start_odd, cert, n_items);
+                launch_stage0(h->use_fast, all_in_tile, p.n_weak[0], p.lay.hp, g * p.blocks_per_frame, smem, st, h->fast[0], dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, 0, start_odd, cert, n_items);
             }
             // odd columns: with the adaptive stride they are reachable only as ragged row suffixes -> list of 32-window runs
             // and persistent warps (k_scan_odd); without it (or without the fast filter) the tile kernel does them all
@@ -523,18 +526,16 @@ int run_group(sc_handle* h, sc_handle::Lane& L, int s0, int g, int frame0, sc_de
             KernelSpan ks(h, K_STAGE0_ODD, st);
             if (odd_list) {
                 const int grid = h->n_sms * SC_STAGE0_MIN_CTAS;
-                switch (p.lay.hp) {
-#define SC_ODD(HPV) sck::k_scan_odd<HPV><<<grid, 256, 0, st>>>(h->fast[1], dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, start_odd, \
-                                                            L.d_chunks.as<uint32_t>() + rows0 + (rows0 + 1023) / 1024, small + SM_CHUNKS, small + SM_CURSOR, cert, n_items)
-                    case 256: SC_ODD(256); break;
-                    case 512: SC_ODD(512); break;
-                    case 1024: SC_ODD(1024); break;
-                    case 2048: SC_ODD(2048); break;
-                    default: SC_ODD(4096); break;
+                switch (p.lay.hp * 8 + (p.n_weak[0] == 2 || p.n_weak[0] == 3 ? p.n_weak[0] : 0)) {
+#define SC_ODD(HPV, NWV) case HPV * 8 + NWV: sck::k_scan_odd<HPV, NWV><<<grid, 256, 0, st>>>(h->fast[1], dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, start_odd, \
+                                                            L.d_chunks.as<uint32_t>() + rows0 + (rows0 + 1023) / 1024, small + SM_CHUNKS, small + SM_CURSOR, cert, n_items); break
+#define SC_ODD3(HPV) SC_ODD(HPV, 0); SC_ODD(HPV, 2); SC_ODD(HPV, 3)
+                    SC_ODD3(256); SC_ODD3(512); SC_ODD3(1024); SC_ODD3(2048); SC_ODD3(4096);
+#undef SC_ODD3
 #undef SC_ODD
                 }
             } else {
-                launch_stage0(h->use_fast, all_in_tile, p.lay.hp, g * p.blocks_per_frame, smem, st, h->fast[1], dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, 1, start_odd, cert, n_items);
+                launch_stage0(h->use_fast, all_in_tile, p.n_weak[0], p.lay.hp, g * p.blocks_per_frame, smem, st, h->fast[1], dp, S, geom, w, wb, multi, pass, rec, small + SM_REC, h->rec_cap, 1, start_odd, cert, n_items);
             }
         }
         const int tail_grid = h->n_sms * 8;

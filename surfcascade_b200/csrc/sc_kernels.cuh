@@ -666,6 +666,59 @@ __device__ __forceinline__ float fast_tail(const float* v, const WT& w, float wb
     return rcp_approx(__fadd_rn(1.f, ex2_approx(__fmul_rn(z, -1.44269502f))));
 }
 
+// The same on box sums read from the compact plane: those are exact non-negative integers, so the two-sided clip is
+// min(v_i, t) -- 32 FMNMX instead of 32 saturating FMAs + 16 packed adds -- and nothing needs scaling by 1 / (2t):
+//   z = (w . c) / sqrt(|c|^2 + eps),  c_i = min(v_i, t),  t = theta sqrt(|v|^2 + eps)   (sums stay below 2^37).
+// t carries the relative error of rsqrt.approx (2 ulp) times two roundings, like `a` above; min is exact; the two FFMA2 chains
+// and the final rsqrt are the ones of fast_tail(): the same distance budget covers it.
+template <typename WT>
+__device__ __forceinline__ float fast_tail_nonneg(const float* v, const WT& w, float wb) {
+    float2 s = make_float2(FLT_EPSILON, 0.f);
+#pragma unroll
+    for (int i = 0; i < 16; i++) s = fma2(make_float2(v[2 * i], v[2 * i + 1]), make_float2(v[2 * i], v[2 * i + 1]), s);
+    const float n2 = __fadd_rn(s.x, s.y);
+    const float t = __fmul_rn(__fmul_rn(n2, rsqrt_approx(n2)), 0.353553385f);  // theta |v|
+    float2 sg = make_float2(FLT_EPSILON, 0.f), d = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const float2 g = make_float2(fminf(v[2 * i], t), fminf(v[2 * i + 1], t));
+        sg = fma2(g, g, sg);
+        d = fma2(g, make_float2(w[2 * i], w[2 * i + 1]), d);
+    }
+    const float z = __fmaf_rn(__fadd_rn(d.x, d.y), rsqrt_approx(__fadd_rn(sg.x, sg.y)), wb);
+    return rcp_approx(__fadd_rn(1.f, ex2_approx(__fmul_rn(z, -1.44269502f))));
+}
+
+// Stage-0 sum of the fast weak outputs of one window.  NW > 0: the stage's weak-classifier count as a compile-time constant --
+// the loop is unrolled, so weights are constant-bank operands of the FFMA2s and the corner offsets sit at fixed constant
+// addresses (no LDC / index arithmetic per weak classifier); NW == 0: run-time count (fp.n_weak).
+template <int HP>
+__device__ __forceinline__ float filter_weak(const ScFastParams& fp, int si, int q, const char* __restrict__ base, bool compact) {
+    ScGeom g;
+#pragma unroll
+    for (int k = 0; k < 10; k++) g.c[k] = fp.geom[si][q][k];
+    g.shape = (int)fp.geom[si][q][10]; g.pad = 0;
+    float v[32];
+    if (compact) {
+        box_sums_c<HP>(base, g, HP, v);
+        return fast_tail_nonneg(v, fp.w[q], fp.wb[q]);
+    }
+    box_sums_p<HP>(base, g, HP, v);
+    return fast_tail(v, fp.w[q], fp.wb[q]);
+}
+template <int HP, int NW>
+__device__ __forceinline__ float filter_sum(const ScFastParams& fp, int si, const char* __restrict__ base, uint32_t cmask) {
+    float sum = 0.f;
+    if (NW > 0) {
+#pragma unroll
+        for (int q = 0; q < SC_EXP_NWEAK(NW); q++) sum = __fadd_rn(sum, filter_weak<HP>(fp, si, q, base, (cmask >> q) & 1u));
+    } else {
+#pragma unroll 1
+        for (int q = 0; q < SC_EXP_NWEAK(fp.n_weak); q++) sum = __fadd_rn(sum, filter_weak<HP>(fp, si, q, base, (cmask >> q) & 1u));
+    }
+    return sum;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Stage 0 over the lattice, one x-parity per launch (see SC_TILE_X in sc_plan.h)
 // ---------------------------------------------------------------------------------------------------------
@@ -687,7 +740,7 @@ __device__ __forceinline__ uint32_t spread16(uint32_t x) {  // bit i (i < 16) ->
 // ALL (exact variant only): force_all mode evaluates every stage of every window; the stages 1..N-1 then run right here,
 // on the window whose corners this thread just gathered, instead of as N-1 more passes of k_scan_stage over a record per
 // window (C4: 242 M records re-read three times).  The records it pushes are final.
-template <int HP, bool FAST, bool ALL = false>
+template <int HP, bool FAST, bool ALL = false, int NW = 0>
 __global__ void __launch_bounds__(SC_TILE_THREADS, FAST ? SC_FAST_MIN_CTAS : (ALL ? 2 : SC_STAGE0_MIN_CTAS)) k_scan_stage0(const __grid_constant__ ScFastParams fp, const ScPlan* __restrict__ plan, const float4* __restrict__ S,
                                                                   const ScGeom* __restrict__ geom_all, const float* __restrict__ w_all,
                                                                   const double* __restrict__ wb_all, uint32_t* __restrict__ multi_bits,
@@ -696,8 +749,9 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, FAST ? SC_FAST_MIN_CTAS : (AL
                                                                   const int* __restrict__ start_odd, const uint32_t* __restrict__ cert, int n_items) {
     constexpr int SC_TILE_Y = FAST ? SC_TILE_Y_FAST : SC_TILE_Y_EXACT;  // tile rows of this variant (sc_plan.h)
     const uint32_t block = blockIdx.x;
-    __shared__ uint32_t s_multi[SC_TILE_Y][4];
-    __shared__ uint32_t s_pass[SC_TILE_Y][4];
+    // per tile row and 32-column half: raw ballot words (bit = lane); phase C spreads them to lattice-column bits
+    __shared__ uint32_t s_multi[SC_TILE_Y][2];
+    __shared__ uint32_t s_pass[SC_TILE_Y][2];
     __shared__ uint16_t s_list[SC_TILE_X * SC_TILE_Y];
     __shared__ uint16_t s_list2[FAST ? SC_TILE_X * SC_TILE_Y : 1];
     __shared__ int s_start[SC_TILE_Y];
@@ -778,14 +832,11 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, FAST ? SC_FAST_MIN_CTAS : (AL
             const uint32_t fail = __ballot_sync(0xffffffffu, valid && !pass);
             uint32_t base = 0;
             if (lane == 0) {
-                s_pass[row][2 * half] = spread16(m) << phase;
-                s_pass[row][2 * half + 1] = spread16(m >> 16) << phase;
+                s_pass[row][half] = m;
                 // prefilter failed -> multi = 2 (ObjDetector.cpp:216-217).  FAST: the windows that pass start with their bit
                 // set too -- 99.7 % of them are rejected with multi = 2 -- and the filter CLEARS the bit of the few it
                 // cannot decide or that do not skip: one shared-memory atomic per ~300 windows instead of one per window
-                const uint32_t mb = FAST ? (fail | m) : fail;
-                s_multi[row][2 * half] = spread16(mb) << phase;
-                s_multi[row][2 * half + 1] = spread16(mb >> 16) << phase;
+                s_multi[row][half] = FAST ? (fail | m) : fail;
                 base = atomicAdd(&s_count, __popc(m));
             }
             base = __shfl_sync(0xffffffffu, base, 0);
@@ -814,20 +865,9 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, FAST ? SC_FAST_MIN_CTAS : (AL
                 const int j = tx * SC_TILE_X + half * 32 + ln;
                 const int gy = ty * SC_TILE_Y + row;
                 const char* base = reinterpret_cast<const char*>(lo4 + (gy * ppitch + SC_COL(j)));
-                float sum = 0.f;
-#pragma unroll 1
-                for (int q = 0; q < SC_EXP_NWEAK(fp.n_weak); q++) {
-                    ScGeom g;
-#pragma unroll
-                    for (int k = 0; k < 10; k++) g.c[k] = fp.geom[si][q][k];
-                    g.shape = (int)fp.geom[si][q][10]; g.pad = 0;
-                    float v[32];
-                    if ((cmask >> q) & 1u) box_sums_c<HP>(base, g, HP, v);
-                    else box_sums_p<HP>(base, g, HP, v);
-                    sum = __fadd_rn(sum, fast_tail(v, fp.w[q], fp.wb[q]));
-                }
+                const float sum = filter_sum<HP, NW>(fp, si, base, cmask);
                 if (!(sum < fp.lim_reject && sum < fp.lim_skip)) {  // not "rejected and skips for certain": rare
-                    atomicAnd(&s_multi[row][2 * half + (ln >> 4)], ~(1u << (2 * (ln & 15) + phase)));
+                    atomicAnd(&s_multi[row][half], ~(1u << ln));
                     undecided = !(sum < fp.lim_reject && sum >= fp.lim_noskip);
                 }
             }
@@ -865,7 +905,7 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, FAST ? SC_FAST_MIN_CTAS : (AL
                 const char* base = reinterpret_cast<const char*>(lo4 + (gy * ppitch + SC_COL(j)));
                 score = stage_score<HP>(base, sg, sw, swb, n_weak, HP);
                 rejected = score < theta0;
-                if (rejected && rejected_skips(score, 0, n_stages)) atomicOr(&s_multi[row][2 * half + (ln >> 4)], 1u << (2 * (ln & 15) + phase));
+                if (rejected && rejected_skips(score, 0, n_stages)) atomicOr(&s_multi[row][half], 1u << ln);
                 rej = rejected ? 0 : (n_stages == 1 ? 1 : -1);
                 if (ALL) {
                     // every later stage is evaluated (force_all); the first rejection keeps its stage and score,
@@ -877,7 +917,7 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, FAST ? SC_FAST_MIN_CTAS : (AL
                             score = sc;
                             if (sc < plan->theta[st]) {
                                 rej = st;
-                                if (rejected_skips(sc, st, n_stages)) atomicOr(&s_multi[row][2 * half + (ln >> 4)], 1u << (2 * (ln & 15) + phase));
+                                if (rejected_skips(sc, st, n_stages)) atomicOr(&s_multi[row][half], 1u << ln);
                             } else if (st == n_stages - 1) {
                                 rej = n_stages;
                             }
@@ -910,12 +950,15 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, FAST ? SC_FAST_MIN_CTAS : (AL
         const int gy = ty * SC_TILE_Y + row, wx = tx * 4 + w;
         if (gy < ny && wx < s_sc.wpr) {
             const size_t wi = (size_t)f * plan->words_per_frame + s_sc.word_base + (size_t)gy * s_sc.wpr + wx;
+            // word w of the row: lanes 16 (w & 1) .. + 15 of half w >> 1, one bit per lattice column 2 j + phase
+            const uint32_t mw = spread16(s_multi[row][w >> 1] >> (16 * (w & 1))) << phase;
+            const uint32_t pw = spread16(s_pass[row][w >> 1] >> (16 * (w & 1))) << phase;
             if (phase == 0) {
-                multi_bits[wi] = s_multi[row][w];
-                pass_bits[wi] = s_pass[row][w];
+                multi_bits[wi] = mw;
+                pass_bits[wi] = pw;
             } else {
-                if (s_multi[row][w]) atomicOr(&multi_bits[wi], s_multi[row][w]);
-                if (s_pass[row][w]) atomicOr(&pass_bits[wi], s_pass[row][w]);
+                if (mw) atomicOr(&multi_bits[wi], mw);
+                if (pw) atomicOr(&pass_bits[wi], pw);
             }
         }
     }
@@ -1018,7 +1061,7 @@ __global__ void __launch_bounds__(1024) k_chunk_fill(const uint32_t* __restrict_
 // The claim of the next unit (cursor atomic -> list entry -> row start: three dependent round trips to L2) is issued by
 // lane 0 before the current unit is processed and only broadcast afterwards.
 // (32-window units without compaction: 0.0495 ms/frame on C2, lanes 70 % busy in the filter.)
-template <int HP>
+template <int HP, int NW = 0>
 __global__ void __launch_bounds__(256, SC_STAGE0_MIN_CTAS) k_scan_odd(const __grid_constant__ ScFastParams fp, const ScPlan* __restrict__ plan, const float4* __restrict__ S,
                                                                       const ScGeom* __restrict__ geom_all, const float* __restrict__ w_all,
                                                                       const double* __restrict__ wb_all, uint32_t* __restrict__ multi_bits,
@@ -1110,18 +1153,7 @@ __global__ void __launch_bounds__(256, SC_STAGE0_MIN_CTAS) k_scan_odd(const __gr
             if (ei < n) {
                 gx = g0 + 2 * (int)s_q[warp][ei];
                 const char* base = reinterpret_cast<const char*>(row4 + SC_COL(gx >> 1));
-                float sum = 0.f;
-#pragma unroll 1
-                for (int q = 0; q < SC_EXP_NWEAK(fp.n_weak); q++) {
-                    ScGeom g;
-#pragma unroll
-                    for (int i = 0; i < 10; i++) g.c[i] = fp.geom[si][q][i];
-                    g.shape = (int)fp.geom[si][q][10]; g.pad = 0;
-                    float v[32];
-                    if ((cmask >> q) & 1u) box_sums_c<HP>(base, g, HP, v);
-                    else box_sums_p<HP>(base, g, HP, v);
-                    sum = __fadd_rn(sum, fast_tail(v, fp.w[q], fp.wb[q]));
-                }
+                const float sum = filter_sum<HP, NW>(fp, si, base, cmask);
                 if (!(sum < fp.lim_reject && sum < fp.lim_skip)) {
                     atomicAnd(&s_mb[warp][(gx >> 5) - (g0 >> 5)], ~(1u << (gx & 31)));
                     exact = !(sum < fp.lim_reject && sum >= fp.lim_noskip);
