@@ -8,6 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libsurfcascade_b200.so")
 CLI = os.path.join(HERE, "ObjDetector")
+CLASS_TEST = os.path.join(HERE, "class_detect")   # tests/cpp/class_detect.cpp: the reference's detect branch over the kept classes
 CU = ["csrc/sc_capi.cu"]
 CPP = ["host/sc_host.cpp", "host/cfgfile.cpp", "host/classes.cpp", "host/Model.cpp", "host/DenseSURFFeatureExtractor.cpp"]
 HEADERS = ["csrc/sc_kernels.cuh", "csrc/sc_plan.h", "host/sc_host.h", "host/sc_access.h", "host/cfgfile.h", "host/Model.h", "host/cvcompat.h",
@@ -40,6 +41,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if os.path.exists(os.path.join(HERE, "host", "ObjDetector.cpp")):
         subprocess.check_call([_nvcc()] + NVCC_FLAGS + ["-o", CLI, os.path.join(HERE, "host", "ObjDetector.cpp"), "-L", HERE, "-lsurfcascade_b200",
                                "-Xlinker", "-rpath,$ORIGIN"])
+    src = os.path.join(HERE, "..", "tests", "cpp", "class_detect.cpp")
+    if os.path.exists(src):
+        subprocess.check_call([_nvcc()] + NVCC_FLAGS + ["-o", CLASS_TEST, src, "-L", HERE, "-lsurfcascade_b200", "-Xlinker", "-rpath,$ORIGIN"])
     return LIB
 
 

@@ -3,21 +3,23 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <stdexcept>
+#include <string>
 
 #include "sc_host.h"
 
 namespace {
+// The reference's methods cannot fail (they index host memory unchecked); a GPU error is reported as an exception, never abort().
 [[noreturn]] void die(sc_handle* h, const char* where) {
-    fprintf(stderr, "DenseSURFFeatureExtractor::%s: %s\n", where, sc_last_error(h));
-    abort();
+    throw std::runtime_error(std::string("DenseSURFFeatureExtractor::") + where + ": " + sc_last_error(h));
 }
 sc_rect to_sc(const Rect& r) { return sc_rect{r.x, r.y, r.width, r.height}; }
 }  // namespace
 
 DenseSURFFeatureExtractor::DenseSURFFeatureExtractor() : handle_(nullptr), owns_handle_(true) {
     if (sc_create(0, &handle_) != SC_OK) {
-        fprintf(stderr, "DenseSURFFeatureExtractor: no usable CUDA device; this library has no CPU path\n");
-        abort();
+        handle_ = nullptr;
+        throw std::runtime_error("DenseSURFFeatureExtractor: no usable CUDA device; this library has no CPU path");
     }
 }
 

@@ -4,6 +4,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <stdexcept>
+#include <string>
 
 #include "CascadeClassifier/CascadeClassifier.h"
 #include "CascadeClassifier/GentleAdaboost.h"
@@ -16,8 +18,8 @@ sc_handle* default_handle() {
     if (!h) {
         const int rc = sc_create(0, &h);
         if (rc != SC_OK || !h) {
-            fprintf(stderr, "surfcascade_b200: no usable CUDA device (sc_create -> %d); this library has no CPU path\n", rc);
-            abort();
+            h = nullptr;
+            throw std::runtime_error("surfcascade_b200: no usable CUDA device (sc_create -> " + std::to_string(rc) + "); this library has no CPU path");
         }
     }
     return h;
@@ -34,10 +36,11 @@ void LogisticRegression::set_weights(const float* w33, double bias) {
 
 float LogisticRegression::Predict(std::vector<float>& x) {
     float p = 0.f;
-    if (x.size() != 32 || sc_weak_predict(sc_host::default_handle(), w, &bias_, x.data(), 1, &p) != SC_OK) {
-        fprintf(stderr, "LogisticRegression::Predict: %s\n", x.size() != 32 ? "descriptor must hold 32 floats" : sc_last_error(sc_host::default_handle()));
-        abort();
-    }
+    // The reference reads x[0..31] unchecked and cannot fail; a GPU error or a short descriptor is reported as an exception
+    // (never abort(): the caller's process is not ours to end).
+    if (x.size() < 32) throw std::invalid_argument("LogisticRegression::Predict: descriptor must hold 32 floats");
+    if (sc_weak_predict(sc_host::default_handle(), w, &bias_, x.data(), 1, &p) != SC_OK)
+        throw std::runtime_error(std::string("LogisticRegression::Predict: ") + sc_last_error(sc_host::default_handle()));
     return p;
 }
 
@@ -52,10 +55,8 @@ float GentleAdaboost::mean_probability(const std::vector<const float*>& descript
         b[i] = weak_classifiers[i]->bias_;
     }
     float mean = 0.f;
-    if (sc_stage_predict(sc_host::default_handle(), w.data(), b.data(), x.data(), n, &mean) != SC_OK) {
-        fprintf(stderr, "GentleAdaboost: %s\n", sc_last_error(sc_host::default_handle()));
-        abort();
-    }
+    if (sc_stage_predict(sc_host::default_handle(), w.data(), b.data(), x.data(), n, &mean) != SC_OK)
+        throw std::runtime_error(std::string("GentleAdaboost: ") + sc_last_error(sc_host::default_handle()));
     return mean;
 }
 
@@ -66,9 +67,9 @@ float GentleAdaboost::Predict(std::vector<std::vector<float>>& x) {
 }
 
 float GentleAdaboost::Predict2(std::vector<std::vector<float>>& x) {
-    if (x.size() != weak_classifiers.size()) { fprintf(stderr, "GentleAdaboost::Predict2: one descriptor per weak classifier expected\n"); abort(); }
+    if (x.size() < weak_classifiers.size()) throw std::invalid_argument("GentleAdaboost::Predict2: one descriptor per weak classifier expected");
     std::vector<const float*> d;
-    for (auto& v : x) d.push_back(v.data());
+    for (size_t i = 0; i < weak_classifiers.size(); i++) d.push_back(x[i].data());
     return mean_probability(d);
 }
 

@@ -15,7 +15,7 @@ struct Access {
     static bool flatten(CascadeClassifier& cc, int tmpl, FlatCascade* out, std::string* why);
 };
 
-// Lazily created handle on CUDA device 0; aborts with a message when no GPU is usable (there is no CPU path).
+// Lazily created handle on CUDA device 0; throws std::runtime_error when no GPU is usable (there is no CPU path).
 sc_handle* default_handle();
 
 }  // namespace sc_host
