@@ -7,7 +7,7 @@ from surfcascade_b200 import capi, synth
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 tag = sys.argv[2] if len(sys.argv) > 2 else ""
-MODEL = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "model_c1.cfg")
+MODEL = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", sys.argv[3] if len(sys.argv) > 3 else "model_c1.cfg")
 h = capi.Handle(0); h.load_model(MODEL, 40)
 base = [synth.frame(1080, 1920, 100 + i) for i in range(4)]
 fd = torch.from_numpy(np.stack([base[i % 4] for i in range(n)])).cuda()

@@ -44,6 +44,23 @@ rows.append(("C4 3840x2160 step 1, all 4 stages (22 weak) forced", f"{ms:.1f} ms
 ms, c, nd = timed_device(fd, 1, 3840, 2160, capi.params(step=1), reps=3)
 rows.append(("4K step 1, reference semantics (prefilter, early reject, stride)", f"{ms:.1f} ms/frame", f"{c[0].grid/ms/1e6:.2f} G grid windows/s", f"visited {c[0].visited}, evaluated {c[0].evaluated}"))
 del fd
+# SURVEY.md 8(d)'s paper-shaped cascade (tests/golden/model_paper8.cfg: 8 stages, 2/3/5/8/12/16/24/32 weak classifiers) on C2 and C4
+PAPER = os.path.join(os.path.dirname(MODEL), "model_paper8.cfg")
+if os.path.exists(PAPER):
+    h.load_model(PAPER, 40)
+    f = np.stack([synth.frame(1080, 1920, 100 + i % 8) for i in range(32)])
+    fd = torch.from_numpy(f).cuda()
+    ms, c, nd = timed_device(fd, 32, 1920, 1080, capi.params(), reps=3)
+    rows.append(("C2 with the paper-shaped 8-stage cascade (102 weak; stage 0: 2 weak, passes ~10 %)", f"{ms/32:.3f} ms/frame", f"{32e3/ms:.0f} frames/s",
+                 f"visited {c[0].visited}, weak evaluations (reference count) {c[0].weak_evals} = {c[0].weak_evals*32/ms/1e6:.1f} G/s, reach {[c[0].reach[i] for i in range(8)]}, raw {nd//32}/frame"))
+    del fd
+    f = synth.frame(2160, 3840, 300, n_objects=12)[None]
+    fd = torch.from_numpy(f).cuda()
+    ms, c, nd = timed_device(fd, 1, 3840, 2160, capi.params(step=1, prefilter=-1, skip_rule=False, force_all_stages=True), reps=2)
+    we = c[0].grid * 102
+    rows.append(("C4 with the paper-shaped cascade: 3840x2160 step 1, all 8 stages (102 weak) forced", f"{ms:.1f} ms/frame", f"{c[0].grid/ms/1e6:.2f} G windows/s", f"{we/ms/1e6:.1f} G exact weak evaluations/s"))
+    del fd
+    h.load_model(MODEL, 40)
 # C5: 100k samples x 608 candidates x 32 floats resident in HBM (7.78 GB)
 N, P = 100000, 608
 X = torch.randn(N, P, 32, device="cuda") * 0.2
