@@ -201,6 +201,30 @@ int sc_detect_collect(sc_handle* h, int ticket, sc_detection* out, size_t cap, s
 int sc_detect_device(sc_handle* h, const uint8_t* d_frames, int nframes, int W, int H,
                      const sc_detect_params* params, sc_detection* d_out, size_t cap, uint32_t* d_n);
 int sc_sync(sc_handle* h);
+
+/* ---- multi-GPU exchange: one process per GPU, frames sharded by the caller, NCCL over NVLink -------------
+ * The reference has one host and no exchange; its counterpart here is the step before ObjDetector.cpp:224-231 (grouping and
+ * output on one host): every rank's detection records travel to `root`.  NCCL is loaded at run time (libnccl.so.2, the copy
+ * already in the process if there is one), so single-GPU users need no NCCL.
+ *   sc_comm_unique_id : rank 0 creates the 128-byte NCCL id; the caller hands it to the other ranks (file, socket, MPI, ...).
+ *   sc_comm_init      : collective over all ranks; the handle's device must be this rank's GPU.  world == 1 is allowed.
+ *   sc_gather_detections : collective.  This rank contributes n_local records at `local` (host or device memory,
+ *       local_on_device); their frame index becomes frame * frame_mul + frame_add on the way (round-robin sharding:
+ *       frame_mul = world, frame_add = rank).  Counts are exchanged first (ncclAllGather), then exactly n records per rank
+ *       move to root (grouped ncclSend / ncclRecv) -- no fixed-size slices.  On root: out (host, cap records) receives the
+ *       ranks' records in rank order, *n_out their number, per_rank[world] (optional) every rank's count; SC_ERR_CAPACITY
+ *       (with *n_out = needed) if cap is too small.  Other ranks: out may be null.  The exchange runs on the handle's own
+ *       communication stream: scan work already enqueued for the next batch (sc_detect_submit / sc_detect_device) keeps the
+ *       GPU busy meanwhile.  Records may be raw windows or, with sc_detect_params.group_threshold > 0, the grouped objects
+ *       of whole frames -- then only final objects cross NVLink and root has no grouping left to do.
+ *   sc_comm_destroy   : collective teardown (also done by sc_destroy). */
+#define SC_COMM_ID_BYTES 128
+int sc_comm_unique_id(void* id /* SC_COMM_ID_BYTES */);
+int sc_comm_init(sc_handle* h, int rank, int world, const void* id /* SC_COMM_ID_BYTES */);
+int sc_gather_detections(sc_handle* h, const sc_detection* local, size_t n_local, int local_on_device, int32_t frame_mul, int32_t frame_add,
+                         int root, sc_detection* out, size_t cap, size_t* n_out, size_t* per_rank);
+int sc_comm_destroy(sc_handle* h);
+
 /* Counters of the last sc_detect_device batch (after sc_sync). */
 int sc_last_counters(sc_handle* h, sc_counters* counters, int nframes);
 /* cudaStream_t of the handle, for callers that time or order work with CUDA events. */

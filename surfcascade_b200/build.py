@@ -11,7 +11,7 @@ CLI = os.path.join(HERE, "ObjDetector")
 CLASS_TEST = os.path.join(HERE, "class_detect")   # tests/cpp/class_detect.cpp: the reference's detect branch over the kept classes
 CU = ["csrc/sc_capi.cu"]
 CPP = ["host/sc_host.cpp", "host/cfgfile.cpp", "host/classes.cpp", "host/Model.cpp", "host/DenseSURFFeatureExtractor.cpp"]
-HEADERS = ["csrc/sc_kernels.cuh", "csrc/sc_plan.h", "host/sc_host.h", "host/sc_access.h", "host/cfgfile.h", "host/Model.h", "host/cvcompat.h",
+HEADERS = ["csrc/sc_kernels.cuh", "csrc/sc_plan.h", "csrc/sc_comm.inc", "host/sc_host.h", "host/sc_access.h", "host/cfgfile.h", "host/Model.h", "host/cvcompat.h",
            "host/CascadeClassifier/CascadeClassifier.h", "host/CascadeClassifier/GentleAdaboost.h", "host/CascadeClassifier/LogisticRegression.h",
            "host/CascadeClassifier/StageClassifier.h", "host/FeatureExtractors/DenseSURFFeatureExtractor.h", "../include/surfcascade.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",

@@ -45,9 +45,21 @@ EXPORTS = ["sc_create", "sc_destroy", "sc_last_error", "sc_version", "sc_set_cas
            "sc_detect_device", "sc_sync", "sc_last_counters", "sc_stream", "sc_launch_count", "sc_group_rectangles",
            "sc_set_profiling", "sc_kernel_stats", "sc_model_flatten", "sc_model_resave", "sc_pool_eval", "sc_pool_hist_device",
            "sc_pool_auc_device", "sc_probe_gather", "sc_probe_stream", "sc_stage0_fast_check", "sc_detect_submit", "sc_detect_collect", "sc_extract_pool_features", "sc_extract_pool_features_device", "sc_mine_negatives", "sc_integral_scan_layout",
-           "sc_integral_compact", "sc_box_sums_compact", "sc_cell_bounds"]
+           "sc_integral_compact", "sc_box_sums_compact", "sc_cell_bounds",
+           "sc_comm_unique_id", "sc_comm_init", "sc_gather_detections", "sc_comm_destroy"]
 
 _lib = None
+
+
+def comm_unique_id() -> bytes:
+    """128-byte NCCL id created by rank 0 (sc_comm_unique_id); hand it to the other ranks."""
+    L = lib()
+    buf = C.create_string_buffer(128)
+    L.sc_comm_unique_id.argtypes = [C.c_char_p]
+    rc = L.sc_comm_unique_id(buf)
+    if rc != 0:
+        raise SurfCascadeError(rc, "sc_comm_unique_id failed (NCCL not loadable?)")
+    return buf.raw
 
 
 class SurfCascadeError(RuntimeError):
@@ -265,6 +277,39 @@ class Handle:
         out = np.zeros((len(w), n_stages), np.float32)
         self._check(lib().sc_stage_scores(self._h, w.ctypes.data, len(w), out.ctypes.data))
         return out
+
+    # ---- multi-GPU exchange over NCCL (sc_comm_init / sc_gather_detections, include/surfcascade.h) ----
+    def comm_init(self, rank: int, world: int, comm_id: bytes) -> None:
+        L = lib()
+        L.sc_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+        self._check(L.sc_comm_init(self._h, rank, world, comm_id))
+        self._comm = (rank, world)
+
+    def comm_destroy(self) -> None:
+        L = lib()
+        L.sc_comm_destroy.argtypes = [C.c_void_p]
+        self._check(L.sc_comm_destroy(self._h))
+
+    def gather_detections(self, local, frame_mul: int = 1, frame_add: int = 0, root: int = 0, cap: int = 1 << 20, device_ptr: int = 0, n_device: int = 0):
+        """Every rank's records to `root` (collective).  `local`: DETECTION_DTYPE array on the host, or device_ptr / n_device for
+        records in device memory.  Returns (records, per_rank_counts) on root, (None, per_rank_counts) elsewhere."""
+        rank, world = self._comm
+        L = lib()
+        L.sc_gather_detections.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int32, C.c_int32, C.c_int, C.c_void_p, C.c_size_t,
+                                           C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        per = (C.c_size_t * world)()
+        n_out = C.c_size_t(0)
+        if device_ptr:
+            src, n, on_dev = device_ptr, n_device, 1
+        else:
+            local = np.ascontiguousarray(local, DETECTION_DTYPE)
+            src, n, on_dev = (local.ctypes.data if len(local) else None), len(local), 0
+        out = np.zeros(cap if rank == root else 0, DETECTION_DTYPE)
+        rc = L.sc_gather_detections(self._h, src, n, on_dev, frame_mul, frame_add, root, out.ctypes.data if rank == root else None, cap, C.byref(n_out), per)
+        if rc == SC_ERR_CAPACITY and rank == root:
+            raise SurfCascadeError(rc, f"gather capacity {cap} < {n_out.value}")
+        self._check(rc)
+        return (out[:n_out.value] if rank == root else None), [int(v) for v in per]
 
     def stage0_fast_check(self, wins):
         """(fast_sum [n], exact_sum [n], margin) of stage 0 for windows {x, y, l} on the last integral()."""

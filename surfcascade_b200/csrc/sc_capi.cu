@@ -56,10 +56,13 @@ bool same_params(const sc_detect_params& a, const sc_detect_params& b) {
 
 }  // namespace
 
+struct sc_comm_state;   // NCCL exchange (sc_comm.inc)
+
 struct sc_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
+    sc_comm_state* comm = nullptr;   // multi-GPU exchange (sc_comm_init)
     int64_t launches = 0;
     int n_sms = 148;
 
@@ -706,6 +709,7 @@ int sc_create(int device, sc_handle** out) {
 void sc_destroy(sc_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    sc_comm_destroy(h);
     if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     for (auto& L : h->lanes) {
         if (L.st) { cudaStreamSynchronize(L.st); cudaStreamDestroy(L.st); }
@@ -1584,3 +1588,5 @@ int sc_group_rectangles(const sc_rect* rects, const double* scores, int n, int g
 }
 
 }  // extern "C"
+
+#include "sc_comm.inc"
