@@ -208,15 +208,22 @@ int sc_sync(sc_handle* h);
  * already in the process if there is one), so single-GPU users need no NCCL.
  *   sc_comm_unique_id : rank 0 creates the 128-byte NCCL id; the caller hands it to the other ranks (file, socket, MPI, ...).
  *   sc_comm_init      : collective over all ranks; the handle's device must be this rank's GPU.  world == 1 is allowed.
- *   sc_gather_detections : collective.  This rank contributes n_local records at `local` (host or device memory,
- *       local_on_device); their frame index becomes frame * frame_mul + frame_add on the way (round-robin sharding:
- *       frame_mul = world, frame_add = rank).  Counts are exchanged first (ncclAllGather), then exactly n records per rank
- *       move to root (grouped ncclSend / ncclRecv) -- no fixed-size slices.  On root: out (host, cap records) receives the
- *       ranks' records in rank order, *n_out their number, per_rank[world] (optional) every rank's count; SC_ERR_CAPACITY
- *       (with *n_out = needed) if cap is too small.  Other ranks: out may be null.  The exchange runs on the handle's own
- *       communication stream: scan work already enqueued for the next batch (sc_detect_submit / sc_detect_device) keeps the
- *       GPU busy meanwhile.  Records may be raw windows or, with sc_detect_params.group_threshold > 0, the grouped objects
- *       of whole frames -- then only final objects cross NVLink and root has no grouping left to do.
+ *   sc_gather_detections : collective.  This rank contributes n_local records at `local` (local_on_device: 0 = host memory;
+ *       1 = device memory, possibly still being written by work on the handle's stream, which the exchange then waits for;
+ *       2 = device memory known to be complete, nothing is waited for); their frame index becomes frame * frame_mul + frame_add
+ *       on the way (round-robin sharding: frame_mul = world, frame_add = rank).  Exactly n_local records per rank move to root,
+ *       with their count -- no fixed-size slices.  Default transport: copy engines over NVLink into a region of root's HBM that
+ *       every rank mapped with CUDA IPC at sc_comm_init (records, then an 8-byte {sequence, count} header in stream order; root
+ *       polls the headers, reads exactly `count` records per rank and acknowledges) -- no kernel runs, so the exchange is not
+ *       queued behind the scan kernels of the next batch (NCCL's own kernels were: csrc/sc_comm.inc).  Fallback (no peer mapping,
+ *       or SC_COMM_NCCL_ONLY=1): ncclAllGather of the counts, then grouped ncclSend / ncclRecv.  On root: out (host, cap
+ *       records) receives the ranks' records in rank order, *n_out their number, per_rank[world] (optional) every rank's count;
+ *       SC_ERR_CAPACITY (with *n_out = needed) if cap is too small.  Other ranks: out may be null, per_rank holds only their own
+ *       count.  The exchange runs on the handle's own high-priority communication stream: scan work already enqueued for the
+ *       next batch (sc_detect_submit / sc_detect_device) keeps the GPU busy meanwhile.  Records may be raw windows or, with
+ *       sc_detect_params.group_threshold > 0, the grouped objects of whole frames -- then only final objects cross NVLink and
+ *       root has no grouping left to do.  Use one root per communicator; a rank may contribute up to SC_COMM_SLOT_RECORDS
+ *       (environment, default 131072) records per call on the peer path.
  *   sc_comm_destroy   : collective teardown (also done by sc_destroy). */
 #define SC_COMM_ID_BYTES 128
 int sc_comm_unique_id(void* id /* SC_COMM_ID_BYTES */);
@@ -227,6 +234,10 @@ int sc_comm_destroy(sc_handle* h);
 
 /* Counters of the last sc_detect_device batch (after sc_sync). */
 int sc_last_counters(sc_handle* h, sc_counters* counters, int nframes);
+/* Bytes the host-buffer detect entry points (sc_detect, sc_detect_submit / sc_detect_collect) have copied host -> device
+ * (frames) and device -> host (counters, counts, detection records) since the handle was created or last reset: counted at
+ * the copies themselves. */
+int sc_transfer_bytes(sc_handle* h, uint64_t* h2d, uint64_t* d2h, int reset);
 /* cudaStream_t of the handle, for callers that time or order work with CUDA events. */
 void* sc_stream(sc_handle* h);
 /* Number of kernel launches issued by this handle so far. */

@@ -46,7 +46,7 @@ EXPORTS = ["sc_create", "sc_destroy", "sc_last_error", "sc_version", "sc_set_cas
            "sc_set_profiling", "sc_kernel_stats", "sc_model_flatten", "sc_model_resave", "sc_pool_eval", "sc_pool_hist_device",
            "sc_pool_auc_device", "sc_probe_gather", "sc_probe_stream", "sc_stage0_fast_check", "sc_detect_submit", "sc_detect_collect", "sc_extract_pool_features", "sc_extract_pool_features_device", "sc_mine_negatives", "sc_integral_scan_layout",
            "sc_integral_compact", "sc_box_sums_compact", "sc_cell_bounds",
-           "sc_comm_unique_id", "sc_comm_init", "sc_gather_detections", "sc_comm_destroy"]
+           "sc_comm_unique_id", "sc_comm_init", "sc_gather_detections", "sc_comm_destroy", "sc_transfer_bytes"]
 
 _lib = None
 
@@ -278,6 +278,14 @@ class Handle:
         self._check(lib().sc_stage_scores(self._h, w.ctypes.data, len(w), out.ctypes.data))
         return out
 
+    def transfer_bytes(self, reset: bool = False) -> tuple[int, int]:
+        """(host -> device, device -> host) bytes copied by the host-buffer detect entry points since creation / last reset."""
+        L = lib()
+        L.sc_transfer_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._check(L.sc_transfer_bytes(self._h, C.byref(a), C.byref(b), int(reset)))
+        return int(a.value), int(b.value)
+
     # ---- multi-GPU exchange over NCCL (sc_comm_init / sc_gather_detections, include/surfcascade.h) ----
     def comm_init(self, rank: int, world: int, comm_id: bytes) -> None:
         L = lib()
@@ -290,7 +298,8 @@ class Handle:
         L.sc_comm_destroy.argtypes = [C.c_void_p]
         self._check(L.sc_comm_destroy(self._h))
 
-    def gather_detections(self, local, frame_mul: int = 1, frame_add: int = 0, root: int = 0, cap: int = 1 << 20, device_ptr: int = 0, n_device: int = 0):
+    def gather_detections(self, local, frame_mul: int = 1, frame_add: int = 0, root: int = 0, cap: int = 1 << 20, device_ptr: int = 0, n_device: int = 0,
+                          complete: bool = False, out=None):
         """Every rank's records to `root` (collective).  `local`: DETECTION_DTYPE array on the host, or device_ptr / n_device for
         records in device memory.  Returns (records, per_rank_counts) on root, (None, per_rank_counts) elsewhere."""
         rank, world = self._comm
@@ -300,11 +309,14 @@ class Handle:
         per = (C.c_size_t * world)()
         n_out = C.c_size_t(0)
         if device_ptr:
-            src, n, on_dev = device_ptr, n_device, 1
+            src, n, on_dev = device_ptr, n_device, (2 if complete else 1)
         else:
             local = np.ascontiguousarray(local, DETECTION_DTYPE)
             src, n, on_dev = (local.ctypes.data if len(local) else None), len(local), 0
-        out = np.zeros(cap if rank == root else 0, DETECTION_DTYPE)
+        if out is None:
+            out = np.zeros(cap if rank == root else 0, DETECTION_DTYPE)
+        elif rank == root:
+            cap = len(out)
         rc = L.sc_gather_detections(self._h, src, n, on_dev, frame_mul, frame_add, root, out.ctypes.data if rank == root else None, cap, C.byref(n_out), per)
         if rc == SC_ERR_CAPACITY and rank == root:
             raise SurfCascadeError(rc, f"gather capacity {cap} < {n_out.value}")

@@ -63,6 +63,7 @@ struct sc_handle {
     cudaStream_t stream = nullptr;
     std::string err;
     sc_comm_state* comm = nullptr;   // multi-GPU exchange (sc_comm_init)
+    unsigned long long h2d_bytes = 0, d2h_bytes = 0;   // bytes the detect entry points copied between host and device (sc_transfer_bytes)
     int64_t launches = 0;
     int n_sms = 148;
 
@@ -601,6 +602,7 @@ int run_supergroup(sc_handle* h, const uint8_t* const* frames, int stride, const
             for (int k = 0; k < n; k++)
                 SC_CUDA(h, cudaMemcpy2DAsync(up + (size_t)(c0 + k) * p.W * p.H, p.W, frames[c0 + k], stride, p.W, p.H,
                                              cudaMemcpyHostToDevice, h->copy_st));
+            h->h2d_bytes += (unsigned long long)n * p.W * p.H;
             SC_CUDA(h, cudaEventRecord(h->ev_chunk[2 * c], h->copy_st));
             SC_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_chunk[2 * c], 0));
         }
@@ -1392,6 +1394,7 @@ int sc_detect_submit(sc_handle* h, const uint8_t* const* frames, int nframes, in
     }
     unsigned char* ho = t.h_out.as<unsigned char>();
     SC_CUDA(h, cudaMemcpyAsync(ho, t.d_counters.p, cbytes, cudaMemcpyDeviceToHost, h->stream));
+    h->d2h_bytes += cbytes;
     t.group_thr = prm.group_threshold > 0 ? prm.group_threshold : 0;
     t.group_eps = prm.group_eps;
     if (t.group_thr > 0) {
@@ -1426,9 +1429,11 @@ int sc_detect_submit(sc_handle* h, const uint8_t* const* frames, int nframes, in
         SC_CUDA(h, cudaMemcpyAsync(ho + cbytes, flags, 8, cudaMemcpyDeviceToHost, h->stream));  // overflow, object count
         SC_CUDA(h, cudaMemcpyAsync(ho + cbytes + 8, t.d_cnt.p, 4, cudaMemcpyDeviceToHost, h->stream));
         SC_CUDA(h, cudaMemcpyAsync(ho + cbytes + 16, gout, (size_t)t.eager * sizeof(sck::ScGroupOut), cudaMemcpyDeviceToHost, h->stream));
+        h->d2h_bytes += 12 + (unsigned long long)t.eager * sizeof(sck::ScGroupOut);
     } else {
         SC_CUDA(h, cudaMemcpyAsync(ho + cbytes, t.d_cnt.p, 4, cudaMemcpyDeviceToHost, h->stream));
         SC_CUDA(h, cudaMemcpyAsync(ho + cbytes + 16, t.d_det.p, (size_t)t.eager * sizeof(sc_detection), cudaMemcpyDeviceToHost, h->stream));
+        h->d2h_bytes += 4 + (unsigned long long)t.eager * sizeof(sc_detection);
     }
     SC_CUDA(h, cudaEventRecord(t.done, h->stream));
     t.busy = true;
@@ -1461,6 +1466,7 @@ int sc_detect_collect(sc_handle* h, int ticket, sc_detection* out, size_t cap, s
             // a frame holds more raw windows than one CTA groups (SC_GROUP_MAX): this batch is grouped on the host
             std::vector<sc_detection> rawd(raw);
             if (raw) SC_CUDA(h, cudaMemcpy(rawd.data(), t.d_det.p, (size_t)raw * sizeof(sc_detection), cudaMemcpyDeviceToHost));
+            h->d2h_bytes += (unsigned long long)raw * sizeof(sc_detection);
             sort_detections(rawd.data(), raw);
             size_t k = 0, m = 0;
             while (k < raw) {
@@ -1486,6 +1492,7 @@ int sc_detect_collect(sc_handle* h, int ticket, sc_detection* out, size_t cap, s
             const size_t seg_bytes = align256((size_t)t.det_cap * sizeof(sc_detection)), tab_bytes = align256(((size_t)3 * t.nframes + 8) * 4);
             SC_CUDA(h, cudaMemcpy(g.data() + k, reinterpret_cast<const sck::ScGroupOut*>(t.d_grp.as<unsigned char>() + seg_bytes + tab_bytes) + k,
                                   (size_t)(objs - k) * sizeof(sck::ScGroupOut), cudaMemcpyDeviceToHost));
+            h->d2h_bytes += (unsigned long long)(objs - k) * sizeof(sck::ScGroupOut);
         }
         std::sort(g.begin(), g.end(), [](const sck::ScGroupOut& a, const sck::ScGroupOut& b) { return a.frame != b.frame ? a.frame < b.frame : a.idx < b.idx; });
         for (uint32_t i = 0; i < objs; i++) out[i] = sc_detection{g[i].frame, g[i].x, g[i].y, g[i].w, g[i].score};
@@ -1498,9 +1505,20 @@ int sc_detect_collect(sc_handle* h, int ticket, sc_detection* out, size_t cap, s
     if (found) {
         const uint32_t k = std::min(found, t.eager);
         memcpy(out, ho + cbytes + 16, (size_t)k * sizeof(sc_detection));
-        if (found > k) SC_CUDA(h, cudaMemcpy(out + k, t.d_det.as<sc_detection>() + k, (size_t)(found - k) * sizeof(sc_detection), cudaMemcpyDeviceToHost));
+        if (found > k) {
+            SC_CUDA(h, cudaMemcpy(out + k, t.d_det.as<sc_detection>() + k, (size_t)(found - k) * sizeof(sc_detection), cudaMemcpyDeviceToHost));
+            h->d2h_bytes += (unsigned long long)(found - k) * sizeof(sc_detection);
+        }
         sort_detections(out, found);
     }
+    return SC_OK;
+}
+
+int sc_transfer_bytes(sc_handle* h, uint64_t* h2d, uint64_t* d2h, int reset) {
+    if (!h) return SC_ERR_INVALID;
+    if (h2d) *h2d = h->h2d_bytes;
+    if (d2h) *d2h = h->d2h_bytes;
+    if (reset) { h->h2d_bytes = 0; h->d2h_bytes = 0; }
     return SC_OK;
 }
 
