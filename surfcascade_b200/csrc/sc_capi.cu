@@ -215,13 +215,13 @@ sc_detect_params default_params() {
 
 // Distance budget between the fast filter's sum of weak outputs and the reference arithmetic's, stage 0
 // (sc_kernels.cuh "Error budget", doubled), plus the float summations and the division by n on both sides.
-double fast_margin(const sc_handle* h) {
+double fast_margin(const sc_handle* h, int stage = 0) {
     const double u = 5.9604644775390625e-8;  // 2^-24
-    const int n0 = h->n_weak[0];
+    const int n0 = h->n_weak[stage], wb = h->weak_base[stage];
     double margin = 0.0;
     for (int q = 0; q < n0; q++) {
         double n2 = 0.0;
-        for (int i = 0; i < 32; i++) n2 += (double)h->w[(size_t)q * 33 + i] * h->w[(size_t)q * 33 + i];
+        for (int i = 0; i < 32; i++) n2 += (double)h->w[(size_t)(wb + q) * 33 + i] * h->w[(size_t)(wb + q) * 33 + i];
         margin += 2.0 * (0.25 * 121.0 * u * std::sqrt(n2) + 1.5e-6);
     }
     return margin + (double)n0 * n0 * 4.0 * u + 8.0 * u * n0;
@@ -306,6 +306,16 @@ int build_plan(sc_handle* h, int W, int H, const sc_detect_params& prm, std::vec
                                            &(*geom_out)[((size_t)ph * nsc + i) * h->total_weak + k]))
                     return fail(h, SC_ERR_INVALID, "weak classifier patch is not 2x2 / 4x1 / 1x4 cells after projection");
 
+    // Certified fast arithmetic of k_scan_stage (sc_kernels.cuh): the same limits for every stage p, on the float sum of its
+    // fast weak outputs.  Rejected at stage p: multi == 2  <=>  (score + p + 1) / N < 0.5  <=>  score < N / 2 - p - 1.
+    p.stage_fast = (h->allow_fast && !p.force_all) ? 1 : 0;
+    for (int sgi = 0; sgi < h->n_stages; sgi++) {
+        const double m = fast_margin(h, sgi), ns = (double)h->n_weak[sgi], tau_s = 0.5 * h->n_stages - sgi - 1.0;
+        p.fl_reject[sgi] = std::nextafterf((float)(ns * h->theta[sgi] - m), -INFINITY);
+        p.fl_pass[sgi] = std::nextafterf((float)(ns * h->theta[sgi] + m), INFINITY);
+        p.fl_skip[sgi] = std::nextafterf((float)(ns * tau_s - m), -INFINITY);
+        p.fl_noskip[sgi] = std::nextafterf((float)(ns * tau_s + m), INFINITY);
+    }
     // Certified fast filter for stage 0 (sc_kernels.cuh, "Error budget").  Limits are on the float sum of the fast weak outputs.
     const int n0 = h->n_weak[0];
     h->use_fast = fast_plan && nsc >= 1;
@@ -320,6 +330,7 @@ int build_plan(sc_handle* h, int W, int H, const sc_detect_params& prm, std::vec
             fp.lim_reject = std::nextafterf((float)((double)n0 * h->theta[0] - margin), -INFINITY);
             fp.lim_skip = std::nextafterf((float)((double)n0 * tau - margin), -INFINITY);
             fp.lim_noskip = std::nextafterf((float)((double)n0 * tau + margin), INFINITY);
+            fp.lim_pass = h->n_stages > 1 ? std::nextafterf((float)((double)n0 * h->theta[0] + margin), INFINITY) : INFINITY;
             for (int q = 0; q < n0; q++) {
                 fp.wb[q] = (float)((double)h->w[(size_t)q * 33 + 32] * h->bias[q]);
                 memcpy(fp.w[q], &h->w[(size_t)q * 33], 32 * sizeof(float));

@@ -880,6 +880,7 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, FAST ? SC_FAST_MIN_CTAS : (AL
                     if (!(sum < fp.lim_reject && sum < fp.lim_skip)) {  // not "rejected and skips for certain": rare
                         atomicAnd(&s_multi[row][half], ~(1u << ln));
                         undecided = !(sum < fp.lim_reject && sum >= fp.lim_noskip);
+                        if (undecided && sum >= fp.lim_pass) code |= 0x8000u;  // passes stage 0 for certain: no exact stage 0 needed
                     }
                 }
                 const uint32_t m = __ballot_sync(0xffffffffu, undecided);
@@ -911,12 +912,12 @@ __global__ void __launch_bounds__(SC_TILE_THREADS, FAST ? SC_FAST_MIN_CTAS : (AL
         r.fs = 0; r.yx = 0; r.rej = 0; r.score = 0;
         if (i < count) {
             const uint32_t code = list[i];
-            const int row = code >> 6, half = (code >> 5) & 1, ln = code & 31;
+            const int row = (code >> 6) & 0x1ff, half = (code >> 5) & 1, ln = code & 31;
             const int j = tx * SC_TILE_X + half * 32 + ln;
             const int gx = 2 * j + phase, gy = ty * SC_TILE_Y + row;
             float score = 0.f;
             bool rejected = false;
-            int rej = -1;  // FAST: still alive, k_scan_stage(0) decides
+            int rej = (FAST && (code & 0x8000u)) ? -2 : -1;  // FAST: still alive; -1: k_scan_stage(0) decides, -2: stage 0 certainly passed
             if (!FAST) {
                 const char* base = reinterpret_cast<const char*>(lo4 + (gy * ppitch + SC_COL(j)));
                 score = stage_score<HP>(base, sg, sw, swb, n_weak, HP);
@@ -1166,7 +1167,7 @@ __global__ void __launch_bounds__(256, SC_STAGE0_MIN_CTAS) k_scan_odd(const __gr
             constexpr int MODE = decltype(mode_tag)::value;
             for (int b0 = 0; b0 < n; b0 += 32) {
                 const int ei = b0 + lane;
-                bool exact = false;
+                bool exact = false, passed = false;
                 int gx = 0;
                 if (ei < n) {
                     gx = g0 + 2 * (int)s_q[warp][ei];
@@ -1175,6 +1176,7 @@ __global__ void __launch_bounds__(256, SC_STAGE0_MIN_CTAS) k_scan_odd(const __gr
                     if (!(sum < fp.lim_reject && sum < fp.lim_skip)) {
                         atomicAnd(&s_mb[warp][(gx >> 5) - (g0 >> 5)], ~(1u << (gx & 31)));
                         exact = !(sum < fp.lim_reject && sum >= fp.lim_noskip);
+                        passed = exact && sum >= fp.lim_pass;
                     }
                 }
                 const uint32_t m = __ballot_sync(0xffffffffu, exact);
@@ -1188,7 +1190,7 @@ __global__ void __launch_bounds__(256, SC_STAGE0_MIN_CTAS) k_scan_odd(const __gr
                             ScRecord rc;
                             rc.fs = ((uint32_t)f << 8) | (uint32_t)si;
                             rc.yx = ((uint32_t)gy << 16) | (uint32_t)gx;
-                            rc.rej = -1; rc.score = 0;
+                            rc.rej = passed ? -2 : -1; rc.score = 0;  // -2: stage 0 certainly passed (no exact stage 0 needed)
                             rec[slot] = rc;
                         }
                     }
@@ -1219,6 +1221,14 @@ __global__ void __launch_bounds__(256, SC_STAGE0_MIN_CTAS) k_scan_odd(const __gr
 // 32-byte sector reads -- DRAM 50 % busy at 0.35 GB per launch, L2 hit rate 35 % because the 8 integral images of a scan
 // group have left L2 by then -- not on the serial chain, and fewer windows per warp lose the lines x-adjacent survivors share.)
 // ---------------------------------------------------------------------------------------------------------
+// Certified fast arithmetic for the later stages (and for stage 0's undecided windows): the same fast_weak evaluation as the
+// stage-0 filter, with the stage's weights in shared memory and the per-record geometry from global memory, decides a record
+// when the float sum of the fast weak outputs is on the certain side of the stage's limits (ScPlan.fl_*, built like
+// ScFastParams.lim_*): certainly rejected -- and its `multi` certainly 2 or certainly 1 -- or certainly passed (not for the
+// last stage, whose exact score is the detection's output).  What it cannot decide is queued per CTA and run DENSELY through
+// the reference arithmetic (one queued record per thread), so a warp never executes the 690-instruction exact path for a
+// single lane.  Scores of rejected records are not part of any output (k_finalize), so a certified rejection stores none.
+#define SC_STAGE_Q 384   // per-CTA queue of undecided records (drained 128 at a time)
 template <int HP>
 __global__ void __launch_bounds__(128) k_scan_stage(const ScPlan* __restrict__ plan, int stage, const float4* __restrict__ S,
                                                      const ScGeom* __restrict__ geom_all, const float* __restrict__ w_all,
@@ -1227,60 +1237,133 @@ __global__ void __launch_bounds__(128) k_scan_stage(const ScPlan* __restrict__ p
                                                      const uint32_t* __restrict__ in_count, uint32_t* __restrict__ out_idx,
                                                      uint32_t* __restrict__ out_count, uint32_t cap) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
+    __shared__ uint32_t s_q[SC_STAGE_Q];
+    __shared__ uint32_t s_qn;
     const int n_weak = plan->n_weak[stage], wbase = plan->weak_base[stage], total_weak = plan->total_weak;
     float* sw = reinterpret_cast<float*>(s_dyn);
     double* swb = reinterpret_cast<double*>(s_dyn + (size_t)n_weak * SC_W_PITCH * 4);
     for (int i = threadIdx.x; i < n_weak * SC_W_PITCH; i += blockDim.x) sw[i] = w_all[(size_t)wbase * SC_W_PITCH + i];
     for (int i = threadIdx.x; i < n_weak; i += blockDim.x) swb[i] = wb_all[wbase + i];
+    if (threadIdx.x == 0) s_qn = 0;
     __syncthreads();
     const uint32_t count = min(*in_count, cap);
     const int n_stages = plan->n_stages;
     constexpr int ppitch = SC_ROW_ELEMS(HP);
     const bool force = plan->force_all != 0, last = stage == n_stages - 1;
+    const bool fast = plan->stage_fast != 0 && !force;
     const float theta = plan->theta[stage];
+    const float lim_reject = plan->fl_reject[stage], lim_pass = plan->fl_pass[stage], lim_skip = plan->fl_skip[stage], lim_noskip = plan->fl_noskip[stage];
     const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < count; i0 += stride) {
-        const uint32_t i = i0 + threadIdx.x;
-        bool push = false;
-        uint32_t idx = 0;
-        if (i < count) {
-            idx = in_idx ? in_idx[i] : i;
-            ScRecord r = rec[idx];
-            const int f = r.fs >> 8, si = r.fs & 0xff;
-            const int gy = r.yx >> 16, gx = r.yx & 0xffff;
-            const float4* lo4 = S + (size_t)f * plan->lay.frame4;
-            const float score = stage_score<HP>(reinterpret_cast<const char*>(lo4 + ((gy + plan->sc[si].gy0) * ppitch + SC_COL(gx >> 1))),
-                                                geom_all + ((size_t)(gx & 1) * plan->n_scales + si) * total_weak + wbase, sw, swb, n_weak, HP);
-            if (r.rej < 0) {
-                const bool rejected = score < theta;
-                if (rejected) {
-                    r.rej = stage; r.score = __float_as_uint(score);
-                    if (rejected_skips(score, stage, n_stages)) {
-                        const int word_base = plan->sc[si].word_base, wpr = plan->sc[si].wpr;
-                        atomicOr(&multi_bits[(size_t)f * plan->words_per_frame + word_base + (size_t)gy * wpr + (gx >> 5)], 1u << (gx & 31));
-                    }
-                    rec[idx] = r;
-                } else if (last) {
-                    r.rej = n_stages; r.score = __float_as_uint(score);
-                    rec[idx] = r;
-                }
-                push = !rejected && !last;
-            }
-            if (force) push = false;  // force_all walks the full record array at every stage
-        }
+
+    auto window_base = [&](const ScRecord& r) -> const char* {
+        const int f = r.fs >> 8, si = r.fs & 0xff, gy = r.yx >> 16, gx = r.yx & 0xffff;
+        return reinterpret_cast<const char*>(S + (size_t)f * plan->lay.frame4 + ((gy + plan->sc[si].gy0) * ppitch + SC_COL(gx >> 1)));
+    };
+    auto geom_of = [&](const ScRecord& r) -> const ScGeom* {
+        return geom_all + ((size_t)(r.yx & 1u) * plan->n_scales + (r.fs & 0xff)) * total_weak + wbase;
+    };
+    auto set_multi = [&](const ScRecord& r) {
+        const int f = r.fs >> 8, si = r.fs & 0xff, gy = r.yx >> 16, gx = r.yx & 0xffff;
+        atomicOr(&multi_bits[(size_t)f * plan->words_per_frame + plan->sc[si].word_base + (size_t)gy * plan->sc[si].wpr + (gx >> 5)], 1u << (gx & 31));
+    };
+    auto push_alive = [&](bool push, uint32_t idx) {  // warp-converged
         const uint32_t m = __ballot_sync(0xffffffffu, push);
         if (m) {
             uint32_t slot0 = 0;
             if (lane == 0) slot0 = atomicAdd(out_count, __popc(m));
             slot0 = __shfl_sync(0xffffffffu, slot0, 0);
             if (push) {
-                const uint32_t slot = slot0 + __popc(m & ((1u << lane) - 1u));
+                const uint32_t slot = slot0 + __popc(m & lt);
                 if (slot < cap) out_idx[slot] = idx;
             }
         }
+    };
+    // the reference arithmetic on one record (GentleAdaboost::Predict2, threshold, ObjDetector.cpp:196-201,214); returns "stays alive"
+    auto exact_record = [&](uint32_t idx) -> bool {
+        ScRecord r = rec[idx];
+        const float score = stage_score<HP>(window_base(r), geom_of(r), sw, swb, n_weak, HP);
+        if (r.rej >= 0) return false;  // force_all: an earlier stage already rejected it; later stages are evaluated, not recorded
+        const bool rejected = score < theta;
+        if (rejected) {
+            r.rej = stage; r.score = __float_as_uint(score);
+            if (rejected_skips(score, stage, n_stages)) set_multi(r);
+            rec[idx] = r;
+        } else if (last) {
+            r.rej = n_stages; r.score = __float_as_uint(score);
+            rec[idx] = r;
+        } else if (r.rej != -1) {
+            r.rej = -1;
+            rec[idx] = r;
+        }
+        return !rejected && !last && !force;  // force_all walks the full record array at every stage
+    };
+    auto drain = [&](uint32_t take) {  // block-converged: the last `take` (<= 128) queue entries, one per thread
+        const uint32_t qn = s_qn;
+        const bool active = threadIdx.x < take;
+        uint32_t idx = 0;
+        bool alive = false;
+        if (active) { idx = s_q[qn - take + threadIdx.x]; alive = exact_record(idx); }
+        push_alive(alive, idx);
+        __syncthreads();
+        if (threadIdx.x == 0) s_qn = qn - take;
+        __syncthreads();
+    };
+
+    for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < count; i0 += stride) {  // block-uniform trip count
+        const uint32_t i = i0 + threadIdx.x;
+        bool push = false, undecided = false;
+        uint32_t idx = 0;
+        if (i < count) {
+            idx = in_idx ? in_idx[i] : i;
+            if (!fast) {
+                undecided = true;
+            } else {
+                ScRecord r = rec[idx];
+                if (stage == 0 && r.rej == -2) {          // the stage-0 filter certified the pass
+                    push = true;
+                } else {
+                    const char* base = window_base(r);
+                    const ScGeom* gq = geom_of(r);
+                    float sum = 0.f;
+                    for (int q = 0; q < n_weak; q++) {
+                        ScGeom g;
+                        const uint4* gs = reinterpret_cast<const uint4*>(gq + q);
+                        const uint4 g0 = gs[0], g1 = gs[1], g2 = gs[2];
+                        g.c[0] = g0.x; g.c[1] = g0.y; g.c[2] = g0.z; g.c[3] = g0.w; g.c[4] = g1.x; g.c[5] = g1.y; g.c[6] = g1.z; g.c[7] = g1.w;
+                        g.c[8] = g2.x; g.c[9] = g2.y; g.shape = g2.z; g.pad = 0;
+                        float v[32];
+                        box_sums_p<HP>(base, g, HP, v);
+                        sum = __fadd_rn(sum, fast_tail(v, sw + q * SC_W_PITCH, (float)swb[q]));
+                    }
+                    if (sum < lim_reject) {
+                        if (sum < lim_skip) { r.rej = stage; r.score = 0u; rec[idx] = r; set_multi(r); }
+                        else if (sum >= lim_noskip) { r.rej = stage; r.score = 0u; rec[idx] = r; }
+                        else undecided = true;
+                    } else if (sum >= lim_pass && !last) {
+                        push = true;
+                    } else {
+                        undecided = true;
+                    }
+                }
+            }
+        }
+        push_alive(push, idx);
+        {   // queue what needs the reference arithmetic
+            const uint32_t m = __ballot_sync(0xffffffffu, undecided);
+            uint32_t q0 = 0;
+            if (m && lane == 0) q0 = atomicAdd(&s_qn, __popc(m));
+            q0 = __shfl_sync(0xffffffffu, q0, 0);
+            if (undecided) s_q[q0 + __popc(m & lt)] = idx;   // at most 255 queued before + 128 new <= SC_STAGE_Q
+        }
+        __syncthreads();
+        if (s_qn >= 128) drain(128);   // block-uniform (s_qn is read after the barrier by every thread)
     }
+    __syncthreads();
+    while (s_qn > 0) drain(min(s_qn, 128u));
 }
+
 
 // ---------------------------------------------------------------------------------------------------------
 // Adaptive-stride replay (ObjDetector.cpp:185-186,214-217): one thread per (frame, scale, lattice row)

@@ -115,6 +115,9 @@ struct ScPlan {
     long long windows_per_frame;  // grid windows per frame
     ScLayout lay;
     float theta[SC_PLAN_MAX_STAGES];
+    // certified fast arithmetic of k_scan_stage, per stage, on the float sum of the stage's fast weak outputs (as ScFastParams.lim_*)
+    int stage_fast, pad1[3];
+    float fl_reject[SC_PLAN_MAX_STAGES], fl_pass[SC_PLAN_MAX_STAGES], fl_skip[SC_PLAN_MAX_STAGES], fl_noskip[SC_PLAN_MAX_STAGES];
     int n_weak[SC_PLAN_MAX_STAGES];
     int weak_base[SC_PLAN_MAX_STAGES];
     ScScale sc[SC_PLAN_MAX_SCALES];
@@ -140,8 +143,10 @@ struct ScFastParams {
     // certified decisions on the float sum of the fast weak outputs (see fast_weak() for the error budget):
     //   sum <  lim_reject                  -> the reference's stage score is < theta for certain
     //   sum <  lim_skip / >= lim_noskip    -> the rejected window's `multi` is 2 / 1 for certain
+    //   sum >= lim_pass                    -> the stage score is >= theta for certain (no exact stage 0 needed; +inf when the
+    //                                         cascade has a single stage, whose score is the detection's output)
     // anything else is re-evaluated with the reference's exact arithmetic
-    float lim_reject, lim_skip, lim_noskip, pad1;
+    float lim_reject, lim_skip, lim_noskip, lim_pass;
     float wb[8];                                         // float(w[32] * bias)
     int block_base[SC_PLAN_MAX_SCALES];                  // first stage-0 CTA of every scale inside a frame
     int row_base[SC_PLAN_MAX_SCALES];                    // first lattice row of every scale inside a frame (k_scan_odd)
