@@ -1,11 +1,11 @@
-"""BASELINE configs C3 and C4 on N GPUs of one box (one process per GPU, NCCL over NVLink):
+"""BASELINE configs C4 and C5 on N GPUs of one box (one process per GPU; C3 is bench.py --workload c3):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/run_multi.py
 
-C3: 1024 1080p frames sharded frame f -> rank f mod N (128-frame device-resident batches), detections gathered to every
-    rank and grouped per frame on rank 0 (host groupRectangles).
 C4: ONE 3840x2160 frame, step 1, all stages forced: every rank computes the integral image itself and scans its band of
-    every scale's lattice rows (sc_detect_params.band_index / band_count); same gather.
+    every scale's lattice rows (sc_detect_params.band_index / band_count); the bands' detections are gathered on rank 0 with
+    sc_gather_detections (C-ABI).
+C5: pool evaluation sharded by sample, one all-reduce of the level histograms.
 Times are CUDA-event times on the handle's stream, max over ranks.  One JSON line on rank 0."""
 import json, os, sys, time
 import numpy as np
@@ -13,7 +13,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
 from surfcascade_b200 import capi, synth
-from surfcascade_b200 import dist as scdist
 
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 json_fd = os.dup(1); os.dup2(2, 1)
@@ -40,41 +39,15 @@ def barrier():
     torch.cuda.synchronize()
 
 
-out = {"n_gpus": world}
-# ---- C3 ------------------------------------------------------------------------------------------------------
-n_total = int(os.environ.get("C3_FRAMES", "1024"))
-mine = scdist.shard_frames(n_total, rank, world)
-base = [synth.frame(1080, 1920, 100 + i) for i in range(8)]
-B = 128
+out = {"n_gpus": world, "C3": "see bench.py --workload c3 (1024-frame batch, host frames in, grouped objects gathered on rank 0 through sc_gather_detections)"}
 cap = 1 << 18
-d_out = torch.zeros(cap * 24, dtype=torch.uint8, device=dev); d_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
-batches = [mine[i:i + B] for i in range(0, len(mine), B)]
-dev_batch = torch.from_numpy(np.stack([base[f % 8] for f in (batches[0] if batches else [0])])).to(dev)   # frame f is synthetic frame f mod 8
-h.detect_device(dev_batch.data_ptr(), dev_batch.shape[0], 1920, 1080, d_out.data_ptr(), cap, d_cnt.data_ptr(), capi.params()); h.sync()  # warm-up
-barrier()
+d_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-e0.record(stream)
-gathered = []
-for b in batches:
-    # every batch of this rank holds the same synthetic content pattern (f mod 8 repeats with period 8 | world)
-    h.detect_device(dev_batch.data_ptr(), len(b), 1920, 1080, d_out.data_ptr(), cap, d_cnt.data_ptr(), capi.params())
-    if world > 1:
-        with torch.cuda.stream(stream):
-            gathered.append(scdist.gather_records(d_out[: (1 << 16) * 24], d_cnt))
-e1.record(stream); h.sync(); barrier()
-ms = max_over_ranks(e0.elapsed_time(e1))
-t0 = time.perf_counter()
-n_groups = 0
-if rank == 0:   # host grouping of rank 0's own share (every rank's records are there after the gather; one share timed)
-    n = int(d_cnt.item())
-    rec = np.frombuffer(d_out[: n * 24].cpu().numpy().tobytes(), capi.DETECTION_DTYPE)
-    for f in np.unique(rec["frame"]):
-        r = rec[rec["frame"] == f]
-        gr, _ = capi.group_rectangles(np.stack([r["x"], r["y"], r["l"], r["l"]], 1), r["score"])
-        n_groups += len(gr)
-group_s = time.perf_counter() - t0
-out["C3"] = {"frames": n_total, "ms": round(ms, 2), "frames_per_s": round(n_total / ms * 1e3, 1), "frames_per_rank": len(mine),
-             "host_grouping_ms_last_batch_rank0": round(group_s * 1e3, 2), "objects_last_batch_rank0": n_groups}
+if world > 1:
+    ids = [capi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    h.comm_init(rank, world, ids[0])     # the path's own exchange (C-ABI): sc_gather_detections
+gbuf = np.zeros((1 << 20) if rank == 0 else 0, capi.DETECTION_DTYPE)
 # ---- C4 ------------------------------------------------------------------------------------------------------
 img = torch.from_numpy(synth.frame(2160, 3840, 300, n_objects=12)[None]).to(dev)
 cap4 = 1 << 20
@@ -84,11 +57,13 @@ h.detect_device(img.data_ptr(), 1, 3840, 2160, d_out4.data_ptr(), cap4, d_cnt.da
 barrier()
 e0.record(stream)
 reps = 3
+n_gathered = 0
 for _ in range(reps):
     h.detect_device(img.data_ptr(), 1, 3840, 2160, d_out4.data_ptr(), cap4, d_cnt.data_ptr(), prm)
     if world > 1:
-        with torch.cuda.stream(stream):
-            scdist.gather_records(d_out4[: (1 << 16) * 24], d_cnt)
+        h.sync()
+        got, per = h.gather_detections(None, frame_mul=1, frame_add=0, root=0, device_ptr=d_out4.data_ptr(), n_device=int(d_cnt.item()), complete=True, out=gbuf)
+        n_gathered = sum(per)
 e1.record(stream); h.sync(); barrier()
 ms4 = max_over_ranks(e0.elapsed_time(e1)) / reps
 c = h.last_counters(1)[0]
@@ -96,11 +71,11 @@ tot = torch.tensor([c.grid, int(d_cnt.item())], dtype=torch.int64, device=dev)
 if world > 1:
     dist.all_reduce(tot)
 out["C4"] = {"ms_per_frame": round(ms4, 2), "windows": int(tot[0].item()), "windows_per_s": round(int(tot[0].item()) / ms4 * 1e3 / 1e9, 3), "unit": "G windows/s",
-             "raw_detections": int(tot[1].item()), "split": f"{world} row bands per scale, integral replicated"}
+             "raw_detections": int(tot[1].item()), "gathered_on_rank0": n_gathered, "split": f"{world} row bands per scale, integral replicated"}
 # ---- C5 ------------------------------------------------------------------------------------------------------
 # candidate scoring of one boosting round: X [100k][608][32] sharded by sample; every rank streams its shard into the
 # 608 x 2 x 21 level histograms, ONE all-reduce (NCCL) of 102 KB, AUC of every candidate on every rank
-del d_out4, img, dev_batch
+del d_out4, img
 torch.cuda.empty_cache()
 N5, P5 = 100000, 608
 n_loc = len(range(rank, N5, world))
@@ -128,4 +103,5 @@ out["C5"] = {"ms": round(ms5, 3), "GB_streamed": round(N5 * P5 * 128 / 1e9, 2), 
 if rank == 0:
     os.write(json_fd, (json.dumps(out) + "\n").encode())
 if world > 1:
+    h.comm_destroy()
     dist.destroy_process_group()
