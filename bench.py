@@ -230,12 +230,14 @@ def run_ours(args):
     no_exchange = os.environ.get("SC_BENCH_NO_EXCHANGE") == "1"  # scaling diagnosis only: the line says so
     h = capi.Handle(local)
     h.load_model(wl["model"], 40)
+    hx = None  # the exchange has its own handle (a handle is thread-compatible, not thread-safe) and its own host thread
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)  # plumbing: barriers, the max over ranks, the NCCL id
         ids = [capi.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
-        h.comm_init(rank, world, ids[0])  # the path's own exchange: sc_gather_detections over NCCL (C-ABI)
+        hx = capi.Handle(local)
+        hx.comm_init(rank, world, ids[0])  # the path's own exchange: sc_gather_detections (C-ABI)
     prm = capi.params()
     prm_g = capi.params(group_threshold=2, group_eps=0.2)
     stream = torch.cuda.ExternalStream(h.stream, device=dev)
@@ -252,45 +254,71 @@ def run_ours(args):
         if not c3:
             dev_sets.append(ht.to(dev))
     cap = 1 << 16 if not c3 else 1 << 18
-    d_out = [torch.zeros(cap * 24, dtype=torch.uint8, device=dev) for _ in range(2)]
-    d_cnt = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(2)]
-    cnt_host = torch.zeros(2, dtype=torch.int32).pin_memory()
-    evs = [torch.cuda.Event(), torch.cuda.Event()]
+    NB = 4  # output buffers in flight: the exchange thread may lag the enqueueing thread by up to NB - 1 steps
+    d_out = [torch.zeros(cap * 24, dtype=torch.uint8, device=dev) for _ in range(NB)]
+    d_cnt = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(NB)]
+    cnt_host = torch.zeros(NB, dtype=torch.int32).pin_memory()
+    evs = [torch.cuda.Event() for _ in range(NB)]
     gbuf = np.zeros(cap * world if rank == 0 else 0, capi.DETECTION_DTYPE)
     xstat = {"calls": 0, "records": 0, "local": 0}
-    pending = [None]
 
-    def exchange(k):
-        """Step k's records (complete: its event has passed) to rank 0 with their real count, on the library's own stream."""
-        t0 = time.perf_counter()
-        with torch.cuda.stream(side):
-            side.wait_event(evs[k])
-            cnt_host[k:k + 1].copy_(d_cnt[k], non_blocking=True)
-        side.synchronize()
-        t1 = time.perf_counter()
-        n = min(int(cnt_host[k]), cap)
-        fm, fa = (1, 0) if os.environ.get("SC_BENCH_NO_RENUMBER") else (world, rank)
-        got, per = h.gather_detections(None, frame_mul=fm, frame_add=fa, root=0, device_ptr=d_out[k].data_ptr(), n_device=n, complete=True, out=gbuf)
-        xstat["calls"] += 1; xstat["records"] += sum(per); xstat["local"] += n
-        xstat["wait_s"] = xstat.get("wait_s", 0.0) + (t1 - t0); xstat["gather_s"] = xstat.get("gather_s", 0.0) + (time.perf_counter() - t1)
+    # The exchange runs on its own host thread (and its own handle / stream): sc_gather_detections is host-synchronous -- root
+    # waits for every rank's header -- and with it on the enqueueing thread every rank's host was tied to the slowest rank at
+    # every step with one step of lookahead; on 8 GPUs and 16 shared host cores that halved the throughput (14.6 k frames/s).
+    import queue
+    import threading
+    jobs = queue.Queue()
+    free = [threading.Semaphore(1) for _ in range(NB)]
+    xerr = []
+
+    def exchange_worker():
+        torch.cuda.set_device(local)
+        while True:
+            job = jobs.get()
+            if job is None:
+                return
+            try:
+                if job[0] == "dev":
+                    k = job[1]
+                    with torch.cuda.stream(side):
+                        side.wait_event(evs[k])
+                        cnt_host[k:k + 1].copy_(d_cnt[k], non_blocking=True)
+                    side.synchronize()
+                    n = min(int(cnt_host[k]), cap)
+                    got, per = hx.gather_detections(None, frame_mul=world, frame_add=rank, root=0, device_ptr=d_out[k].data_ptr(), n_device=n, complete=True, out=gbuf)
+                    xstat["calls"] += 1; xstat["records"] += sum(per); xstat["local"] += n
+                    free[k].release()
+                else:
+                    got, per = hx.gather_detections(job[1], frame_mul=world, frame_add=rank, root=0, out=gbuf)
+                    xstat["host_records"] = xstat.get("host_records", 0) + sum(per)
+            except Exception as e:  # noqa: BLE001
+                xerr.append(e)
+                if job[0] == "dev":
+                    free[job[1]].release()
+            finally:
+                jobs.task_done()
+
+    worker = None
+    if world > 1 and not no_exchange:
+        worker = threading.Thread(target=exchange_worker, daemon=True)
+        worker.start()
 
     def step_device(s):
-        k = s & 1
+        k = s % NB
         x = dev_sets[s % n_sets]
-        t0 = time.perf_counter()
+        if worker:
+            free[k].acquire()   # buffer k's previous records have been exchanged
         h.detect_device(x.data_ptr(), B, W, H, d_out[k].data_ptr(), cap, d_cnt[k].data_ptr(), prm)
-        xstat["enqueue_s"] = xstat.get("enqueue_s", 0.0) + (time.perf_counter() - t0)
-        if world > 1 and not no_exchange:
-            # the one exchange step of the path (SURVEY.md 8e): step s - 1's records travel while step s computes
+        if worker:
+            # the one exchange step of the path: this step's records travel while the next steps compute
             evs[k].record(stream)
-            if pending[0] is not None:
-                exchange(pending[0])
-            pending[0] = k
+            jobs.put(("dev", k))
 
     def flush_exchange():
-        if world > 1 and pending[0] is not None:
-            exchange(pending[0])
-            pending[0] = None
+        if worker:
+            jobs.join()
+            if xerr:
+                raise xerr[0]
 
     def barrier():
         if world > 1:
@@ -342,13 +370,13 @@ def run_ours(args):
                 out = out.copy()
                 out["frame"] += (s % n_sub) * B   # frame index inside this rank's share of the batch
                 acc.append(out)
-            if world > 1 and not no_exchange and (s + 1) % n_sub == 0:
-                mine = np.concatenate(acc) if c3 else out
-                got, per = h.gather_detections(mine, frame_mul=world, frame_add=rank, root=0, out=gbuf)
-                n_got += sum(per)
+            if worker and (s + 1) % n_sub == 0:
+                jobs.put(("host", np.concatenate(acc) if c3 else out.copy()))
                 acc = []
             pend = nxt
+        flush_exchange()
         torch.cuda.synchronize()
+        n_got = xstat.pop("host_records", 0)
         return time.perf_counter() - t0, n_out, n_got
 
     clocks = ClockSampler(local)
@@ -365,14 +393,10 @@ def run_ours(args):
         if rank == 0:
             clocks.start()
         launches0 = h.launch_count
-        xstat.update(calls=0, records=0, local=0, wait_s=0.0, gather_s=0.0, enqueue_s=0.0)
+        xstat.update(calls=0, records=0, local=0)
         ms = timed(step_device, args.steps)
         launches = h.launch_count - launches0
         xrec = dict(xstat)
-        if os.environ.get("SC_BENCH_TRACE"):
-            sys.stderr.flush()
-            print(f"[bench rank {rank}] per step: enqueue {1e3 * xrec['enqueue_s'] / args.steps:.3f} ms, wait {1e3 * xrec['wait_s'] / max(xrec['calls'], 1):.3f} ms, "
-                  f"gather {1e3 * xrec['gather_s'] / max(xrec['calls'], 1):.3f} ms, device {ms / args.steps:.3f} ms", file=sys.stderr)
         clk = clocks.stop() if rank == 0 else {}
         fps = world * B * args.steps / (ms / 1e3)
         # per-kernel split of one more timed pass (same steps) with event spans inside the library
@@ -473,8 +497,7 @@ def run_ours(args):
             if world > 1:
                 line["exchange"]["device_resident_records_to_rank0_per_step"] = xrec["records"] / max(xrec["calls"], 1)
                 line["exchange"]["device_resident_bytes_per_rank_per_step"] = 24 * xrec["local"] / max(xrec["calls"], 1)
-                line["exchange"]["host_ms_per_step"] = {"waiting_for_the_step_to_finish": 1e3 * xrec.get("wait_s", 0.0) / max(xrec["calls"], 1),
-                                                        "inside_sc_gather_detections": 1e3 * xrec.get("gather_s", 0.0) / max(xrec["calls"], 1)}
+                line["exchange"]["host_thread"] = "sc_gather_detections runs on its own host thread and handle; up to 3 steps of lookahead for the enqueueing thread"
             # algorithmic gather bytes of the scan per frame: 32 B x (4 per prefilter + 9|10 corners per weak eval)
             ev_ms, ev_n = stats.get("k_scan_stage0", (0.0, 0))       # even lattice columns, one launch per 8-frame scan group
             odd_ms, _ = stats.get("k_scan_stage0_odd", (0.0, 0))      # reachable odd columns
@@ -540,7 +563,11 @@ def run_ours(args):
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
-        h.comm_destroy()
+        if worker:
+            jobs.put(None)
+            worker.join()
+        hx.comm_destroy()
+        hx.close()
         dist.destroy_process_group()
 
 
