@@ -82,7 +82,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):
+        """Start of the region whose samples count (the sampler itself is started earlier: nvidia-smi takes a while to come up)."""
+        self.t_mark = time.time()
 
     def stop(self) -> dict:
         if not self.proc:
@@ -94,7 +98,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t_mark = getattr(self, "t_mark", 0.0)
+        inside = [ln for (t, ln) in self.lines if t >= t_mark]
+        if not inside:  # a region shorter than the sampling period: the samples closest to it
+            inside = [ln for (_, ln) in self.lines[-2:]]
+        for ln in inside:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -271,6 +279,8 @@ def run_ours(args):
     free = [threading.Semaphore(1) for _ in range(NB)]
     xerr = []
 
+    blk_ev = torch.cuda.Event(blocking=True)
+
     def exchange_worker():
         torch.cuda.set_device(local)
         while True:
@@ -283,7 +293,8 @@ def run_ours(args):
                     with torch.cuda.stream(side):
                         side.wait_event(evs[k])
                         cnt_host[k:k + 1].copy_(d_cnt[k], non_blocking=True)
-                    side.synchronize()
+                        blk_ev.record(side)
+                    blk_ev.synchronize()   # blocking-sync event: this thread sleeps, it does not spin on a core the enqueueing threads need
                     n = min(int(cnt_host[k]), cap)
                     got, per = hx.gather_detections(None, frame_mul=world, frame_add=rank, root=0, device_ptr=d_out[k].data_ptr(), n_device=n, complete=True, out=gbuf)
                     xstat["calls"] += 1; xstat["records"] += sum(per); xstat["local"] += n
@@ -384,6 +395,8 @@ def run_ours(args):
     stats = {}
     launches = 0
     ms = ms_prof = None
+    if rank == 0:
+        clocks.start()   # before the warm-up steps; only samples taken after mark() are reported
     if not c3:
         for s in range(args.warmup):
             step_device(s)
@@ -391,7 +404,7 @@ def run_ours(args):
         h.sync()
         cnts = h.last_counters(B)
         if rank == 0:
-            clocks.start()
+            clocks.mark()
         launches0 = h.launch_count
         xstat.update(calls=0, records=0, local=0)
         ms = timed(step_device, args.steps)
@@ -410,10 +423,10 @@ def run_ours(args):
     # The steps go through sc_detect_submit / sc_detect_collect with two batches in flight, as a streaming caller would:
     # every step still uploads its own frames from pinned host memory and downloads its own detections and counters.
     if c3:
-        if rank == 0:
-            clocks.start()
         for _ in range(max(args.warmup, 1)):
             pipelined_pass(prm_g)            # untimed: allocates the tickets' buffers, warms the clocks
+        if rank == 0:
+            clocks.mark()
         launches0 = h.launch_count
         h.transfer_bytes(reset=True)
         e2e_grouped_s, n_obj, n_got_g = pipelined_pass(prm_g)
