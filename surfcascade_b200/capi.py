@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsurfcascade_b200.so")
+LIB_PATH = os.environ.get("SC_LIB") or os.path.join(HERE, "libsurfcascade_b200.so")  # SC_LIB: another build of the library (tuning variants)
 SC_MAX_STAGES = 16
 
 SC_OK, SC_ERR_INVALID, SC_ERR_CUDA, SC_ERR_STATE, SC_ERR_CAPACITY, SC_ERR_IO, SC_ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6

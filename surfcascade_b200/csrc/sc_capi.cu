@@ -447,7 +447,10 @@ int run_integral(sc_handle* h, const uint8_t* d_img, int n, int slot0, bool unde
         // per-frame cell-sum bounds that certify the compact plane for this batch's stage-0 filter (k_cell_bounds)
         uint32_t* cert = h->d_cert.as<uint32_t>() + (size_t)slot0 * n_items;
         SC_CUDA(h, cudaMemsetAsync(cert, 0, (size_t)n * n_items * 4, st));
-        const int chunks = 4;
+#ifndef SC_CERT_CHUNKS
+#define SC_CERT_CHUNKS 4   // CTAs per (frame, cell edge): 4 -> 0.0098, 16 -> see DESIGN.md 6b
+#endif
+        const int chunks = SC_CERT_CHUNKS;
         KernelSpan ks(h, K_CERT);
         sck::k_cell_bounds<<<dim3(n_items * chunks, n), 256, 0, st>>>(S, p.lay, p.W, p.H, h->d_cert_items.as<int>(), n_items, chunks, cert);
     }

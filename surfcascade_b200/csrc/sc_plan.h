@@ -35,7 +35,9 @@
 
 // k_scan_odd work unit: a run of up to SC_ODD_UNIT reachable odd-column windows of one lattice row (one warp per unit:
 // prefilter in four 32-window passes, the survivors compacted into a dense list for the fast filter).
+#ifndef SC_ODD_UNIT
 #define SC_ODD_UNIT 128
+#endif
 
 // Integral strips: one warp walks one 32-column strip down the frame, SC_WALK_RB rows per prefetch block.
 #define SC_STRIP 32
