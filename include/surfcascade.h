@@ -94,6 +94,11 @@ int sc_create(int device, sc_handle** out);
 void sc_destroy(sc_handle* h);
 const char* sc_last_error(const sc_handle* h);
 const char* sc_version(void);
+/* Checked build only (surfcascade_b200/build.py --checked -> libsurfcascade_b200_checked.so, -DSC_CHECKED): every gather from an
+ * integral-image plane is range-tested on the device before it is issued; returns the number of violations counted so far
+ * (process-wide: use ONE handle per process with this build), -1 in the normal build.  Stands in for compute-sanitizer's
+ * memcheck on the gather addresses, which is closed on the B200 pool. */
+int sc_checked_violations(int reset);
 
 /* ---- model ---------------------------------------------------------------------------------------- */
 /* Replaces ObjDetector.cpp:108-130 (pool + Model::Load + fitted patches), given an already flattened cascade. */

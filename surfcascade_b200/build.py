@@ -8,6 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libsurfcascade_b200.so")
 CLI = os.path.join(HERE, "ObjDetector")
+LIB_CHECKED = os.path.join(HERE, "libsurfcascade_b200_checked.so")   # -DSC_CHECKED: range-tested gathers (tests/test_gpu_checked_build.py)
 CLASS_TEST = os.path.join(HERE, "class_detect")   # tests/cpp/class_detect.cpp: the reference's detect branch over the kept classes
 CU = ["csrc/sc_capi.cu"]
 CPP = ["host/sc_host.cpp", "host/cfgfile.cpp", "host/classes.cpp", "host/Model.cpp", "host/DenseSURFFeatureExtractor.cpp"]
@@ -32,6 +33,11 @@ def stale() -> bool:
     return any(os.path.getmtime(os.path.join(HERE, f)) > t for f in CU + CPP + HEADERS + ["build.py"])
 
 
+def build_checked() -> str:
+    subprocess.check_call([_nvcc()] + NVCC_FLAGS + ["-DSC_CHECKED", "-shared", "-o", LIB_CHECKED] + [os.path.join(HERE, f) for f in CU + CPP])
+    return LIB_CHECKED
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB
@@ -48,4 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--checked" in sys.argv:
+        print(build_checked())
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

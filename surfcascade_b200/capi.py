@@ -46,7 +46,7 @@ EXPORTS = ["sc_create", "sc_destroy", "sc_last_error", "sc_version", "sc_set_cas
            "sc_set_profiling", "sc_kernel_stats", "sc_model_flatten", "sc_model_resave", "sc_pool_eval", "sc_pool_hist_device",
            "sc_pool_auc_device", "sc_probe_gather", "sc_probe_stream", "sc_stage0_fast_check", "sc_detect_submit", "sc_detect_collect", "sc_extract_pool_features", "sc_extract_pool_features_device", "sc_mine_negatives", "sc_integral_scan_layout",
            "sc_integral_compact", "sc_box_sums_compact", "sc_cell_bounds",
-           "sc_comm_unique_id", "sc_comm_init", "sc_gather_detections", "sc_comm_destroy", "sc_transfer_bytes"]
+           "sc_comm_unique_id", "sc_comm_init", "sc_gather_detections", "sc_comm_destroy", "sc_transfer_bytes", "sc_checked_violations"]
 
 _lib = None
 

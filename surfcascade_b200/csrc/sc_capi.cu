@@ -56,6 +56,14 @@ bool same_params(const sc_detect_params& a, const sc_detect_params& b) {
 
 }  // namespace
 
+#ifdef SC_CHECKED
+// checked build: address ranges the range-tested gathers accept: [0,1) the scan's integral buffer, [2,3) the parity hooks' one
+static void checked_set_range(int which, const void* p, size_t bytes) {
+    unsigned long long r[2] = {(unsigned long long)p, (unsigned long long)p + bytes};
+    cudaMemcpyToSymbol(sck::sc_chk_range, r, sizeof(r), (size_t)which * 16);
+}
+#endif
+
 struct sc_comm_state;   // NCCL exchange (sc_comm.inc)
 
 struct sc_handle {
@@ -398,6 +406,9 @@ int ensure_group_buffers(sc_handle* h, int want_frames, bool own_images) {
     if (own_images) SC_CUDA(h, h->d_img.ensure(align256((size_t)gi * p.W * p.H)));
     SC_CUDA(h, h->d_carry.ensure(align256((size_t)gi * p.H * p.n_strips * 32)));
     SC_CUDA(h, h->d_S.ensure((size_t)gi * p.lay.frame4 * 16));
+#ifdef SC_CHECKED
+    checked_set_range(0, h->d_S.p, h->d_S.cap);
+#endif
     SC_CUDA(h, h->d_cert.ensure(std::max<size_t>((size_t)gi * h->cert_ce.size(), 1) * 4));
     // a second lane only when more than one scan group can be in flight and the worst-case record arrays stay modest
     h->n_lanes = want_lanes;
@@ -500,7 +511,8 @@ int run_group(sc_handle* h, sc_handle::Lane& L, int s0, int g, int frame0, sc_de
     uint32_t* small = L.d_small.as<uint32_t>();
     SC_CUDA(h, cudaMemsetAsync(small, 0, (SM_DET) * 4, st));  // rec + stage counts; det count is the caller's
     float4* S = h->d_S.as<float4>() + (size_t)s0 * p.lay.frame4;
-    if (p.n_scales > 0 && p.n_stages > 0) {
+    // (a row band of a tiny frame can be empty: band_count larger than a scale's lattice rows -- nothing to launch then)
+    if (p.n_scales > 0 && p.n_stages > 0 && p.blocks_per_frame > 0 && p.rows_per_frame > 0) {
         const ScGeom* geom = h->d_geom.as<ScGeom>();
         const float* w = h->d_w.as<float>();
         const double* wb = h->d_wb.as<double>();
@@ -697,7 +709,19 @@ void sort_detections(sc_detection* d, size_t n) {
 
 extern "C" {
 
+#ifdef SC_CHECKED
+const char* sc_version(void) { return "surfcascade-b200 0.3 (sm_100a, checked build)"; }
+int sc_checked_violations(int reset) {
+    unsigned int v = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&v, sck::sc_chk_bad, 4);
+    if (reset) { const unsigned int z = 0; cudaMemcpyToSymbol(sck::sc_chk_bad, &z, 4); }
+    return (int)v;
+}
+#else
 const char* sc_version(void) { return "surfcascade-b200 0.3 (sm_100a)"; }
+int sc_checked_violations(int) { return -1; }   // not a checked build
+#endif
 
 int sc_create(int device, sc_handle** out) {
     if (!out) return SC_ERR_INVALID;
@@ -858,6 +882,9 @@ int sc_integral(sc_handle* h, const uint8_t* gray, int W, int H, int stride, flo
     SC_CUDA(h, h->d_hook_img.ensure(align256((size_t)W * H)));
     SC_CUDA(h, h->d_hook_carry.ensure(align256((size_t)H * n_strips * 32)));
     SC_CUDA(h, h->d_hook_S.ensure((size_t)L.frame4 * 16));
+#ifdef SC_CHECKED
+    checked_set_range(1, h->d_hook_S.p, h->d_hook_S.cap);
+#endif
     SC_CUDA(h, cudaMemcpy2DAsync(h->d_hook_img.p, W, gray, stride, W, H, cudaMemcpyHostToDevice, h->stream));
     sck::k_strip_carry<<<(H + 3) / 4, 128, 0, h->stream>>>(h->d_hook_img.as<uint8_t>(), W, H, n_strips, 1, h->d_hook_carry.as<int>());
 #if SC_WALK_TILED

@@ -32,6 +32,26 @@ namespace sck {
 #endif
 
 // ---------------------------------------------------------------------------------------------------------
+// Checked build (-DSC_CHECKED, surfcascade_b200/build.py --checked): every gather from an integral-image plane -- the corner
+// fetches of the descriptors, the prefilter, the compact plane, the far-corner probes -- is tested against the address ranges of
+// the integral buffers before it is issued; a violation is counted (sc_checked_violations) and the load replaced by zeros.
+// compute-sanitizer is closed on this pool; this build is what tests/test_gpu_checked_build.py runs in its place.
+// ---------------------------------------------------------------------------------------------------------
+#ifdef SC_CHECKED
+__device__ unsigned long long sc_chk_range[4];   // [lo0, hi0, lo1, hi1): the scan's integral buffer and the hooks' one
+__device__ unsigned int sc_chk_bad;
+__device__ __forceinline__ bool sc_chk(const void* p, unsigned bytes) {
+    const unsigned long long a = (unsigned long long)p;
+    const bool ok = (a >= sc_chk_range[0] && a + bytes <= sc_chk_range[1]) || (a >= sc_chk_range[2] && a + bytes <= sc_chk_range[3]);
+    if (!ok) atomicAdd(&sc_chk_bad, 1u);
+    return ok;
+}
+#define SC_LDG4(T, ptr) (sc_chk((ptr), 16u) ? __ldg(ptr) : T())
+#else
+#define SC_LDG4(T, ptr) __ldg(ptr)
+#endif
+
+// ---------------------------------------------------------------------------------------------------------
 // Gradient channels (T2bFilter, DenseSURFFeatureExtractor.cpp:199-349) as four packed pairs:
 // low 16 bits = negative part (even channel), high 16 bits = positive part (odd channel).
 // ---------------------------------------------------------------------------------------------------------
@@ -327,7 +347,7 @@ __device__ __forceinline__ Px load_px(const char* __restrict__ base, uint32_t of
 #ifdef SC_EXP_HALF  // timing experiment only (wrong results): 16 bytes per corner
     const float4 lo = __ldg(p), hi = lo;
 #else
-    const float4 lo = __ldg(p), hi = __ldg(p + (HP ? HP : hp));
+    const float4 lo = SC_LDG4(float4, p), hi = SC_LDG4(float4, p + (HP ? HP : hp));
 #endif
     Px r;
     r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w; r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
@@ -436,8 +456,8 @@ __device__ __forceinline__ float stage_score(const char* __restrict__ base, cons
 // DenseSURFFeatureExtractor::sum (:351-358) and the compare at ObjDetector.cpp:188; pf = byte offsets of the corners
 // (0,0) (l,0) (0,l) (l,l) from the window's low-half element
 __device__ __forceinline__ float window_sum(const char* __restrict__ base, const uint32_t* pf) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(base + pf[0])), b = __ldg(reinterpret_cast<const float4*>(base + pf[1]));
-    const float4 c = __ldg(reinterpret_cast<const float4*>(base + pf[2])), d = __ldg(reinterpret_cast<const float4*>(base + pf[3]));
+    const float4 a = SC_LDG4(float4, reinterpret_cast<const float4*>(base + pf[0])), b = SC_LDG4(float4, reinterpret_cast<const float4*>(base + pf[1]));
+    const float4 c = SC_LDG4(float4, reinterpret_cast<const float4*>(base + pf[2])), d = SC_LDG4(float4, reinterpret_cast<const float4*>(base + pf[3]));
     const float s0 = __fsub_rn(__fadd_rn(a.x, d.x), __fadd_rn(b.x, c.x));
     const float s1 = __fsub_rn(__fadd_rn(a.y, d.y), __fadd_rn(b.y, c.y));
     const float s2 = __fsub_rn(__fadd_rn(a.z, d.z), __fadd_rn(b.z, c.z));
@@ -545,7 +565,7 @@ __device__ __forceinline__ void cell_sum_c(const uint4& A, const uint4& B, const
 
 template <int HP>
 __device__ __forceinline__ uint4 load_n(const char* __restrict__ base, uint32_t off, int hp) {
-    return __ldg(reinterpret_cast<const uint4*>(base + off) + SC_NOFF(HP ? HP : hp));
+    return SC_LDG4(uint4, reinterpret_cast<const uint4*>(base + off) + SC_NOFF(HP ? HP : hp));
 }
 
 // box_sums() from the compact plane (same values as box_sums() / box_sums_p() under the two certified conditions)
@@ -575,7 +595,7 @@ __device__ __forceinline__ void box_sums_c(const char* __restrict__ base, const 
 // are monotone in x and y), i.e. the reference's float box sums ARE the integer box sums the compact plane yields.
 template <int HP>
 __device__ __forceinline__ bool compact_far_ok(const float4* __restrict__ far) {
-    const float4 lo = __ldg(far), hi = __ldg(far + HP);
+    const float4 lo = SC_LDG4(float4, far), hi = SC_LDG4(float4, far + HP);
     const float m = fmaxf(fmaxf(fmaxf(lo.x, lo.y), fmaxf(lo.z, lo.w)), fmaxf(fmaxf(hi.x, hi.y), fmaxf(hi.z, hi.w)));
     return m <= 8388608.f;
 }
