@@ -1592,45 +1592,106 @@ int sc_mine_negatives(sc_handle* h, const uint8_t* const* frames, const int32_t*
     int have = 0, used = nframes;
     std::vector<sc_detection> wins;
     std::vector<sc_rect> rects;
-    for (int i = 0; i < nframes && have < need; i++) {
+    DevBuf d_pool, d_wins, d_X;
+    constexpr int MINE_BATCH = 16;   // equally sized consecutive images scanned per sc_detect call
+    int i = 0;
+    while (i < nframes && have < need) {
         const int W = Ws[i], H = Hs[i];
-        if (!frames[i] || W < tmpl || H < tmpl) continue;  // :137-138
-        wins.clear();
+        if (!frames[i] || W < tmpl || H < tmpl) { i++; continue; }  // :137-138
         if (first) {
+            // the first fill takes every window of the ladder: no scan; per image IntegralImage + the descriptors of host-built rects
+            wins.clear();
             std::vector<int> sides;
             sc_host::scale_ladder(W, H, tmpl, 1.1, &sides);
             for (int l : sides)
                 for (int y = 0; y <= H - l; y += 10)
                     for (int x = 0; x + l <= W; x += 10) wins.push_back(sc_detection{0, x, y, l, 0.0});
-        } else {
-            size_t cap = 1024, n = 0;
-            for (;;) {
-                wins.resize(cap);
-                const uint8_t* one[1] = {frames[i]};
-                const int rc = sc_detect(h, one, 1, W, H, strides[i], &prm, wins.data(), cap, &n, nullptr);
-                if (rc == SC_ERR_CAPACITY) { cap = n + 16; continue; }
+            const int take = (int)std::min<size_t>(wins.size(), (size_t)(need - have));
+            if (take > 0) {
+                int rc = sc_integral(h, frames[i], W, H, strides[i], nullptr);
                 if (rc != SC_OK) return rc;
-                break;
+                rects.resize((size_t)take * P);
+                for (int k = 0; k < take; k++)
+                    for (int p = 0; p < P; p++) {
+                        sc_rect r = sc_host::project_patch(tmpl, wins[k].l, pool[p]);  // ProjectPatches(win, patches, new_patches), :158
+                        r.x += wins[k].x; r.y += wins[k].y;
+                        rects[(size_t)k * P + p] = r;
+                    }
+                rc = sc_features(h, rects.data(), take * P, X + (size_t)have * P * 32);
+                if (rc != SC_OK) return rc;
+                have += take;
             }
-            wins.resize(n);  // sorted by (l, y, x): the reference's loop order (:146-156)
+            if (have == need) used = i + 1;
+            i++;
+            continue;
         }
-        const int take = (int)std::min<size_t>(wins.size(), (size_t)(need - have));
-        if (take > 0) {
-            int rc = sc_integral(h, frames[i], W, H, strides[i], nullptr);
+        // a batch: the run of consecutive usable images of this size (the reference's order is kept: images are consumed in
+        // order and the fill may stop inside the batch -- the images behind that point were scanned for nothing, never used)
+        int nb = 1;
+        while (nb < MINE_BATCH && i + nb < nframes && frames[i + nb] && Ws[i + nb] == W && Hs[i + nb] == H && strides[i + nb] == strides[i]) nb++;
+        size_t cap = 4096, n = 0;
+        for (;;) {
+            wins.resize(cap);
+            const int rc = sc_detect(h, frames + i, nb, W, H, strides[i], &prm, wins.data(), cap, &n, nullptr);
+            if (rc == SC_ERR_CAPACITY) { cap = n + 16; continue; }
             if (rc != SC_OK) return rc;
-            rects.resize((size_t)take * P);
-            for (int k = 0; k < take; k++)
-                for (int p = 0; p < P; p++) {
-                    sc_rect r = sc_host::project_patch(tmpl, wins[k].l, pool[p]);  // ProjectPatches(win, patches, new_patches), :158
-                    r.x += wins[k].x; r.y += wins[k].y;
-                    rects[(size_t)k * P + p] = r;
+            break;
+        }
+        wins.resize(n);  // sorted by (frame, l, y, x): per image the reference's loop order (:146-156)
+        // the scan's integral images of the batch are still in d_S (one super-group) unless the frames are so large that the batch was split
+        const bool resident = nb <= h->int_frames && h->have_plan && h->plan.W == W && h->plan.H == H;
+        std::vector<sck::ScMineWin> mw;
+        size_t k0 = 0;
+        for (int f = 0; f < nb && have + (int)mw.size() < need; f++) {
+            size_t k1 = k0;
+            while (k1 < n && wins[k1].frame == f) k1++;
+            const int take = (int)std::min<size_t>(k1 - k0, (size_t)(need - have - (int)mw.size()));
+            for (int k = 0; k < take; k++) mw.push_back(sck::ScMineWin{f, wins[k0 + k].x, wins[k0 + k].y, wins[k0 + k].l});
+            if (have + (int)mw.size() == need) used = i + f + 1;
+            k0 = k1;
+        }
+        if (!mw.empty()) {
+            SC_CUDA(h, cudaSetDevice(h->device));
+            if (resident) {
+                const size_t nw = mw.size();
+                SC_CUDA(h, d_pool.ensure((size_t)P * sizeof(sc_rect)));
+                SC_CUDA(h, d_wins.ensure(nw * sizeof(sck::ScMineWin)));
+                SC_CUDA(h, d_X.ensure(nw * P * 32 * sizeof(float)));
+                SC_CUDA(h, cudaMemcpyAsync(d_pool.p, pool.data(), (size_t)P * sizeof(sc_rect), cudaMemcpyHostToDevice, h->stream));
+                SC_CUDA(h, cudaMemcpyAsync(d_wins.p, mw.data(), nw * sizeof(sck::ScMineWin), cudaMemcpyHostToDevice, h->stream));
+                const long long threads = (long long)nw * P;
+                sck::k_mine_descriptors<<<(unsigned)((threads + 127) / 128), 128, 0, h->stream>>>(h->d_S.as<float4>(), h->plan.lay, d_wins.as<sck::ScMineWin>(), (int)nw,
+                                                                                           d_pool.as<int4>(), P, tmpl, d_X.as<float>());
+                h->launches++;
+                SC_CUDA(h, cudaGetLastError());
+                SC_CUDA(h, cudaMemcpyAsync(X + (size_t)have * P * 32, d_X.p, nw * P * 32 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+                SC_CUDA(h, cudaStreamSynchronize(h->stream));
+            } else {
+                // very large frames: per image, through the hook layout
+                size_t done = 0;
+                while (done < mw.size()) {
+                    const int f = mw[done].slot;
+                    size_t e2 = done;
+                    while (e2 < mw.size() && mw[e2].slot == f) e2++;
+                    int rc = sc_integral(h, frames[i + f], W, H, strides[i], nullptr);
+                    if (rc != SC_OK) return rc;
+                    rects.resize((e2 - done) * P);
+                    for (size_t k = done; k < e2; k++)
+                        for (int p = 0; p < P; p++) {
+                            sc_rect r = sc_host::project_patch(tmpl, mw[k].l, pool[p]);
+                            r.x += mw[k].x; r.y += mw[k].y;
+                            rects[(k - done) * P + p] = r;
+                        }
+                    rc = sc_features(h, rects.data(), (int)((e2 - done) * P), X + ((size_t)have + done) * P * 32);
+                    if (rc != SC_OK) return rc;
+                    done = e2;
                 }
-            rc = sc_features(h, rects.data(), take * P, X + (size_t)have * P * 32);
-            if (rc != SC_OK) return rc;
-            have += take;
+            }
+            have += (int)mw.size();
         }
-        if (have == need) used = i + 1;
+        i += nb;
     }
+    d_pool.release(); d_wins.release(); d_X.release();
     *filled = have;
     *frames_used = used;
     return SC_OK;

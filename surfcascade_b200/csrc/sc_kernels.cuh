@@ -1753,6 +1753,48 @@ __global__ void k_box_sums_compact(const float4* __restrict__ S, const ScLayout 
     for (int k = 0; k < 32; k++) out[(size_t)i * 32 + k] = v[k];
 }
 
+// Hard-negative mining (next row N2): the descriptors of ALL pool patches projected into each accepted window
+// (FillNegSamples, DenseSURFFeatureExtractor.cpp:157-176), read from the integral images the mining scan itself produced
+// (its layout L, frame slots of the scan batch) -- no second IntegralImage per image, no host-built rect list.
+// One thread per (window, pool patch).  ProjectPatches' float arithmetic (:486-508) is restated on the device operation
+// for operation: scale = fl(l / tmpl), x' = (int)fl(x * scale), the short side (int)fl(side * scale), the long side its multiple.
+struct ScMineWin { int32_t slot, x, y, l; };
+__global__ void __launch_bounds__(128) k_mine_descriptors(const float4* __restrict__ S, const ScLayout L, const ScMineWin* __restrict__ wins, int n_wins,
+                                                           const int4* __restrict__ pool, int P, int tmpl, float* __restrict__ X) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n_wins * P) return;
+    const int k = (int)(t / P), pi = (int)(t - (long long)k * P);
+    const ScMineWin w = wins[k];
+    const int4 pt = pool[pi];  // x, y, w, h on the template
+    const float scale = __fdiv_rn((float)w.l, (float)tmpl);
+    int rx = (int)__fmul_rn((float)pt.x, scale) + w.x, ry = (int)__fmul_rn((float)pt.y, scale) + w.y, rw, rh;
+    if (pt.z >= pt.w) { rh = (int)__fmul_rn((float)pt.w, scale); rw = rh * (pt.z / pt.w); }
+    else { rw = (int)__fmul_rn((float)pt.z, scale); rh = rw * (pt.w / pt.z); }
+    ScGeom g;
+    g.pad = 0;
+    if (rw == rh) {
+        const int ce = rw / 2;
+        g.shape = 0;
+        for (int b = 0; b < 3; b++)
+            for (int a = 0; a < 3; a++) g.c[3 * b + a] = (uint32_t)(16 * sc_layout_index(L, rx + a * ce, ry + b * ce));
+        g.c[9] = 0;
+    } else {
+        const int ce = min(rw, rh);
+        const bool wide = rw > rh;
+        g.shape = 1;
+        for (int c = 0; c < 5; c++) {
+            const int x0 = rx + (wide ? c * ce : 0), y0 = ry + (wide ? 0 : c * ce);
+            g.c[c] = (uint32_t)(16 * sc_layout_index(L, x0, y0));
+            g.c[5 + c] = (uint32_t)(16 * sc_layout_index(L, x0 + (wide ? 0 : ce), y0 + (wide ? ce : 0)));
+        }
+    }
+    float v[32];
+    descriptor<0>(reinterpret_cast<const char*>(S + (size_t)w.slot * L.frame4), g, L.hp, v);
+    float4* o = reinterpret_cast<float4*>(X + ((size_t)k * P + pi) * 32);
+#pragma unroll
+    for (int c = 0; c < 8; c++) o[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+
 // Training-side descriptor extraction (next row N3): ExtractNextImageFeatures -> IntegralImage + ExtractFeatures over the
 // template pool (DenseSURFFeatureExtractor.cpp:65-120) for a batch of template-sized samples.  One CTA per sample, nothing
 // but the sample and its descriptors touches HBM: channels, exact integer row prefixes and the reference's sequential

@@ -12,9 +12,14 @@ from surfcascade_b200 import capi, synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("first,need", [(True, 700), (False, 60), (False, 100000)])
-def test_mine_negatives_matches_fill_neg_samples(gpu_handle, oracle_cascade, first, need):
-    frames = [synth.negative_frame(20, 120, 160), np.zeros((30, 30), np.uint8), synth.frame(150, 200, 21), synth.negative_frame(22, 240, 320)]
+@pytest.mark.parametrize("first,need,layout", [(True, 700, "mixed"), (False, 60, "mixed"), (False, 100000, "mixed"), (False, 300, "runs"), (False, 1200, "runs"), (False, 492, "runs"), (False, 100000, "runs"),
+                                               (True, 900, "runs")])
+def test_mine_negatives_matches_fill_neg_samples(gpu_handle, oracle_cascade, first, need, layout):
+    if layout == "mixed":   # every image its own size: one-image batches
+        frames = [synth.negative_frame(20, 120, 160), np.zeros((30, 30), np.uint8), synth.frame(150, 200, 21), synth.negative_frame(22, 240, 320)]
+    else:                   # runs of equally sized images: scanned as batches, the fill stops inside a batch (need = 300, 1200) or exactly at an image boundary (492)
+        frames = [synth.negative_frame(30, 120, 160), synth.frame(120, 160, 31), synth.negative_frame(32, 120, 160), np.zeros((30, 30), np.uint8),
+                  synth.frame(150, 200, 33), synth.frame(150, 200, 34), synth.negative_frame(35, 120, 160)]
     if not first:
         # the trained cascade rejects almost everything on these frames: cut it to its first stage so that samples exist
         import dataclasses
