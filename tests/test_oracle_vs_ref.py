@@ -148,3 +148,24 @@ def test_fill_neg_samples_restatement(tmp_path, oracle_cascade, first, totals):
         assert dones[call] == (len(want) == need)
         start += used
     assert len(got[0]) > 0
+
+
+def test_paper_shaped_cascade_reference_vs_restatement():
+    """tests/golden/model_paper8.cfg (8 stages, 2 / 3 / 5 / 8 / 12 / 16 / 24 / 32 weak classifiers) through the reference's
+    own Model::Load and detect loop against the restatement: window set, scores and counters.  (The GPU path is checked against the
+    restatement on this model in tests/test_gpu_big_pins.py.)"""
+    import os
+    from oracle import modelcfg
+    model = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "model_paper8.cfg")
+    c = modelcfg.load(model)
+    assert c.n_stages == 8 and c.n_weak.tolist() == [2, 3, 5, 8, 12, 16, 24, 32]
+    bc = O.BoundCascade(c)
+    for img in (synth.frame(240, 320, 1), synth.frame(150, 400, 2)):
+        d = O.detect(O.integral(img), bc, O.params(base=40))
+        r = R.detect([img], model, base=40, nthreads=1, group=False)
+        assert len(d.x) == len(r.x)
+        order = np.lexsort((r.x, r.y, r.l))
+        assert np.array_equal(d.x, r.x[order]) and np.array_equal(d.y, r.y[order]) and np.array_equal(d.l, r.l[order])
+        assert np.array_equal(d.score, r.score[order])
+        assert r.counters[0, :3].tolist() == [d.counters[O.C_VISITED], d.counters[O.C_PREFILTER], d.counters[O.C_WEAK]]
+        assert d.counters[O.C_REACH0 + 3] > 0   # deep stages are entered
