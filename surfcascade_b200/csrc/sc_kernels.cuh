@@ -732,12 +732,32 @@ __device__ __forceinline__ float filter_weak(const ScFastParams& fp, int si, int
     box_sums_p<HP>(base, g, HP, v);
     return fast_tail(v, fp.w[q], fp.wb[q]);
 }
+// L1 prefetch of the NEXT weak classifier's corners of the same window (no register cost: the lines arrive while this weak
+// classifier's tail runs).  Timing variant, off unless -DSC_PREFETCH_NEXT.
+template <int HP, int MODE>
+__device__ __forceinline__ void prefetch_weak(const ScFastParams& fp, int si, int q, const char* __restrict__ base, bool compact) {
+#ifdef SC_PREFETCH_NEXT
+    const int n = fp.geom[si][q][10] == 0u ? 9 : 10;
+    const bool c = MODE == SC_MODE_COMPACT || (MODE == SC_MODE_MIXED && compact);
+#pragma unroll
+    for (int k = 0; k < 10; k++) {
+        if (k < n) {
+            const char* a = base + fp.geom[si][q][k] + (c ? 16 * SC_NOFF(HP) : 0);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+            if (!c) asm volatile("prefetch.global.L1 [%0];" ::"l"(a + 16 * SC_HI(HP)));
+        }
+    }
+#endif
+}
 template <int HP, int NW, int MODE>
 __device__ __forceinline__ float filter_sum(const ScFastParams& fp, int si, const char* __restrict__ base, uint32_t cmask) {
     float sum = 0.f;
     if (NW > 0) {
 #pragma unroll
-        for (int q = 0; q < SC_EXP_NWEAK(NW); q++) sum = __fadd_rn(sum, filter_weak<HP, MODE>(fp, si, q, base, (cmask >> q) & 1u));
+        for (int q = 0; q < SC_EXP_NWEAK(NW); q++) {
+            if (q + 1 < NW) prefetch_weak<HP, MODE>(fp, si, q + 1, base, (cmask >> (q + 1)) & 1u);
+            sum = __fadd_rn(sum, filter_weak<HP, MODE>(fp, si, q, base, (cmask >> q) & 1u));
+        }
     } else {
 #pragma unroll 1
         for (int q = 0; q < SC_EXP_NWEAK(fp.n_weak); q++) sum = __fadd_rn(sum, filter_weak<HP, MODE>(fp, si, q, base, (cmask >> q) & 1u));
